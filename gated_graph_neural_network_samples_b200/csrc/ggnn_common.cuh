@@ -1,0 +1,72 @@
+// Shared device-side definitions of the GGNN propagation engine (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ggnn {
+
+constexpr int MAX_LAYERS = 16;
+constexpr int MAX_RES = 4;     // residual inputs per layer
+constexpr int KC = 16;         // K rows of a weight operand per shared-memory stage (FFMA path)
+
+enum { CELL_GRU = 0, CELL_RNN = 1 };
+enum { ACT_TANH = 0, ACT_RELU = 1 };
+enum { GATHER_SPARSE = 0, GATHER_DENSE = 1 };
+
+struct LayerDev {
+    const float* edge_w;   // [T][D][D]
+    const float* edge_b;   // [T][D] or nullptr
+    const float* gate_k;   // [(Din+D)][2D]
+    const float* gate_b;   // [2D]
+    const float* cand_k;   // [(Din+D)][D]   (RNN: the only kernel)
+    const float* cand_b;   // [D]
+    int steps;
+    int nres;
+    int res[MAX_RES];      // indices into node_states_per_layer
+};
+
+// Per-(layer,step) activations kept for the backward pass; each [V][D] (device), index = global step.
+struct SaveDev {
+    float* h_in;   // state entering the step
+    float* agg;    // aggregated incoming messages after bias/mean (the cell's message input)
+    float* r;      // reset gate   (GRU)
+    float* u;      // update gate  (GRU)
+    float* c;      // candidate    (GRU) -- for RNN the new state itself is enough
+};
+
+struct FwdParams {
+    int V, D, T, L;
+    int use_bias, use_avg, cell, act;
+    int gather_mode;          // GATHER_SPARSE / GATHER_DENSE
+    int dense_v;              // vertices per graph (dense)
+    int save;                 // keep activations for backward
+    const int* tile_start;    // [ntiles+1] first node of each tile
+    const unsigned* tile_mask;// [ntiles] bit t set iff some node of the tile has an incoming type-t message
+    const int* row_ptr;       // [V*T+1] CSR rows keyed target*T+type (stable in message order)
+    const int* csr_src;       // [M] source node of each CSR slot
+    const float* dense_adj;   // [b][T][v][v]
+    const float* indeg;       // [V][T] num_incoming_edges_per_type
+    const float* denom;       // [V] fp32(sum_t indeg) + 1e-7f
+    const float* state[MAX_LAYERS + 1];   // node_states_per_layer: [0]=h0 ... [L]=result (read side)
+    float* state_w[MAX_LAYERS + 1];       // write side ([0] unused)
+    LayerDev layer[MAX_LAYERS];
+    SaveDev save_buf;         // base pointers; step s lives at +s*V*D
+    int step_base[MAX_LAYERS];// global step index of (layer,0)
+    // global (one step per launch) mode
+    int g_layer, g_step;
+    const float* g_in;
+    float* g_out;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float activate(float v, int act) { return act == ACT_TANH ? tanhf(v) : fmaxf(v, 0.0f); }
+
+}  // namespace ggnn

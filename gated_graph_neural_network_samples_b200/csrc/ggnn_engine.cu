@@ -1,0 +1,662 @@
+// Host side of the GGNN propagation engine + the C ABI declared in include/ggnn_b200.h.
+//
+// Mirrors the two ChemModel hooks of the reference for this path:
+//   ggnn_create / ggnn_set_weights            <- prepare_specific_graph_model        (sparse:63-115, dense:68-91)
+//   ggnn_set_graph_* + ggnn_forward           <- compute_final_node_representations  (sparse:117-218, dense:93-117)
+// Host work per batch: validate indices, stable counting sort of the type-major message list by
+// (target, type) -> CSR, find where the batch can be cut between connected components, pack tiles.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ggnn_b200.h"
+#include "ggnn_common.cuh"
+#include "ggnn_fwd_ffma.cuh"
+
+using namespace ggnn;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct HostPinned {
+    void* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct ggnn_engine {
+    // model shape
+    int D = 0, T = 0, L = 0;
+    int steps[MAX_LAYERS] = {0};
+    int nres[MAX_LAYERS] = {0};
+    int res[MAX_LAYERS][MAX_RES] = {{0}};
+    int step_base[MAX_LAYERS] = {0};
+    int total_steps = 0;
+    int use_bias = 0, use_avg = 0, cell = 0, act = 0, precision = 0, device = 0;
+    int num_sms = 148;
+    size_t max_smem = 0;
+    bool weights_set = false;
+    ggnn_layer_weights w[MAX_LAYERS];
+
+    // batch
+    bool graph_set = false;
+    int gather_mode = GATHER_SPARSE;
+    int V = 0, dense_v = 0;
+    int64_t M = 0;
+    // plan
+    int variant = 0;  // 0: RG=8,CS=1 (64-row tiles)   1: RG=4,CS=2 (32-row tiles)
+    int nb1 = 0;
+    bool local = false;
+    int ntiles = 0;
+    int max_span = 0;
+    std::string plan_text;
+
+    // device memory
+    DevBuf graph_buf;   // packed: row_ptr | csr_src | csr_msg | indeg | denom | tile_start | tile_mask | (dense adj)
+    HostPinned graph_stage;
+    size_t off_row_ptr = 0, off_src = 0, off_msg = 0, off_indeg = 0, off_denom = 0, off_tiles = 0, off_mask = 0, off_adj = 0;
+    DevBuf state_buf;   // intermediate layer states (L-1) + 2 ping-pong step buffers, each [V][D]
+    DevBuf save_bufs;   // 5 x total_steps x [V][D]
+    DevBuf io_buf;      // h0 / h_out staging for ggnn_forward_host
+    DevBuf bwd_buf;     // backward scratch
+    const float* last_h0 = nullptr;
+    float* last_out = nullptr;
+    bool save = false;
+    bool saved_valid = false;
+    int last_launches = 0;
+    std::string err;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CU_TRY(e, call)                                                                           \
+    do {                                                                                          \
+        cudaError_t _st = (call);                                                                 \
+        if (_st != cudaSuccess) return (e)->fail(GGNN_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_st)); \
+    } while (0)
+
+static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* grads, int32_t num_layers,
+                              float* d_h0, ggnn_stream_t stream);
+
+// ------------------------------------------------------------------------------------------ kernel table
+namespace {
+
+typedef void (*FwdKernel)(const FwdParams);
+
+template <int RG, int CS, int NB1, bool LOCAL>
+FwdKernel fwd_kernel_ptr() {
+    constexpr int NB2 = (2 * NB1 > 8) ? 8 : 2 * NB1;
+    constexpr int MINB = (CS == 2 && NB1 <= 2) ? 2 : 1;
+    return ggnn_fwd_ffma_kernel<RG, CS, NB1, NB2, LOCAL, MINB>;
+}
+
+FwdKernel pick_fwd_kernel(int variant, int nb1, bool local) {
+    if (variant == 0) {
+        if (nb1 == 1) return local ? fwd_kernel_ptr<8, 1, 1, true>() : fwd_kernel_ptr<8, 1, 1, false>();
+        if (nb1 == 2) return local ? fwd_kernel_ptr<8, 1, 2, true>() : fwd_kernel_ptr<8, 1, 2, false>();
+        if (nb1 == 4) return local ? fwd_kernel_ptr<8, 1, 4, true>() : fwd_kernel_ptr<8, 1, 4, false>();
+    } else {
+        if (nb1 == 1) return local ? fwd_kernel_ptr<4, 2, 1, true>() : fwd_kernel_ptr<4, 2, 1, false>();
+        if (nb1 == 2) return local ? fwd_kernel_ptr<4, 2, 2, true>() : fwd_kernel_ptr<4, 2, 2, false>();
+        if (nb1 == 4) return local ? fwd_kernel_ptr<4, 2, 4, true>() : fwd_kernel_ptr<4, 2, 4, false>();
+    }
+    return nullptr;
+}
+
+int variant_mt(int variant) { return variant == 0 ? 64 : 32; }
+int variant_cs(int variant) { return variant == 0 ? 1 : 2; }
+
+int pick_nb1(int variant, int D) {
+    const int per = 32 * variant_cs(variant);
+    int nb = (D + per - 1) / per;
+    if (nb <= 1) return 1;
+    if (nb <= 2) return 2;
+    if (nb <= 4) return 4;
+    return 0;
+}
+
+size_t fwd_smem_bytes(int variant, int nb1, int D, int T) {
+    const int MT = variant_mt(variant), CS = variant_cs(variant);
+    const int nb2 = std::min(8, 2 * nb1);
+    const int pw = 32 * nb2 * CS;
+    return sizeof(float) * ((size_t)4 * MT * D + (size_t)2 * KC * pw + (size_t)2 * MT * KC + (size_t)T * D);
+}
+
+// Decide tile size / mode, then pack tiles greedily between `cuts` (sorted node indices where the batch
+// may be split, cuts.front()==0, cuts.back()==V).
+int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& tile_start) {
+    const int V = e->V, D = e->D;
+    int max_span = 0;
+    for (size_t i = 1; i < cuts.size(); ++i) max_span = std::max(max_span, cuts[i] - cuts[i - 1]);
+    e->max_span = max_span;
+    const bool a_ok = pick_nb1(0, D) > 0 && fwd_smem_bytes(0, pick_nb1(0, D), D, e->T) <= e->max_smem;
+    const bool b_ok = pick_nb1(1, D) > 0 && fwd_smem_bytes(1, pick_nb1(1, D), D, e->T) <= e->max_smem;
+    if (!a_ok && !b_ok) return e->fail(GGNN_EUNSUPPORTED, "hidden_size=%d does not fit any fp32 tile variant", D);
+    const char* force = getenv("GGNN_FFMA_VARIANT");
+    int variant;
+    bool local;
+    const bool a_local = a_ok && max_span <= 64, b_local = b_ok && max_span <= 32;
+    if (force && (force[0] == '0' || force[0] == '1') && ((force[0] == '0') ? a_ok : b_ok)) {
+        variant = force[0] - '0';
+        local = variant == 0 ? a_local : b_local;
+    } else if (b_local && (!a_local || (long)V <= (long)32 * e->num_sms * 2)) {
+        variant = 1; local = true;
+    } else if (a_local) {
+        variant = 0; local = true;
+    } else {
+        variant = a_ok ? 0 : 1; local = false;
+    }
+    const char* force_global = getenv("GGNN_FORCE_GLOBAL");
+    if (force_global && force_global[0] == '1') local = false;
+    e->variant = variant;
+    e->local = local;
+    e->nb1 = pick_nb1(variant, D);
+    const int MT = variant_mt(variant);
+    tile_start.clear();
+    tile_start.push_back(0);
+    if (local) {
+        int cur = 0;
+        for (size_t i = 1; i < cuts.size(); ++i) {
+            if (cuts[i] - cur > MT) {           // adding this component would overflow: close the tile before it
+                tile_start.push_back(cuts[i - 1]);
+                cur = cuts[i - 1];
+            }
+        }
+        if (V > cur) tile_start.push_back(V);
+    } else {
+        for (int r = MT; r < V; r += MT) tile_start.push_back(r);
+        if (V > 0) tile_start.push_back(V);
+    }
+    if (V == 0) tile_start.assign(1, 0);
+    e->ntiles = (int)tile_start.size() - 1;
+    char buf[256];
+    snprintf(buf, sizeof buf, "fp32-ffma %s tiles=%d rows/tile<=%d warps=8 colsplit=%d nb1=%d max_component=%d smem=%zuB",
+             local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)", e->ntiles, MT,
+             variant_cs(variant), e->nb1, max_span, fwd_smem_bytes(variant, e->nb1, D, e->T));
+    e->plan_text = buf;
+    return GGNN_OK;
+}
+
+}  // namespace
+
+static int ggnn_backward_impl(ggnn_engine* e, const float*, const ggnn_layer_grads*, int32_t, float*, ggnn_stream_t) {
+    return e->fail(GGNN_EUNSUPPORTED, "ggnn_backward is not built in this revision");
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* ggnn_last_error(const ggnn_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
+    auto bad = [&](const char* msg) { g_create_error = msg; return (int)GGNN_EINVAL; };
+    if (!cfg || !out) return bad("null argument");
+    *out = nullptr;
+    if (cfg->hidden_size <= 0 || cfg->hidden_size % 4 != 0) return bad("hidden_size must be a positive multiple of 4");
+    if (cfg->hidden_size > 256) { g_create_error = "hidden_size > 256 is not supported by this build"; return GGNN_EUNSUPPORTED; }
+    if (cfg->num_edge_types <= 0 || cfg->num_edge_types > 32) return bad("num_edge_types must be in 1..32");
+    if (cfg->num_layers <= 0 || cfg->num_layers > MAX_LAYERS) return bad("num_layers must be in 1..16");
+    if (!cfg->layer_timesteps) return bad("layer_timesteps is null");
+    if (cfg->cell != GGNN_CELL_GRU && cfg->cell != GGNN_CELL_RNN) return bad("Unknown RNN cell type");              // sparse:112
+    if (cfg->activation != GGNN_ACT_TANH && cfg->activation != GGNN_ACT_RELU) return bad("Unknown activation function type");  // sparse:81
+    if (cfg->precision != GGNN_PREC_FP32) { g_create_error = "only GGNN_PREC_FP32 is built in this revision"; return GGNN_EUNSUPPORTED; }
+    ggnn_engine* e = new ggnn_engine();
+    e->D = cfg->hidden_size; e->T = cfg->num_edge_types; e->L = cfg->num_layers;
+    e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
+    e->cell = cfg->cell; e->act = cfg->activation; e->precision = cfg->precision; e->device = cfg->device;
+    int total = 0;
+    for (int l = 0; l < e->L; ++l) {
+        if (cfg->layer_timesteps[l] < 0) { delete e; return bad("negative layer_timesteps entry"); }
+        e->steps[l] = cfg->layer_timesteps[l];
+        e->step_base[l] = total;
+        total += e->steps[l];
+        int nr = 0;
+        if (cfg->residual_offsets && cfg->residual_layers) {
+            nr = cfg->residual_offsets[l + 1] - cfg->residual_offsets[l];
+            if (nr < 0 || nr > MAX_RES) { delete e; return bad("a layer has more than 4 residual inputs"); }
+            for (int i = 0; i < nr; ++i) {
+                int r = cfg->residual_layers[cfg->residual_offsets[l] + i];
+                // node_states_per_layer has l+1 entries when layer l is built (sparse:144: IndexError otherwise)
+                if (r < 0 || r > l) { delete e; return bad("residual connection refers to a layer that does not exist yet"); }
+                e->res[l][i] = r;
+            }
+        }
+        e->nres[l] = nr;
+    }
+    e->total_steps = total;
+    cudaError_t st = cudaSetDevice(e->device);
+    cudaDeviceProp prop;
+    if (st == cudaSuccess) st = cudaGetDeviceProperties(&prop, e->device);
+    if (st != cudaSuccess) {
+        g_create_error = std::string("CUDA device unavailable: ") + cudaGetErrorString(st);
+        delete e;
+        return GGNN_ECUDA;
+    }
+    e->num_sms = prop.multiProcessorCount;
+    e->max_smem = prop.sharedMemPerBlockOptin;
+    memset(e->w, 0, sizeof e->w);
+    *out = e;
+    return GGNN_OK;
+}
+
+int ggnn_destroy(ggnn_engine* e) {
+    if (!e) return GGNN_OK;
+    cudaSetDevice(e->device);
+    e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
+    e->graph_stage.release();
+    delete e;
+    return GGNN_OK;
+}
+
+int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t num_layers) {
+    if (!e) return GGNN_EINVAL;
+    if (!layers || num_layers != e->L) return e->fail(GGNN_EINVAL, "expected %d layers of weights, got %d", e->L, num_layers);
+    for (int l = 0; l < e->L; ++l) {
+        const ggnn_layer_weights& w = layers[l];
+        if (!w.edge_weights || !w.cand_kernel || !w.cand_bias) return e->fail(GGNN_EINVAL, "layer %d: null edge_weights/cand_kernel/cand_bias", l);
+        if (e->use_bias && !w.edge_biases) return e->fail(GGNN_EINVAL, "layer %d: use_edge_bias set but edge_biases is null", l);
+        if (e->cell == CELL_GRU && (!w.gate_kernel || !w.gate_bias)) return e->fail(GGNN_EINVAL, "layer %d: GRU needs gate_kernel/gate_bias", l);
+        const void* ps[6] = {w.edge_weights, w.edge_biases, w.gate_kernel, w.gate_bias, w.cand_kernel, w.cand_bias};
+        for (const void* q : ps)
+            if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: weight pointers must be 16-byte aligned", l);
+        e->w[l] = w;
+    }
+    e->weights_set = true;
+    return GGNN_OK;
+}
+
+static int upload_graph(ggnn_engine* e, size_t bytes, cudaStream_t st) {
+    CU_TRY(e, e->graph_buf.reserve(bytes));
+    CU_TRY(e, cudaMemcpyAsync(e->graph_buf.ptr, e->graph_stage.ptr, bytes, cudaMemcpyHostToDevice, st));
+    return GGNN_OK;
+}
+
+static int reserve_states(ggnn_engine* e) {
+    const size_t vd = (size_t)std::max(e->V, 1) * e->D * sizeof(float);
+    CU_TRY(e, e->state_buf.reserve(vd * (size_t)(e->L + 1)));
+    if (e->save) CU_TRY(e, e->save_bufs.reserve(vd * 5 * (size_t)std::max(e->total_steps, 1)));
+    return GGNN_OK;
+}
+
+int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
+                          const float* indeg, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    e->graph_set = false; e->saved_valid = false;
+    if (V < 0 || !adj || !num_edges || (!indeg && V > 0)) return e->fail(GGNN_EINVAL, "null/negative argument");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int T = e->T;
+    int64_t M = 0;
+    for (int t = 0; t < T; ++t) {
+        if (num_edges[t] < 0 || (num_edges[t] > 0 && !adj[t])) return e->fail(GGNN_EINVAL, "adjacency list %d is null/negative", t);
+        M += num_edges[t];
+    }
+    if (M > 0x7fffffff || (int64_t)V * T + 1 > 0x7fffffff) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
+    e->V = V; e->M = M; e->gather_mode = GATHER_SPARSE; e->dense_v = 0;
+
+    // ---- pass 1: validate, count per (target,type), mark which node boundaries are spanned by an edge
+    std::vector<int> counts((size_t)V * T + 1, 0);
+    std::vector<int> diff((size_t)V + 2, 0);
+    for (int t = 0; t < T; ++t) {
+        const int32_t* a = adj[t];
+        for (int i = 0; i < num_edges[t]; ++i) {
+            const int s = a[2 * i], d = a[2 * i + 1];
+            if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
+                return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
+            ++counts[(size_t)d * T + t + 1];
+            const int lo = std::min(s, d), hi = std::max(s, d);
+            if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
+        }
+    }
+    std::vector<int> cuts;
+    cuts.push_back(0);
+    {
+        int cover = 0;
+        for (int i = 1; i < V; ++i) {
+            cover += diff[i];
+            if (cover == 0) cuts.push_back(i);
+        }
+        if (V > 0) cuts.push_back(V);
+    }
+    std::vector<int> tile_start;
+    int rc = build_plan(e, cuts, tile_start);
+    if (rc) return rc;
+    const int ntiles = e->ntiles;
+
+    // ---- layout of the packed upload
+    size_t off = 0;
+    e->off_row_ptr = off; off = align_up(off + sizeof(int) * ((size_t)V * T + 1), 16);
+    e->off_src = off;     off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
+    e->off_msg = off;     off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
+    e->off_indeg = off;   off = align_up(off + sizeof(float) * (size_t)std::max(V, 1) * T, 16);
+    e->off_denom = off;   off = align_up(off + sizeof(float) * (size_t)std::max(V, 1), 16);
+    e->off_tiles = off;   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
+    e->off_mask = off;    off = align_up(off + sizeof(unsigned) * (size_t)std::max(ntiles, 1), 16);
+    e->off_adj = off;
+    CU_TRY(e, e->graph_stage.reserve(off));
+    char* base = (char*)e->graph_stage.ptr;
+    int* row_ptr = (int*)(base + e->off_row_ptr);
+    int* csr_src = (int*)(base + e->off_src);
+    int* csr_msg = (int*)(base + e->off_msg);
+    float* h_indeg = (float*)(base + e->off_indeg);
+    float* h_denom = (float*)(base + e->off_denom);
+    int* h_tiles = (int*)(base + e->off_tiles);
+    unsigned* h_mask = (unsigned*)(base + e->off_mask);
+
+    // ---- pass 2: exclusive scan + stable fill (iteration in message order keeps the reference's order per row)
+    row_ptr[0] = 0;
+    for (size_t k = 1; k <= (size_t)V * T; ++k) row_ptr[k] = row_ptr[k - 1] + counts[k];
+    {
+        std::vector<int>& pos = counts;  // reuse as write cursors
+        for (size_t k = 0; k < (size_t)V * T; ++k) pos[k] = row_ptr[k];
+        int m = 0;
+        for (int t = 0; t < T; ++t) {
+            const int32_t* a = adj[t];
+            for (int i = 0; i < num_edges[t]; ++i, ++m) {
+                const int slot = pos[(size_t)a[2 * i + 1] * T + t]++;
+                csr_src[slot] = a[2 * i];
+                csr_msg[slot] = m;
+            }
+        }
+    }
+    for (int v = 0; v < V; ++v) {
+        float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
+        for (int t = 0; t < T; ++t) { h_indeg[(size_t)v * T + t] = indeg[(size_t)v * T + t]; s += indeg[(size_t)v * T + t]; }
+        h_denom[v] = s + 1e-7f;
+    }
+    for (int i = 0; i <= ntiles; ++i) h_tiles[i] = tile_start[i];
+    for (int i = 0; i < ntiles; ++i) {
+        unsigned mask = 0;
+        for (int v = tile_start[i]; v < tile_start[i + 1]; ++v)
+            for (int t = 0; t < T; ++t)
+                if (row_ptr[(size_t)v * T + t + 1] > row_ptr[(size_t)v * T + t]) mask |= 1u << t;
+        h_mask[i] = mask;
+    }
+    rc = upload_graph(e, off, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = reserve_states(e);
+    if (rc) return rc;
+    e->graph_set = true;
+    return GGNN_OK;
+}
+
+int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    e->graph_set = false; e->saved_valid = false;
+    if (b < 0 || v <= 0 || (!adjm && b > 0)) return e->fail(GGNN_EINVAL, "null/negative argument");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int T = e->T;
+    if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
+    const int V = b * v;
+    e->V = V; e->M = 0; e->gather_mode = GATHER_DENSE; e->dense_v = v;
+    std::vector<int> cuts;
+    for (int g = 0; g <= b; ++g) cuts.push_back(g * v);
+    if (b == 0) cuts.assign(1, 0);
+    std::vector<int> tile_start;
+    int rc = build_plan(e, cuts, tile_start);
+    if (rc) return rc;
+    const int ntiles = e->ntiles;
+    const size_t adj_elems = (size_t)b * T * v * v;
+    size_t off = 0;
+    e->off_row_ptr = off; off = align_up(off + 16, 16);
+    e->off_src = off; e->off_msg = off;
+    e->off_indeg = off;   off = align_up(off + sizeof(float) * (size_t)std::max(V, 1) * T, 16);
+    e->off_denom = off;   off = align_up(off + sizeof(float) * (size_t)std::max(V, 1), 16);
+    e->off_tiles = off;   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
+    e->off_mask = off;    off = align_up(off + sizeof(unsigned) * (size_t)std::max(ntiles, 1), 16);
+    e->off_adj = off;     off = align_up(off + sizeof(float) * std::max<size_t>(adj_elems, 1), 16);
+    CU_TRY(e, e->graph_stage.reserve(off));
+    char* base = (char*)e->graph_stage.ptr;
+    float* h_indeg = (float*)(base + e->off_indeg);
+    float* h_denom = (float*)(base + e->off_denom);
+    int* h_tiles = (int*)(base + e->off_tiles);
+    unsigned* h_mask = (unsigned*)(base + e->off_mask);
+    float* h_adj = (float*)(base + e->off_adj);
+    if (adj_elems) memcpy(h_adj, adjm, sizeof(float) * adj_elems);
+    // in-degree per type = row sums of A_t (the dense model adds the bias to every source row before A.m,
+    // dense:107-112, which equals bias * row-sum after the adjacency product)
+    for (int g = 0; g < b; ++g)
+        for (int i = 0; i < v; ++i) {
+            float tot = 0.0f;
+            for (int t = 0; t < T; ++t) {
+                const float* row = adjm + (((size_t)g * T + t) * v + i) * v;
+                float s = 0.0f;
+                for (int j = 0; j < v; ++j) s += row[j];
+                h_indeg[((size_t)g * v + i) * T + t] = s;
+                tot += s;
+            }
+            h_denom[(size_t)g * v + i] = tot + 1e-7f;
+        }
+    for (int i = 0; i <= ntiles; ++i) h_tiles[i] = tile_start[i];
+    for (int i = 0; i < ntiles; ++i) {
+        unsigned mask = 0;
+        for (int n = tile_start[i]; n < tile_start[i + 1]; ++n)
+            for (int t = 0; t < T; ++t)
+                if (h_indeg[(size_t)n * T + t] != 0.0f) mask |= 1u << t;
+        // rows with cancelling +/- entries would have zero row-sum but non-zero entries: scan those rows fully
+        if (mask != ((T >= 32) ? 0xffffffffu : ((1u << T) - 1u))) {
+            for (int n = tile_start[i]; n < tile_start[i + 1]; ++n) {
+                const int g = n / v, ii = n % v;
+                for (int t = 0; t < T; ++t) {
+                    if (mask & (1u << t)) continue;
+                    const float* row = adjm + (((size_t)g * T + t) * v + ii) * v;
+                    for (int j = 0; j < v; ++j) if (row[j] != 0.0f) { mask |= 1u << t; break; }
+                }
+            }
+        }
+        h_mask[i] = mask;
+    }
+    rc = upload_graph(e, off, (cudaStream_t)stream);
+    if (rc) return rc;
+    rc = reserve_states(e);
+    if (rc) return rc;
+    e->graph_set = true;
+    return GGNN_OK;
+}
+
+static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_out) {
+    memset(&p, 0, sizeof p);
+    p.V = e->V; p.D = e->D; p.T = e->T; p.L = e->L;
+    p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
+    p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
+    char* g = (char*)e->graph_buf.ptr;
+    p.tile_start = (const int*)(g + e->off_tiles);
+    p.tile_mask = (const unsigned*)(g + e->off_mask);
+    p.row_ptr = (const int*)(g + e->off_row_ptr);
+    p.csr_src = (const int*)(g + e->off_src);
+    p.dense_adj = (const float*)(g + e->off_adj);
+    p.indeg = (const float*)(g + e->off_indeg);
+    p.denom = (const float*)(g + e->off_denom);
+    const size_t vd = (size_t)std::max(e->V, 1) * e->D;
+    float* sb = (float*)e->state_buf.ptr;
+    p.state[0] = h0; p.state_w[0] = nullptr;
+    for (int l = 1; l <= e->L; ++l) {
+        float* ptr = (l == e->L) ? h_out : sb + (size_t)(l - 1) * vd;
+        p.state[l] = ptr; p.state_w[l] = ptr;
+    }
+    for (int l = 0; l < e->L; ++l) {
+        LayerDev& ld = p.layer[l];
+        ld.edge_w = e->w[l].edge_weights; ld.edge_b = e->w[l].edge_biases;
+        ld.gate_k = e->w[l].gate_kernel; ld.gate_b = e->w[l].gate_bias;
+        ld.cand_k = e->w[l].cand_kernel; ld.cand_b = e->w[l].cand_bias;
+        ld.steps = e->steps[l]; ld.nres = e->nres[l];
+        for (int i = 0; i < MAX_RES; ++i) ld.res[i] = e->res[l][i];
+        p.step_base[l] = e->step_base[l];
+    }
+    if (e->save) {
+        float* s = (float*)e->save_bufs.ptr;
+        const size_t per = vd * (size_t)std::max(e->total_steps, 1);
+        p.save_buf.h_in = s; p.save_buf.agg = s + per; p.save_buf.r = s + 2 * per; p.save_buf.u = s + 3 * per; p.save_buf.c = s + 4 * per;
+    }
+}
+
+int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    if (!e->weights_set) return e->fail(GGNN_ESTATE, "ggnn_set_weights has not been called");
+    if (!e->graph_set) return e->fail(GGNN_ESTATE, "no graph set (ggnn_set_graph_sparse/dense)");
+    if ((!h0 || !h_out) && e->V > 0) return e->fail(GGNN_EINVAL, "null state pointer");
+    if (((uintptr_t)h0 & 15) || ((uintptr_t)h_out & 15)) return e->fail(GGNN_EINVAL, "state pointers must be 16-byte aligned");
+    CU_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    e->last_launches = 0;
+    e->last_h0 = h0; e->last_out = h_out; e->saved_valid = false;
+    if (e->V == 0) return GGNN_OK;
+    if (e->save) { int rc = reserve_states(e); if (rc) return rc; }
+    const size_t vd_bytes = (size_t)e->V * e->D * sizeof(float);
+    if (e->total_steps == 0) {  // no propagation at all: result is the input (sparse:152 with empty loops)
+        if (h_out != h0) CU_TRY(e, cudaMemcpyAsync(h_out, h0, vd_bytes, cudaMemcpyDeviceToDevice, st));
+        return GGNN_OK;
+    }
+    FwdParams p;
+    fill_params(e, p, h0, h_out);
+    FwdKernel k = pick_fwd_kernel(e->variant, e->nb1, e->local);
+    if (!k) return e->fail(GGNN_EUNSUPPORTED, "no kernel for variant=%d nb1=%d", e->variant, e->nb1);
+    const size_t smem = fwd_smem_bytes(e->variant, e->nb1, e->D, e->T);
+    CU_TRY(e, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = 256;
+    if (e->local) {
+        // layers with zero timesteps just alias the previous state (sparse:152): copy afterwards
+        k<<<e->ntiles, threads, smem, st>>>(p);
+        ++e->last_launches;
+    } else {
+        const size_t vd = (size_t)e->V * e->D;
+        float* tmp0 = (float*)e->state_buf.ptr + (size_t)(e->L - 1 > 0 ? e->L - 1 : 0) * vd;
+        float* tmp1 = tmp0 + vd;
+        for (int l = 0; l < e->L; ++l) {
+            const float* in = p.state[l];
+            if (e->steps[l] == 0) {
+                CU_TRY(e, cudaMemcpyAsync(p.state_w[l + 1], in, vd_bytes, cudaMemcpyDeviceToDevice, st));
+                continue;
+            }
+            for (int s = 0; s < e->steps[l]; ++s) {
+                float* out = (s == e->steps[l] - 1) ? p.state_w[l + 1] : ((s & 1) ? tmp1 : tmp0);
+                p.g_layer = l; p.g_step = s; p.g_in = in; p.g_out = out;
+                k<<<e->ntiles, threads, smem, st>>>(p);
+                ++e->last_launches;
+                in = out;
+            }
+        }
+    }
+    CU_TRY(e, cudaGetLastError());
+    if (e->save) e->saved_valid = true;
+    return GGNN_OK;
+}
+
+int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    if (!e->graph_set) return e->fail(GGNN_ESTATE, "no graph set (ggnn_set_graph_sparse/dense)");
+    if ((!h0_host || !h_out_host) && e->V > 0) return e->fail(GGNN_EINVAL, "null host pointer");
+    CU_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = (size_t)e->V * e->D * sizeof(float);
+    const size_t slot = align_up(std::max<size_t>(bytes, 16), 256);
+    CU_TRY(e, e->io_buf.reserve(2 * slot));
+    float* d_in = (float*)e->io_buf.ptr;
+    float* d_out = (float*)((char*)e->io_buf.ptr + slot);
+    if (bytes) CU_TRY(e, cudaMemcpyAsync(d_in, h0_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = ggnn_forward(e, d_in, d_out, stream);
+    if (rc) return rc;
+    if (bytes) CU_TRY(e, cudaMemcpyAsync(h_out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(e, cudaStreamSynchronize(st));
+    return GGNN_OK;
+}
+
+int ggnn_set_save_for_backward(ggnn_engine* e, int32_t enable) {
+    if (!e) return GGNN_EINVAL;
+    e->save = enable != 0;
+    e->saved_valid = false;
+    return GGNN_OK;
+}
+
+int ggnn_backward(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* grads, int32_t num_layers,
+                  float* d_h0, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    return ggnn_backward_impl(e, d_h_out, grads, num_layers, d_h0, stream);
+}
+
+int ggnn_num_messages(const ggnn_engine* e, int64_t* out) {
+    if (!e || !out) return GGNN_EINVAL;
+    *out = e->M;
+    return GGNN_OK;
+}
+
+int ggnn_get_csr(ggnn_engine* e, int32_t* row_ptr, int32_t* src, int32_t* msg) {
+    if (!e) return GGNN_EINVAL;
+    if (!e->graph_set || e->gather_mode != GATHER_SPARSE) return e->fail(GGNN_ESTATE, "no sparse graph set");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaDeviceSynchronize());
+    char* g = (char*)e->graph_buf.ptr;
+    if (row_ptr) CU_TRY(e, cudaMemcpy(row_ptr, g + e->off_row_ptr, sizeof(int) * ((size_t)e->V * e->T + 1), cudaMemcpyDeviceToHost));
+    if (src && e->M) CU_TRY(e, cudaMemcpy(src, g + e->off_src, sizeof(int) * (size_t)e->M, cudaMemcpyDeviceToHost));
+    if (msg && e->M) CU_TRY(e, cudaMemcpy(msg, g + e->off_msg, sizeof(int) * (size_t)e->M, cudaMemcpyDeviceToHost));
+    return GGNN_OK;
+}
+
+int ggnn_layer_state(ggnn_engine* e, int32_t layer, const float** dev_ptr) {
+    if (!e || !dev_ptr) return GGNN_EINVAL;
+    if (layer < 0 || layer > e->L) return e->fail(GGNN_EINVAL, "layer index %d out of range", layer);
+    if (!e->last_out) return e->fail(GGNN_ESTATE, "no forward has run");
+    const size_t vd = (size_t)std::max(e->V, 1) * e->D;
+    if (layer == 0) *dev_ptr = e->last_h0;
+    else if (layer == e->L) *dev_ptr = e->last_out;
+    else *dev_ptr = (const float*)e->state_buf.ptr + (size_t)(layer - 1) * vd;
+    return GGNN_OK;
+}
+
+int ggnn_copy_layer_state(ggnn_engine* e, int32_t layer, float* dst, ggnn_stream_t stream) {
+    const float* src = nullptr;
+    int rc = ggnn_layer_state(e, layer, &src);
+    if (rc) return rc;
+    if (!dst) return e->fail(GGNN_EINVAL, "null destination");
+    CU_TRY(e, cudaSetDevice(e->device));
+    if (e->V > 0)
+        CU_TRY(e, cudaMemcpyAsync(dst, src, (size_t)e->V * e->D * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return GGNN_OK;
+}
+
+int ggnn_last_launch_count(const ggnn_engine* e) { return e ? e->last_launches : 0; }
+const char* ggnn_plan_description(const ggnn_engine* e) { return e ? e->plan_text.c_str() : ""; }
+
+}  // extern "C"

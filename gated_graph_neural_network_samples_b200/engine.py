@@ -1,0 +1,217 @@
+"""Python face of the C ABI (include/ggnn_b200.h): one ``PropagationEngine`` per model instance and GPU.
+
+PyTorch is used for device memory and streams only; all arithmetic of the propagation step runs in
+libggnn_b200.so (hand-written sm_100a kernels).  There is no fallback: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+WEIGHT_FIELDS = ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias")
+
+
+def residual_inputs_of_layer(params: dict, layer_idx: int) -> List[int]:
+    """sparse:140-145 -- ``params['residual_connections'].get(str(layer_idx))``."""
+    lst = (params.get("residual_connections") or {}).get(str(layer_idx))
+    return [] if lst is None else [int(x) for x in lst]
+
+
+def layer_input_width(params: dict, layer_idx: int) -> int:
+    return int(params["hidden_size"]) * (1 + len(residual_inputs_of_layer(params, layer_idx)))
+
+
+def weight_shapes(params: dict, num_edge_types: int, layer_idx: int) -> Dict[str, tuple]:
+    """Shapes of one layer's trainables exactly as created at sparse:86-115 (+ TF-1.3 cell variables)."""
+    D, T = int(params["hidden_size"]), int(num_edge_types)
+    din = layer_input_width(params, layer_idx)
+    shapes = {"edge_weights": (T, D, D)}
+    if params.get("use_edge_bias", False):
+        shapes["edge_biases"] = (T, D)
+    if params.get("graph_rnn_cell", "GRU").lower() == "gru":
+        shapes.update(gate_kernel=(din + D, 2 * D), gate_bias=(2 * D,), cand_kernel=(din + D, D), cand_bias=(D,))
+    else:
+        shapes.update(cand_kernel=(din + D, D), cand_bias=(D,))
+    return shapes
+
+
+class GgnnError(Exception):
+    """Raised for every non-zero return of the C ABI (the reference raises plain ``Exception``s too)."""
+
+
+class PropagationEngine:
+    def __init__(self, params: dict, num_edge_types: int, device: int = 0, precision: str = "fp32"):
+        self._h = C.c_void_p()
+        self.lib = _lib.load()
+        self.params = dict(params)
+        self.D = int(params["hidden_size"])
+        self.T = int(num_edge_types)
+        steps = [int(s) for s in params["layer_timesteps"]]
+        self.L = len(steps)
+        act = params.get("graph_rnn_activation", "tanh").lower()
+        if act not in ("tanh", "relu"):
+            raise Exception("Unknown activation function type '%s'." % act)                  # sparse:81
+        cell = params.get("graph_rnn_cell", "GRU").lower()
+        if cell not in ("gru", "rnn"):
+            # CudnnCompatibleGRUCell (sparse:105-108) is a different cell (reset gate applied after the
+            # recurrent matmul); it is in no BASELINE config and not provided by tensorflow==1.3.0.
+            raise Exception("Unknown RNN cell type '%s'." % cell)                            # sparse:112
+        if params.get("use_propagation_attention", False):
+            raise Exception("use_propagation_attention is not implemented by the B200 engine yet")
+        offs, flat = [0], []
+        for l in range(self.L):
+            flat += residual_inputs_of_layer(params, l)
+            offs.append(len(flat))
+        self._steps = (C.c_int32 * self.L)(*steps)
+        self._offs = (C.c_int32 * (self.L + 1))(*offs)
+        self._flat = (C.c_int32 * max(len(flat), 1))(*flat)
+        cfg = _lib.GgnnConfig(self.D, self.T, self.L, self._steps, self._offs, self._flat,
+                              int(bool(params.get("use_edge_bias", False))),
+                              int(bool(params.get("use_edge_msg_avg_aggregation", False))),
+                              0 if cell == "gru" else 1, 0 if act == "tanh" else 1,
+                              PRECISIONS[precision], int(device))
+        rc = self.lib.ggnn_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise GgnnError(self.lib.ggnn_last_error(None).decode())
+        self.device = int(device)
+        self.V = 0
+        self._weights_keepalive = None
+        self._graph_keepalive = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GgnnError(self.lib.ggnn_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.ggnn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream() -> int:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------ model
+    def set_weights(self, layers: Sequence[dict]):
+        """``layers[l]``: dict of contiguous fp32 CUDA tensors keyed like ``ggnn_layer_weights``."""
+        arr = (_lib.GgnnLayerWeights * len(layers))()
+        keep = []
+        for l, w in enumerate(layers):
+            shapes = weight_shapes(self.params, self.T, l)
+            for f in WEIGHT_FIELDS:
+                t = w.get(f)
+                if t is None or f not in shapes:
+                    setattr(arr[l], f, None)
+                    continue
+                if not (t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4):
+                    raise GgnnError("layer %d %s must be a contiguous fp32 CUDA tensor" % (l, f))
+                if tuple(t.reshape(shapes[f]).shape) != shapes[f]:
+                    raise GgnnError("layer %d %s has shape %s, expected %s" % (l, f, tuple(t.shape), shapes[f]))
+                setattr(arr[l], f, t.data_ptr())
+                keep.append(t)
+        self._check(self.lib.ggnn_set_weights(self._h, arr, len(layers)))
+        self._weights_keepalive = keep
+
+    # ------------------------------------------------------------------ batch
+    def set_graph_sparse(self, adjacency_lists: Sequence[np.ndarray], num_incoming_edges_per_type: np.ndarray):
+        """Reference wire format (sparse:331-348): per type an ``[E_t, 2]`` int32 (source, target) list and the
+        ``[V, T]`` in-degree table.  HOST arrays; index validation, CSR build and upload happen in the library."""
+        if len(adjacency_lists) != self.T:
+            raise GgnnError("expected %d adjacency lists, got %d" % (self.T, len(adjacency_lists)))
+        adjs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, 2)) for a in adjacency_lists]
+        indeg = np.ascontiguousarray(np.asarray(num_incoming_edges_per_type, dtype=np.float32))
+        if indeg.ndim != 2 or indeg.shape[1] != self.T:
+            raise GgnnError("num_incoming_edges_per_type must be [V, %d]" % self.T)
+        V = indeg.shape[0]
+        ptrs = (C.c_void_p * self.T)(*[a.ctypes.data for a in adjs])
+        counts = (C.c_int32 * self.T)(*[a.shape[0] for a in adjs])
+        self._check(self.lib.ggnn_set_graph_sparse(self._h, V, ptrs, counts, indeg.ctypes.data, self._stream()))
+        self.V = V
+        self._graph_keepalive = (adjs, indeg)
+
+    def set_graph_dense(self, adjacency_matrix: np.ndarray):
+        """Dense wire format (dense:214-224): ``[b, T, v, v]`` float32 with ``A[g, t, dest, src]``."""
+        a = np.ascontiguousarray(np.asarray(adjacency_matrix, dtype=np.float32))
+        if a.ndim != 4 or a.shape[1] != self.T or a.shape[2] != a.shape[3]:
+            raise GgnnError("adjacency_matrix must be [b, %d, v, v]" % self.T)
+        self._check(self.lib.ggnn_set_graph_dense(self._h, a.shape[0], a.shape[2], a.ctypes.data, self._stream()))
+        self.V = a.shape[0] * a.shape[2]
+        self._graph_keepalive = (a,)
+
+    # ------------------------------------------------------------------ the hot path
+    def forward(self, h0, out=None):
+        """compute_final_node_representations on device tensors: ``h0`` [V, D] fp32 CUDA -> [V, D]."""
+        import torch
+        if not (h0.is_cuda and h0.dtype == torch.float32 and h0.is_contiguous()):
+            raise GgnnError("h0 must be a contiguous fp32 CUDA tensor")
+        if h0.numel() != self.V * self.D:
+            raise GgnnError("h0 has %d elements, the graph has %d nodes x %d" % (h0.numel(), self.V, self.D))
+        if out is None:
+            out = torch.empty_like(h0)
+        self._check(self.lib.ggnn_forward(self._h, h0.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def forward_host(self, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Same through HOST buffers (H2D + propagation + D2H inside the call, synchronous)."""
+        h0 = np.ascontiguousarray(h0, dtype=np.float32)
+        if h0.size != self.V * self.D:
+            raise GgnnError("h0 has %d elements, the graph has %d nodes x %d" % (h0.size, self.V, self.D))
+        if out is None:
+            out = np.empty_like(h0)
+        self._check(self.lib.ggnn_forward_host(self._h, h0.ctypes.data, out.ctypes.data, self._stream()))
+        return out
+
+    def set_save_for_backward(self, enable: bool):
+        self._check(self.lib.ggnn_set_save_for_backward(self._h, int(bool(enable))))
+
+    def backward(self, d_out, grads: Sequence[dict], d_h0=None):
+        arr = (_lib.GgnnLayerGrads * len(grads))()
+        for l, g in enumerate(grads):
+            for f in WEIGHT_FIELDS:
+                t = g.get(f)
+                setattr(arr[l], f, None if t is None else t.data_ptr())
+        self._check(self.lib.ggnn_backward(self._h, d_out.data_ptr(), arr, len(grads),
+                                           None if d_h0 is None else d_h0.data_ptr(), self._stream()))
+
+    # ------------------------------------------------------------------ introspection
+    def num_messages(self) -> int:
+        m = C.c_int64()
+        self._check(self.lib.ggnn_num_messages(self._h, C.byref(m)))
+        return int(m.value)
+
+    def csr(self):
+        M = self.num_messages()
+        row_ptr = np.empty(self.V * self.T + 1, np.int32)
+        src = np.empty(M, np.int32)
+        msg = np.empty(M, np.int32)
+        self._check(self.lib.ggnn_get_csr(self._h, row_ptr.ctypes.data, src.ctypes.data, msg.ctypes.data))
+        return row_ptr, src, msg
+
+    def layer_state(self, layer: int):
+        """Copy of node_states_per_layer[layer] (0 = h0, L = result) of the last forward, as a CUDA tensor."""
+        import torch
+        out = torch.empty(self.V, self.D, dtype=torch.float32, device="cuda:%d" % self.device)
+        self._check(self.lib.ggnn_copy_layer_state(self._h, int(layer), out.data_ptr(), self._stream()))
+        return out
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.ggnn_last_launch_count(self._h))
+
+    @property
+    def plan(self) -> str:
+        return self.lib.ggnn_plan_description(self._h).decode()

@@ -1,0 +1,136 @@
+/*
+ * ggnn_b200.h -- C ABI of the B200-native GGNN propagation engine (libggnn_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of microsoft/gated-graph-neural-network-samples: the
+ * propagation step behind ChemModel's two graph-model hooks
+ *
+ *     prepare_specific_graph_model()          chem_tensorflow.py:205  (sparse:63-115, dense:68-91)
+ *     compute_final_node_representations()    chem_tensorflow.py:208  (sparse:117-218, dense:93-117)
+ *
+ * The reference has no FFI (it is TF-1 graph construction in Python), so these entry points are what
+ * a ctypes binding inside those two hooks calls (INTEGRATION.md shows the stub).  Plain pointers and
+ * sizes only; no torch/TF types.  All functions return 0 on success or a negative GGNN_E* code; the
+ * text is available from ggnn_last_error().  Nothing throws across the ABI.
+ *
+ * Ownership: the caller owns every tensor it passes (node states, weights, gradients); they must stay
+ * valid until the stream work completes.  The engine owns its handle, the device copy of the batch's
+ * graph structure (CSR + tiling) and its scratch.  One engine per GPU/stream; not thread-safe.
+ * Launches are asynchronous on the caller's stream; there is no hidden device synchronisation except
+ * in the *_host convenience calls, which return after the result is in host memory.
+ */
+#ifndef GGNN_B200_H
+#define GGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ggnn_engine ggnn_engine;
+typedef void* ggnn_stream_t; /* a cudaStream_t (0 = default stream) */
+
+enum { GGNN_OK = 0, GGNN_EINVAL = -1, GGNN_ECUDA = -2, GGNN_ESTATE = -3, GGNN_EUNSUPPORTED = -4, GGNN_ERANGE = -5 };
+enum { GGNN_CELL_GRU = 0, GGNN_CELL_RNN = 1 };  /* params['graph_rnn_cell']        sparse:102-112 */
+enum { GGNN_ACT_TANH = 0, GGNN_ACT_RELU = 1 };  /* params['graph_rnn_activation']  sparse:75-81   */
+/* arithmetic of the dense contractions */
+enum { GGNN_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores (bit-for-bit fp32 semantics, order aside) */
+       GGNN_PREC_BF16X3 = 1, /* tcgen05 tensor cores, bf16 hi/lo split, 3 MMAs (~2^-16 rel / product) */
+       GGNN_PREC_BF16 = 2 }; /* tcgen05 tensor cores, single bf16 MMA ("fast", outside the 1e-4 bar) */
+
+/* Mirrors the keys of self.params the two hooks read (sparse:40-61, chem_tensorflow.py:17-37). */
+typedef struct ggnn_config {
+    int32_t hidden_size;                  /* params['hidden_size'] (D)                                 */
+    int32_t num_edge_types;               /* self.num_edge_types (T), chem_tensorflow.py:120           */
+    int32_t num_layers;                   /* len(params['layer_timesteps'])                            */
+    const int32_t* layer_timesteps;       /* [num_layers]                        sparse:53,131         */
+    const int32_t* residual_offsets;      /* [num_layers+1] CSR over layers      sparse:48-51,140-145  */
+    const int32_t* residual_layers;       /* [residual_offsets[num_layers]] indices into node_states_per_layer */
+    int32_t use_edge_bias;                /* sparse:45,98,202                                          */
+    int32_t use_edge_msg_avg_aggregation; /* sparse:47,206                                             */
+    int32_t cell;                         /* GGNN_CELL_*                                               */
+    int32_t activation;                   /* GGNN_ACT_*                                                */
+    int32_t precision;                    /* GGNN_PREC_*                                               */
+    int32_t device;                       /* CUDA device ordinal                                       */
+} ggnn_config;
+
+/* Device pointers to one layer's trainables, fp32 row-major, shapes as created at sparse:86-115:
+ *   edge_weights [T, D, D]   (the reference Variable is [T*D, D]; same bytes, sparse:88-90)
+ *   edge_biases  [T, D]      or NULL when !use_edge_bias (dense model: [T,1,D], same bytes)
+ *   GRU: gate_kernel [Din+D, 2D], gate_bias [2D]  (columns: r first, u second)
+ *        cand_kernel [Din+D, D],  cand_bias [D]
+ *   RNN: cand_kernel [Din+D, D], cand_bias [D] hold BasicRNNCell's kernel/bias; gate_* are NULL.
+ * Din = D * (1 + number of residual inputs of the layer); kernel rows are ordered
+ * [residual states ..., aggregated messages, recurrent state] (sparse:211-216 + TF-1.3 _linear).   */
+typedef struct ggnn_layer_weights {
+    const float* edge_weights;
+    const float* edge_biases;
+    const float* gate_kernel;
+    const float* gate_bias;
+    const float* cand_kernel;
+    const float* cand_bias;
+} ggnn_layer_weights;
+
+/* Same layout, device pointers the backward pass ACCUMULATES into (caller zeroes them). */
+typedef struct ggnn_layer_grads {
+    float* edge_weights;
+    float* edge_biases;
+    float* gate_kernel;
+    float* gate_bias;
+    float* cand_kernel;
+    float* cand_bias;
+} ggnn_layer_grads;
+
+/* prepare_specific_graph_model (sparse:63-115 / dense:68-91): fix the model shape. */
+int ggnn_create(const ggnn_config* cfg, ggnn_engine** out);
+int ggnn_destroy(ggnn_engine* e);
+const char* ggnn_last_error(const ggnn_engine* e); /* e may be NULL: error of the last failed ggnn_create */
+
+/* Bind the trainables (device pointers, one entry per layer); pointers are read at every forward. */
+int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t num_layers);
+
+/* Feed one batch's graph structure in the reference wire format (sparse:331-348), HOST pointers:
+ *   adjacency_lists[t] -> [num_edges[t], 2] int32 (col 0 = source, col 1 = target), message order kept
+ *   num_incoming_edges_per_type -> [V, T] float32
+ * Validates indices (TF-CPU gather raises on OOB), builds the stable target-sorted CSR and the tile
+ * plan, and uploads them on `stream`. */
+int ggnn_set_graph_sparse(ggnn_engine* e, int32_t num_nodes, const int32_t* const* adjacency_lists,
+                          const int32_t* num_edges, const float* num_incoming_edges_per_type,
+                          ggnn_stream_t stream);
+
+/* Dense wire format (dense:214-224): adjacency_matrix [b, T, v, v] float32 HOST pointer with
+ * A[g, t, dest, src] (dense:30-36).  Rows are the b*v padded nodes. */
+int ggnn_set_graph_dense(ggnn_engine* e, int32_t num_graphs, int32_t num_vertices,
+                         const float* adjacency_matrix, ggnn_stream_t stream);
+
+/* compute_final_node_representations (sparse:117-218 / dense:93-117).
+ * h0, h_out: DEVICE [V, D] fp32 (dense: [b*v, D]).  Asynchronous on `stream`. */
+int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t stream);
+
+/* Same with HOST buffers: H2D copy of h0, propagation, D2H copy of the result, stream-synchronised. */
+int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
+
+/* Gradient of the propagation (what optimizer.compute_gradients builds, chem_tensorflow.py:184).
+ * Must follow a ggnn_forward on the same graph with save_for_backward enabled.
+ * d_h_out: DEVICE [V, D]; grads: per layer, accumulated into; d_h0: DEVICE [V, D] or NULL. */
+int ggnn_set_save_for_backward(ggnn_engine* e, int32_t enable);
+int ggnn_backward(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* grads, int32_t num_layers,
+                  float* d_h0, ggnn_stream_t stream);
+
+/* Introspection used by the parity tests and the benchmark. */
+int ggnn_num_messages(const ggnn_engine* e, int64_t* out);
+/* Copies the engine's device CSR back: row_ptr [V*T+1] (rows keyed target*T+type), src [M], msg [M]. */
+int ggnn_get_csr(ggnn_engine* e, int32_t* row_ptr, int32_t* src, int32_t* msg);
+/* Pointer to node_states_per_layer[layer] (layer 0 = h0, num_layers = final), valid after forward. */
+int ggnn_layer_state(ggnn_engine* e, int32_t layer, const float** dev_ptr);
+/* Device-to-device copy of that state into dst [V, D] on `stream`. */
+int ggnn_copy_layer_state(ggnn_engine* e, int32_t layer, float* dst, ggnn_stream_t stream);
+/* Kernel launches issued by the last forward / backward call, and plan description text. */
+int ggnn_last_launch_count(const ggnn_engine* e);
+const char* ggnn_plan_description(const ggnn_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGNN_B200_H */

@@ -1,0 +1,81 @@
+"""Helpers shared by the GPU parity tests: drive the C-ABI engine on inputs the oracle also sees."""
+import json
+import os
+
+import numpy as np
+
+from gated_graph_neural_network_samples_b200 import packing, synthetic
+
+# north_star tolerance: node hidden states within 1e-4 relative (fp32)
+RTOL = 1e-4
+ATOL = 1e-5
+
+
+def to_cuda_weights(weights):
+    import torch
+    out = []
+    for w in weights:
+        d = {}
+        for k, v in w.items():
+            key = {"rnn_kernel": "cand_kernel", "rnn_bias": "cand_bias"}.get(k, k)
+            d[key] = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).cuda().contiguous()
+        out.append(d)
+    return out
+
+
+def engine_sparse(params, T, weights, adj, indeg, h0, precision="fp32", return_engine=False):
+    import torch
+    from gated_graph_neural_network_samples_b200.engine import PropagationEngine
+    eng = PropagationEngine(params, T, precision=precision)
+    eng.set_weights(to_cuda_weights(weights))
+    eng.set_graph_sparse(adj, indeg)
+    out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0, dtype=np.float32)).cuda())
+    torch.cuda.synchronize()
+    res = out.cpu().numpy()
+    return (res, eng) if return_engine else res
+
+
+def dense_params_as_engine_params(dparams, D):
+    return {"hidden_size": D, "layer_timesteps": [int(dparams["num_timesteps"])], "residual_connections": {},
+            "use_edge_bias": bool(dparams.get("use_edge_bias", True)), "use_edge_msg_avg_aggregation": False,
+            "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh"}
+
+
+def engine_dense(dparams, T, w, adjm, h0, precision="fp32"):
+    import torch
+    from gated_graph_neural_network_samples_b200.engine import PropagationEngine
+    b, v, D = h0.shape
+    params = dense_params_as_engine_params(dparams, D)
+    eng = PropagationEngine(params, T, precision=precision)
+    w = dict(w)
+    if "edge_biases" in w:
+        w["edge_biases"] = np.asarray(w["edge_biases"]).reshape(T, D)
+    eng.set_weights(to_cuda_weights([w]))
+    eng.set_graph_dense(adjm)
+    out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0.reshape(b * v, D), dtype=np.float32)).cuda())
+    torch.cuda.synchronize()
+    return out.cpu().numpy().reshape(b, v, D)
+
+
+def molecule_batch(n, D, T=4, seed=0, noise=0.1):
+    mols = synthetic.make_molecules(n, seed=seed, num_bond_types=T)
+    b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), D, T)
+    if noise:
+        rng = np.random.default_rng(seed + 1000)
+        b["initial_node_representation"] = (b["initial_node_representation"]
+                                            + rng.normal(0, noise, b["initial_node_representation"].shape)).astype(np.float32)
+    return mols, b
+
+
+def load_golden_sparse(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "prop_sparse_%s.npz" % name))
+    p = json.loads(str(z["params_json"]))
+    L = len(p["layer_timesteps"])
+    w = [{k[len("w%d_" % li):]: z[k] for k in z.files if k.startswith("w%d_" % li)} for li in range(L)]
+    adj = [z["adj%d" % e] for e in range(4)]
+    return z, p, w, adj
+
+
+def max_rel_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
