@@ -38,7 +38,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GGNN_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("GGNN_PRECISION", "auto"),
+                    help="auto = bf16x3 (tcgen05, fp32-accurate split, within the 1e-4 parity bar) when hidden <= 128, else fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     return ap.parse_args()
@@ -178,6 +179,8 @@ def main():
     # no data-path collective: forward propagation never crosses graphs)
     w = workloads.build(args.config, seed=rank)
     P = w["engine_params"]
+    if args.precision == "auto":
+        args.precision = "bf16x3" if int(P["hidden_size"]) <= 128 else "fp32"
     eng = PropagationEngine(P, w["num_edge_types"], device=local_rank, precision=args.precision)
     dev_w = [{k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in lw.items()} for lw in w["weights"]]
     eng.set_weights(dev_w)
@@ -289,7 +292,7 @@ def main():
         line = {
             "metric": "GGNN node-state-updates/sec (propagation step)", "value": value, "unit": "node-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else args.precision,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 operands split hi+lo, 3 tensor-core MMAs, fp32 accumulate)", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (w["name"], "BASELINE.json configs[1]" if w["name"] == "cfg2" else "see workloads.py"),
                        "V_per_gpu": w["V"], "M_per_gpu": w["M"], "graphs_per_gpu": w["num_graphs"],

@@ -18,6 +18,7 @@
 #include "../../include/ggnn_b200.h"
 #include "ggnn_common.cuh"
 #include "ggnn_fwd_ffma.cuh"
+#include "ggnn_fwd_tc.cuh"
 
 using namespace ggnn;
 
@@ -84,6 +85,7 @@ struct ggnn_engine {
     bool local = false;
     int ntiles = 0;
     int max_span = 0;
+    int max_tile_msgs = 0;   // largest number of messages whose target lies in one tile
     std::string plan_text;
 
     // device memory
@@ -94,6 +96,13 @@ struct ggnn_engine {
     DevBuf save_bufs;   // 5 x total_steps x [V][D]
     DevBuf io_buf;      // h0 / h_out staging for ggnn_forward_host
     DevBuf bwd_buf;     // backward scratch
+    DevBuf tc_weights;  // pre-split, pre-tiled bf16 copies of the weights (tensor-core path)
+    DevBuf tc_respre;   // residual pre-products [ntiles][128][3*DP]
+    DevBuf err_flag;    // device int written by kernels on a barrier timeout
+    DevBuf dbg_buf;     // optional phase timestamps (GGNN_TC_DEBUG_TIMING=1)
+    bool weights_dirty = true;
+    int DP = 0;         // hidden size padded to a multiple of 16 (tensor-core path)
+    size_t tc_off_edge[MAX_LAYERS] = {0}, tc_off_gate_r[MAX_LAYERS] = {0}, tc_off_gate_u[MAX_LAYERS] = {0}, tc_off_cand[MAX_LAYERS] = {0};
     const float* last_h0 = nullptr;
     float* last_out = nullptr;
     bool save = false;
@@ -172,6 +181,32 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
     int max_span = 0;
     for (size_t i = 1; i < cuts.size(); ++i) max_span = std::max(max_span, cuts[i] - cuts[i - 1]);
     e->max_span = max_span;
+    if (e->precision != GGNN_PREC_FP32) {
+        e->variant = 2;
+        e->nb1 = 0;
+        e->local = max_span <= tc::TILE_M;
+        const char* fg = getenv("GGNN_FORCE_GLOBAL");
+        if (fg && fg[0] == '1') e->local = false;
+        tile_start.clear();
+        tile_start.push_back(0);
+        if (e->local) {
+            int cur = 0;
+            for (size_t i = 1; i < cuts.size(); ++i)
+                if (cuts[i] - cur > tc::TILE_M) { tile_start.push_back(cuts[i - 1]); cur = cuts[i - 1]; }
+            if (V > cur) tile_start.push_back(V);
+        } else {
+            for (int r = tc::TILE_M; r < V; r += tc::TILE_M) tile_start.push_back(r);
+            if (V > 0) tile_start.push_back(V);
+        }
+        if (V == 0) tile_start.assign(1, 0);
+        e->ntiles = (int)tile_start.size() - 1;
+        char buf[256];
+        snprintf(buf, sizeof buf, "tcgen05-%s %s tiles=%d rows/tile<=128 DP=%d max_component=%d",
+                 e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)",
+                 e->ntiles, e->DP, max_span);
+        e->plan_text = buf;
+        return GGNN_OK;
+    }
     const bool a_ok = pick_nb1(0, D) > 0 && fwd_smem_bytes(0, pick_nb1(0, D), D, e->T) <= e->max_smem;
     const bool b_ok = pick_nb1(1, D) > 0 && fwd_smem_bytes(1, pick_nb1(1, D), D, e->T) <= e->max_smem;
     if (!a_ok && !b_ok) return e->fail(GGNN_EUNSUPPORTED, "hidden_size=%d does not fit any fp32 tile variant", D);
@@ -242,7 +277,11 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     if (!cfg->layer_timesteps) return bad("layer_timesteps is null");
     if (cfg->cell != GGNN_CELL_GRU && cfg->cell != GGNN_CELL_RNN) return bad("Unknown RNN cell type");              // sparse:112
     if (cfg->activation != GGNN_ACT_TANH && cfg->activation != GGNN_ACT_RELU) return bad("Unknown activation function type");  // sparse:81
-    if (cfg->precision != GGNN_PREC_FP32) { g_create_error = "only GGNN_PREC_FP32 is built in this revision"; return GGNN_EUNSUPPORTED; }
+    if (cfg->precision != GGNN_PREC_FP32 && cfg->precision != GGNN_PREC_BF16X3 && cfg->precision != GGNN_PREC_BF16) return bad("unknown precision");
+    if (cfg->precision != GGNN_PREC_FP32 && cfg->hidden_size > 128) {
+        g_create_error = "the tensor-core path (bf16x3/bf16) supports hidden_size <= 128 in this revision; use GGNN_PREC_FP32";
+        return GGNN_EUNSUPPORTED;
+    }
     ggnn_engine* e = new ggnn_engine();
     e->D = cfg->hidden_size; e->T = cfg->num_edge_types; e->L = cfg->num_layers;
     e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
@@ -267,6 +306,7 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
         e->nres[l] = nr;
     }
     e->total_steps = total;
+    e->DP = (e->D + 15) / 16 * 16;
     cudaError_t st = cudaSetDevice(e->device);
     cudaDeviceProp prop;
     if (st == cudaSuccess) st = cudaGetDeviceProperties(&prop, e->device);
@@ -278,6 +318,11 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     e->num_sms = prop.multiProcessorCount;
     e->max_smem = prop.sharedMemPerBlockOptin;
     memset(e->w, 0, sizeof e->w);
+    if (e->err_flag.reserve(sizeof(int)) != cudaSuccess || cudaMemset(e->err_flag.ptr, 0, sizeof(int)) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed";
+        delete e;
+        return GGNN_ECUDA;
+    }
     *out = e;
     return GGNN_OK;
 }
@@ -286,6 +331,7 @@ int ggnn_destroy(ggnn_engine* e) {
     if (!e) return GGNN_OK;
     cudaSetDevice(e->device);
     e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
+    e->tc_weights.release(); e->tc_respre.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
     delete e;
     return GGNN_OK;
@@ -305,6 +351,7 @@ int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t n
         e->w[l] = w;
     }
     e->weights_set = true;
+    e->weights_dirty = true;   // the tensor-core path re-tiles its bf16 copies at the next forward
     return GGNN_OK;
 }
 
@@ -414,6 +461,9 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
                 if (row_ptr[(size_t)v * T + t + 1] > row_ptr[(size_t)v * T + t]) mask |= 1u << t;
         h_mask[i] = mask;
     }
+    e->max_tile_msgs = 0;
+    for (int i = 0; i < ntiles; ++i)
+        e->max_tile_msgs = std::max(e->max_tile_msgs, row_ptr[(size_t)tile_start[i + 1] * T] - row_ptr[(size_t)tile_start[i] * T]);
     rc = upload_graph(e, off, (cudaStream_t)stream);
     if (rc) return rc;
     rc = reserve_states(e);
@@ -532,6 +582,138 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------ tensor-core path (host)
+static int tc_prepare_weights(ggnn_engine* e, cudaStream_t st) {
+    const int D = e->D, DP = e->DP, T = e->T, NKS = DP / 16;
+    size_t off = 0;
+    for (int l = 0; l < e->L; ++l) {
+        const int nseg = e->nres[l] + 2;
+        e->tc_off_edge[l] = off; off += (size_t)T * NKS * 64 * DP;
+        e->tc_off_gate_r[l] = off; off += (size_t)nseg * NKS * 64 * DP;
+        e->tc_off_gate_u[l] = off; off += (size_t)nseg * NKS * 64 * DP;
+        e->tc_off_cand[l] = off; off += (size_t)nseg * NKS * 64 * DP;
+    }
+    if (off > e->tc_weights.cap) e->weights_dirty = true;
+    CU_TRY(e, e->tc_weights.reserve(off));
+    if (!e->weights_dirty) return GGNN_OK;
+    uint8_t* base = (uint8_t*)e->tc_weights.ptr;
+    for (int l = 0; l < e->L; ++l) {
+        const int nseg = e->nres[l] + 2;
+        auto launch = [&](const float* W, uint8_t* out, int segs, int src_ld, int src_col0) {
+            const long long total = (long long)segs * NKS * 2 * DP;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, 1024);
+            tc::ggnn_tile_weights_kernel<<<blocks, 256, 0, st>>>(W, out, D, DP, segs, src_ld, src_col0);
+            ++e->last_launches;
+        };
+        launch(e->w[l].edge_weights, base + e->tc_off_edge[l], T, D, 0);
+        if (e->cell == CELL_GRU) {
+            launch(e->w[l].gate_kernel, base + e->tc_off_gate_r[l], nseg, 2 * D, 0);
+            launch(e->w[l].gate_kernel, base + e->tc_off_gate_u[l], nseg, 2 * D, D);
+        }
+        launch(e->w[l].cand_kernel, base + e->tc_off_cand[l], nseg, D, 0);
+    }
+    CU_TRY(e, cudaGetLastError());
+    e->weights_dirty = false;
+    return GGNN_OK;
+}
+
+static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_t st) {
+    const int DP = e->DP;
+    int rc = tc_prepare_weights(e, st);
+    if (rc) return rc;
+    bool any_res = false;
+    for (int l = 0; l < e->L; ++l) any_res |= e->nres[l] > 0;
+    if (any_res) CU_TRY(e, e->tc_respre.reserve((size_t)e->ntiles * tc::TILE_M * 3 * DP * sizeof(float)));
+    tc::TcParams p;
+    memset(&p, 0, sizeof p);
+    p.V = e->V; p.D = e->D; p.DP = DP; p.T = e->T; p.L = e->L;
+    p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
+    p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
+    p.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
+    const size_t opb = (size_t)DP * 512, stage = (size_t)DP * 64;
+    // tile-local sparse graphs: stage the tile's CSR slice in shared memory when it is small enough
+    p.csr_cache = 0; p.csr_cap_msgs = 0;
+    size_t csr_b = 0;
+    if (e->local && e->gather_mode == GATHER_SPARSE && e->T <= 16 && e->max_tile_msgs <= 4096) {
+        p.csr_cache = 1;
+        p.csr_cap_msgs = (e->max_tile_msgs + 15) / 16 * 16;
+        csr_b = (size_t)((tc::TILE_M * e->T + 1 + 7) & ~7) * 2 + (size_t)p.csr_cap_msgs;
+    }
+    const size_t bias_b = (size_t)3 * DP * sizeof(float) + csr_b + 64;
+    const size_t avail = e->max_smem > 1024 ? e->max_smem - 1024 : 0;
+    if (avail < 3 * opb + bias_b + 2 * stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
+    p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - 3 * opb - bias_b) / stage);
+    if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(2, std::min(p.nstages, atoi(ns)));
+    p.fake_weights = getenv("GGNN_TC_FAKE_WEIGHTS") ? 1 : 0;
+    const size_t smem = 3 * opb + bias_b + (size_t)p.nstages * stage;
+    char* g = (char*)e->graph_buf.ptr;
+    p.tile_start = (const int*)(g + e->off_tiles);
+    p.tile_mask = (const unsigned*)(g + e->off_mask);
+    p.row_ptr = (const int*)(g + e->off_row_ptr);
+    p.csr_src = (const int*)(g + e->off_src);
+    p.dense_adj = (const float*)(g + e->off_adj);
+    p.indeg = (const float*)(g + e->off_indeg);
+    p.denom = (const float*)(g + e->off_denom);
+    const size_t vd = (size_t)std::max(e->V, 1) * e->D;
+    float* sb = (float*)e->state_buf.ptr;
+    p.state[0] = h0;
+    for (int l = 1; l <= e->L; ++l) {
+        float* ptr = (l == e->L) ? h_out : sb + (size_t)(l - 1) * vd;
+        p.state[l] = ptr; p.state_w[l] = ptr;
+    }
+    uint8_t* wb = (uint8_t*)e->tc_weights.ptr;
+    for (int l = 0; l < e->L; ++l) {
+        tc::TcLayer& ld = p.layer[l];
+        ld.w_edge = wb + e->tc_off_edge[l]; ld.w_gate_r = wb + e->tc_off_gate_r[l]; ld.w_gate_u = wb + e->tc_off_gate_u[l];
+        ld.w_cand = wb + e->tc_off_cand[l];
+        ld.edge_b = e->w[l].edge_biases; ld.gate_b = e->w[l].gate_bias; ld.cand_b = e->w[l].cand_bias;
+        ld.steps = e->steps[l]; ld.nres = e->nres[l];
+        for (int i = 0; i < MAX_RES; ++i) ld.res[i] = e->res[l][i];
+        p.step_base[l] = e->step_base[l];
+    }
+    if (e->save) {
+        float* s = (float*)e->save_bufs.ptr;
+        const size_t per = vd * (size_t)std::max(e->total_steps, 1);
+        p.save_buf.h_in = s; p.save_buf.agg = s + per; p.save_buf.r = s + 2 * per; p.save_buf.u = s + 3 * per; p.save_buf.c = s + 4 * per;
+    }
+    p.res_pre = (float*)e->tc_respre.ptr;
+    p.error_flag = (int*)e->err_flag.ptr;
+    p.dbg = nullptr;
+    if (getenv("GGNN_TC_DEBUG_TIMING")) {
+        CU_TRY(e, e->dbg_buf.reserve(64 * sizeof(long long)));
+        CU_TRY(e, cudaMemsetAsync(e->dbg_buf.ptr, 0, 64 * sizeof(long long), st));
+        p.dbg = (long long*)e->dbg_buf.ptr;
+    }
+    const size_t vd_bytes = (size_t)e->V * e->D * sizeof(float);
+    if (e->local) {
+        CU_TRY(e, cudaFuncSetAttribute(tc::ggnn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::ggnn_fwd_tc_kernel<true><<<e->ntiles, tc::NTHREADS, smem, st>>>(p);
+        ++e->last_launches;
+    } else {
+        CU_TRY(e, cudaFuncSetAttribute(tc::ggnn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float* tmp0 = sb + (size_t)(e->L - 1 > 0 ? e->L - 1 : 0) * vd;
+        float* tmp1 = tmp0 + vd;
+        for (int l = 0; l < e->L; ++l) {
+            const float* in = p.state[l];
+            if (e->steps[l] == 0) {
+                CU_TRY(e, cudaMemcpyAsync(p.state_w[l + 1], in, vd_bytes, cudaMemcpyDeviceToDevice, st));
+                continue;
+            }
+            for (int s = 0; s < e->steps[l]; ++s) {
+                float* out = (s == e->steps[l] - 1) ? p.state_w[l + 1] : ((s & 1) ? tmp1 : tmp0);
+                p.g_layer = l; p.g_step = s; p.g_in = in; p.g_out = out;
+                tc::ggnn_fwd_tc_kernel<false><<<e->ntiles, tc::NTHREADS, smem, st>>>(p);
+                ++e->last_launches;
+                in = out;
+            }
+        }
+    }
+    CU_TRY(e, cudaGetLastError());
+    if (e->save) e->saved_valid = true;
+    return GGNN_OK;
+}
+
 int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
     if (!e->weights_set) return e->fail(GGNN_ESTATE, "ggnn_set_weights has not been called");
@@ -549,6 +731,7 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
         if (h_out != h0) CU_TRY(e, cudaMemcpyAsync(h_out, h0, vd_bytes, cudaMemcpyDeviceToDevice, st));
         return GGNN_OK;
     }
+    if (e->precision != GGNN_PREC_FP32) return forward_tc(e, h0, h_out, st);
     FwdParams p;
     fill_params(e, p, h0, h_out);
     FwdKernel k = pick_fwd_kernel(e->variant, e->nb1, e->local);
@@ -600,6 +783,28 @@ int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, g
     if (rc) return rc;
     if (bytes) CU_TRY(e, cudaMemcpyAsync(h_out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
     CU_TRY(e, cudaStreamSynchronize(st));
+    return GGNN_OK;
+}
+
+int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaStreamSynchronize((cudaStream_t)stream));
+    int flag = 0;
+    CU_TRY(e, cudaMemcpy(&flag, e->err_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+        cudaMemset(e->err_flag.ptr, 0, sizeof(int));
+        return e->fail(GGNN_ECUDA, "propagation kernel reported a barrier timeout (role code %d)", flag);
+    }
+    return GGNN_OK;
+}
+
+int ggnn_debug_timestamps(ggnn_engine* e, int64_t* out64) {
+    if (!e || !out64) return GGNN_EINVAL;
+    if (!e->dbg_buf.ptr) return e->fail(GGNN_ESTATE, "no debug timestamps recorded (set GGNN_TC_DEBUG_TIMING=1)");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaDeviceSynchronize());
+    CU_TRY(e, cudaMemcpy(out64, e->dbg_buf.ptr, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     return GGNN_OK;
 }
 

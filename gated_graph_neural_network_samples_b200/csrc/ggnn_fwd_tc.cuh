@@ -1,0 +1,760 @@
+// Fused GGNN propagation on 5th-gen tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// One CTA owns a tile of up to 128 node rows (UMMA M = 128, cta_group::1).  hidden_size D is padded to
+// DP = roundup(D, 16) <= 128 inside the kernel only.  Per timestep (sparse:153-216):
+//   G1  agg   [128 x DP ]  = sum_t A_t[128 x DP] . W_t          (A_t = per-type sum of gathered source states)
+//   G2  gates [128 x 2DP]  = [agg | h] . K_g                     (+ residual pre-product, + b_g, sigmoid)
+//   G3  cand  [128 x DP ]  = [agg | r*h] . K_c                   (+ residual pre-product, + b_c, act)
+//   h' = u*h + (1-u)*cand
+// fp32 accuracy on bf16 tensor cores: every operand is split x = hi + lo (two bf16, 16 mantissa bits) and each
+// product is issued as 3 MMAs  Ah.Bh + Ah.Bl + Al.Bh  (the dropped Al.Bl term is 2^-16 relative); "fast" mode
+// issues Ah.Bh only.  Accumulators live in TMEM ([h fp32 | agg/cand acc | gate acc] = 4*DP <= 512 columns);
+// the fp32 master copy of the node states also lives in TMEM, so the recurrence never leaves the SM in LOCAL mode.
+//
+// Shared memory: three A-operand tiles (h, agg, A_t / r*h), each hi+lo in the canonical K-major no-swizzle UMMA
+// layout  byte(row, k) = part*(DP*256) + (k/8)*2048 + row*16 + (k%8)*2 ,  plus a ring of weight stages that a
+// producer thread fills with cp.async.bulk (1-D TMA) from a pre-split, pre-tiled bf16 copy of the weights.
+// Warp roles: warps 0-15 = workers (gather, epilogues; TMEM lane quarter = warp%4, column-chunk group = warp/4),
+// warp 16 = MMA issuer (one thread), warp 17 = weight producer (one thread) + TMEM allocator.
+// Every mbarrier wait is bounded; on timeout an error code is written and all roles drain.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ggnn_common.cuh"
+
+namespace ggnn {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane quarter
+constexpr int WARP_MMA = 16;
+constexpr int WARP_PROD = 17;
+constexpr int NTHREADS = 576;
+constexpr int MAX_STAGES = 8;
+
+struct TcLayer {
+    // pre-split (bf16 hi/lo), pre-tiled weights: one 64*DP-byte stage per K-step (16 rows) of a [K x DP] block
+    const uint8_t* w_edge;    // [T*DP/16]       W_t, t-major
+    const uint8_t* w_gate_r;  // [(R+2)*DP/16]   K_g columns [0,D)   rows: residual segments..., agg, h
+    const uint8_t* w_gate_u;  // [(R+2)*DP/16]   K_g columns [D,2D)
+    const uint8_t* w_cand;    // [(R+2)*DP/16]   K_c (RNN: the only kernel)
+    const float* edge_b;    // fp32 originals (unpadded)
+    const float* gate_b;
+    const float* cand_b;
+    int steps, nres;
+    int res[MAX_RES];
+};
+
+struct TcParams {
+    int V, D, DP, T, L;
+    int use_bias, use_avg, cell, act;
+    int gather_mode, dense_v, save;
+    int nparts;   // 3: bf16x3 (fp32-accurate), 1: single bf16 MMA
+    int nstages;  // weight ring depth
+    int csr_cache;      // LOCAL sparse only: the tile's CSR slice is staged in shared memory (uint16 row offsets, uint8 local sources)
+    int csr_cap_msgs;   // capacity of the shared source array
+    const int* tile_start;
+    const unsigned* tile_mask;
+    const int* row_ptr;
+    const int* csr_src;
+    const float* dense_adj;
+    const float* indeg;
+    const float* denom;
+    const float* state[MAX_LAYERS + 1];
+    float* state_w[MAX_LAYERS + 1];
+    TcLayer layer[MAX_LAYERS];
+    SaveDev save_buf;
+    int step_base[MAX_LAYERS];
+    float* res_pre;  // [ntiles][128][3*DP] fp32 scratch: residual pre-products of the current layer
+    int g_layer, g_step;
+    const float* g_in;
+    float* g_out;
+    int* error_flag;
+    int fake_weights;  // timing experiment only (GGNN_TC_FAKE_WEIGHTS=1): weight stages are loaded once and never refreshed -> WRONG results
+    long long* dbg;  // optional [64] clock64 stamps written by tile 0 / thread 0 (profiling aid), or nullptr
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait (~1 s at 2 GHz).  Returns false on timeout or if another role already aborted.
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity, volatile int* abort_flag) {
+    long long t0 = 0;
+    for (int it = 0;; ++it) {
+        uint32_t ok;
+        // the hardware suspends the thread (up to the hint, in ns) instead of spinning; it wakes on phase completion
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return true;
+        if (*abort_flag) return false;
+        __nanosleep(64);   // keep waiting warps off the issue ports: the MMA-issuing thread shares an SM sub-partition with them
+        if (it == 0) t0 = clock64();
+        else if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return false; }
+    }
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try(addr, parity)) return true;
+    return mbar_wait_slow(addr, parity, abort_flag);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+// issue only; the destination registers are valid after tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                   "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor: K-major, SWIZZLE_NONE, version 1 (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: kind::f16, A/B = BF16, D = F32, both K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc_bf16(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {   // true in exactly one (converged) lane
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// x = hi + lo with hi, lo bf16 (round to nearest): 16 mantissa bits kept
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);   // one packed cvt
+        h[j] = *reinterpret_cast<const uint32_t*>(&hp);
+        const float r0 = x[2 * j] - __uint_as_float(h[j] << 16);
+        const float r1 = x[2 * j + 1] - __uint_as_float(h[j] & 0xFFFF0000u);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
+        l[j] = *reinterpret_cast<const uint32_t*>(&lp);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void unpack8_add(const uint4& a, float (&acc)[8], float scale) {
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        acc[2 * j] = fmaf(scale, __uint_as_float(w[j] << 16), acc[2 * j]);
+        acc[2 * j + 1] = fmaf(scale, __uint_as_float(w[j] & 0xFFFF0000u), acc[2 * j + 1]);
+    }
+}
+__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float act_fast(float v, int act) {
+    return act == ACT_TANH ? (1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v))) : fmaxf(v, 0.0f);
+}
+
+// store one [row, 8-column chunk] of an A operand (both parts)
+__device__ __forceinline__ void store_operand_chunk(uint8_t* op, int DP, int kc, int row, const float (&x)[8]) {
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    uint8_t* p = op + (size_t)kc * 2048 + (size_t)row * 16;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + (size_t)DP * 256) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// 8-wide helpers on [row, 8-column chunk] tiles.  D % 4 == 0, so every float4 of a chunk is entirely inside or
+// entirely outside the D real columns.
+__device__ __forceinline__ void load8_guarded(const float* base, int col0, int D, float (&v)[8]) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (col0 + 4 <= D) a = *reinterpret_cast<const float4*>(base + col0);
+    if (col0 + 8 <= D) b = *reinterpret_cast<const float4*>(base + col0 + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8_guarded_cg(const float* base, int col0, int D, float (&v)[8]) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (col0 + 4 <= D) a = __ldcg(reinterpret_cast<const float4*>(base + col0));
+    if (col0 + 8 <= D) b = __ldcg(reinterpret_cast<const float4*>(base + col0 + 4));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8_guarded(float* base, int col0, int D, const float (&v)[8]) {
+    if (col0 + 4 <= D) *reinterpret_cast<float4*>(base + col0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (col0 + 8 <= D) *reinterpret_cast<float4*>(base + col0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void lds8(const float* s, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+template <bool LOCAL>
+__global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_w_full[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_w_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_a_ready;
+    __shared__ __align__(8) uint64_t bar_mma_done;
+    __shared__ __align__(8) uint64_t bar_g1_done[2];   // one per gather buffer (opA, opX): its MMAs are complete
+    __shared__ __align__(8) uint64_t bar_g_ready[2];   // one per gather buffer: A_t written (never more than one phase pending each)
+    __shared__ __align__(8) uint64_t bar_workers;
+    __shared__ uint32_t s_tmem_base;
+    __shared__ int s_abort;
+
+    const int D = p.D, DP = p.DP, T = p.T;
+    const int NKC = DP >> 3;   // 8-column chunks per DP
+    const int NKS = DP >> 4;   // UMMA K-steps (16) per DP-wide operand
+    const uint32_t OPB = (uint32_t)DP * 512u;          // bytes per A operand (hi + lo)
+    const uint32_t STAGE_B = (uint32_t)DP * 64u;       // bytes per weight stage (K = 16 x N = DP, hi + lo)
+    uint8_t* opH = smem;
+    uint8_t* opX = opH + OPB;
+    uint8_t* opA = opX + OPB;
+    uint8_t* ring = opA + OPB;                             // nstages x STAGE_B, 1024-byte aligned (DP*512 and DP*64 are multiples of 1024)
+    float* sBias = reinterpret_cast<float*>(ring + (size_t)p.nstages * STAGE_B);   // [3*DP]: gate r | gate u | cand, zero padded
+    uint16_t* sRowPtr = reinterpret_cast<uint16_t*>(sBias + 3 * DP);              // [128*T + 1] (csr_cache)
+    uint8_t* sSrc = reinterpret_cast<uint8_t*>(sRowPtr + ((TILE_M * T + 1 + 7) & ~7)); // [csr_cap_msgs]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = blockIdx.x;
+    const int row0 = p.tile_start[tile];
+    const int rows = p.tile_start[tile + 1] - row0;
+    const unsigned tmask = p.tile_mask[tile];
+    const size_t VD = (size_t)p.V * D;
+    const int nst = p.nstages;
+
+    if (tid == 0) {
+        s_abort = 0;
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+        mbar_init(&bar_a_ready, NUM_WORKERS / 32);   // one arrival per worker warp
+        mbar_init(&bar_mma_done, 1);
+        mbar_init(&bar_g1_done[0], 1);
+        mbar_init(&bar_g1_done[1], 1);
+        mbar_init(&bar_g_ready[0], NUM_WORKERS / 32);
+        mbar_init(&bar_g_ready[1], NUM_WORKERS / 32);
+        mbar_init(&bar_workers, NUM_WORKERS / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == WARP_PROD) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const uint32_t TM_H = tmem, TM_ACC = tmem + (uint32_t)DP, TM_GATE = tmem + 2u * (uint32_t)DP;
+    volatile int* abortp = &s_abort;
+
+    const int l_begin = LOCAL ? 0 : p.g_layer;
+    const int l_end = LOCAL ? p.L : p.g_layer + 1;
+
+    if (warp < NUM_WORKERS / 32) {
+        // =============================================================================== WORKERS
+        const int q = warp & 3, cg = warp >> 2;      // TMEM lane quarter, column-chunk group
+        constexpr int NCG = NUM_WORKERS / 128;       // chunk groups (warps per lane quarter)
+        const int row = q * 32 + lane;               // tile row == TMEM lane
+        const bool row_ok = row < rows;
+        const int grow = row_ok ? row0 + row : row0; // global node id (clamped for padding rows)
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t ph_done = 0;                         // parity of bar_mma_done
+        uint32_t ph_wk = 0;                           // parity of bar_workers
+        bool ok = true;
+        uint32_t ph_g1 = 0;                           // bit b = parity of bar_g1_done[b]
+        auto workers_sync = [&]() {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_workers);
+            if (!mbar_wait(&bar_workers, ph_wk & 1, abortp)) ok = false;
+            ++ph_wk;
+        };
+        auto wait_mma = [&]() { if (ok) { ok = mbar_wait(&bar_mma_done, ph_done & 1, abortp); ++ph_done; if (ok) tc_fence_after(); } };
+        auto wait_g1 = [&](int b) { if (ok) { ok = mbar_wait(&bar_g1_done[b], (ph_g1 >> b) & 1u, abortp); ph_g1 ^= 1u << b; if (ok) tc_fence_after(); } };
+        // every lane orders its own smem/TMEM writes, then one lane per warp signals the MMA thread
+        auto publish = [&]() { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_a_ready); };
+        auto publish_g = [&](int b) { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_g_ready[b]); };
+        float* res_pre = p.res_pre + (size_t)tile * TILE_M * 3 * DP + (size_t)row * 3 * DP;
+        int dbg_i = 0;
+        auto stamp = [&]() { if (p.dbg && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); };
+        stamp();   // 0: start
+
+        // ---- initial state: global fp32 -> TMEM (fp32 master) + opH (bf16 hi/lo)
+        {
+            const float* hin = (LOCAL ? p.state[0] : p.g_in) + (size_t)grow * D;
+            for (int kc = cg; kc < NKC; kc += NCG) {
+                float v[8];
+                load8_guarded_cg(hin, kc * 8, row_ok ? D : 0, v);
+                tmem_st8(TM_H + lane_addr + kc * 8, v);
+                store_operand_chunk(opH, DP, kc, row, v);
+            }
+            tmem_st_wait();
+        }
+        const bool csr_smem = LOCAL && p.csr_cache && p.gather_mode == GATHER_SPARSE;
+        if (csr_smem) {
+            const int base = p.row_ptr[(size_t)row0 * T];
+            const int nptr = rows * T + 1;
+            for (int i = tid; i < TILE_M * T + 1; i += NUM_WORKERS) sRowPtr[i] = (uint16_t)(p.row_ptr[(size_t)row0 * T + min(i, nptr - 1)] - base);
+            const int mt = p.row_ptr[(size_t)(row0 + rows) * T] - base;
+            for (int i = tid; i < mt; i += NUM_WORKERS) sSrc[i] = (uint8_t)(p.csr_src[base + i] - row0);
+        }
+        workers_sync();
+        stamp();   // 1: state loaded
+
+        for (int l = l_begin; l < l_end && ok; ++l) {
+            const TcLayer& ly = p.layer[l];
+            const int s_begin = LOCAL ? 0 : p.g_step;
+            const int s_end = LOCAL ? ly.steps : p.g_step + 1;
+            const bool gru = p.cell == CELL_GRU;
+            // ---- this layer's cell biases -> shared (zero padded to DP)
+            for (int i = tid; i < 3 * DP; i += NUM_WORKERS) {
+                const int blk = i / DP, col = i - blk * DP;
+                float b = 0.0f;
+                if (col < D) b = (blk < 2) ? (gru ? ly.gate_b[blk * D + col] : 0.0f) : ly.cand_b[col];
+                sBias[i] = b;
+            }
+            workers_sync();
+            // ---- residual pre-products (constant over the layer's timesteps): Pg = res . K_g[res rows], Pc = res . K_c[res rows]
+            if (ly.nres > 0 && s_end > s_begin) {
+                for (int i = 0; i < ly.nres && ok; ++i) {
+                    if (i > 0) wait_mma();
+                    if (!ok) break;
+                    const float* rs = p.state[ly.res[i]] + (size_t)grow * D;
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float v[8];
+                        load8_guarded_cg(rs, kc * 8, row_ok ? D : 0, v);
+                        store_operand_chunk(opA, DP, kc, row, v);
+                    }
+                    publish();
+                }
+                wait_mma();
+                if (ok) {
+                    const int ngate = gru ? 2 * NKC : 0;
+                    for (int c = cg; c < ngate + NKC; c += NCG) {   // gate chunks [0,2NKC) then cand chunks
+                        float v[8];
+                        tmem_ld8((c < ngate ? TM_GATE + c * 8 : TM_ACC + (c - ngate) * 8) + lane_addr, v);
+                        float* dst = res_pre + (c < ngate ? c * 8 : 2 * DP + (c - ngate) * 8);
+                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    }
+                    tc_fence_before();
+                    workers_sync();
+                }
+            }
+            for (int s = s_begin; s < s_end && ok; ++s) {
+                const size_t save_off = (size_t)(p.step_base[l] + s) * VD + (size_t)grow * D;
+                // ------------------------------------------------------------ gather + G1 per present type
+                // A_t tiles alternate between opA and opX so that gathering type n+1 overlaps the MMAs of type n
+                int nty = 0;
+                for (int t = 0; t < T && ok; ++t) {
+                    if (!((tmask >> t) & 1u)) continue;
+                    const int b = nty & 1;
+                    if (nty >= 2) { wait_g1(b); if (!ok) break; }   // the MMAs that read this buffer two types ago are done
+                    uint8_t* gdst = b ? opX : opA;
+                    ++nty;
+                    int beg = 0, end = 0, dg = 0, di = 0;
+                    if (row_ok) {
+                        if (p.gather_mode == GATHER_SPARSE) {
+                            if (csr_smem) { beg = sRowPtr[row * T + t]; end = sRowPtr[row * T + t + 1]; }
+                            else { beg = p.row_ptr[(size_t)grow * T + t]; end = p.row_ptr[(size_t)grow * T + t + 1]; }
+                        } else { dg = grow / p.dense_v; di = grow - dg * p.dense_v; }
+                    }
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float acc[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+                        if (p.gather_mode == GATHER_SPARSE) {
+                            for (int m = beg; m < end; ++m) {
+                                if (LOCAL) {
+                                    const int sl = csr_smem ? (int)sSrc[m] : (p.csr_src[m] - row0);
+                                    const uint8_t* sp = opH + (size_t)kc * 2048 + (size_t)sl * 16;
+                                    unpack8_add(*reinterpret_cast<const uint4*>(sp), acc, 1.0f);
+                                    if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + (size_t)DP * 256), acc, 1.0f);
+                                } else {
+                                    float hv[8];
+                                    load8_guarded_cg(p.g_in + (size_t)p.csr_src[m] * D, kc * 8, D, hv);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) acc[j] += hv[j];
+                                }
+                            }
+                        } else if (row_ok) {
+                            const int nv = p.dense_v;
+                            const float* arow = p.dense_adj + (((size_t)dg * T + t) * nv + di) * nv;
+                            for (int jn = 0; jn < nv; ++jn) {
+                                const float a = arow[jn];
+                                if (a != 0.0f) {
+                                    const int src = dg * nv + jn;
+                                    if (LOCAL) {
+                                        const uint8_t* sp = opH + (size_t)kc * 2048 + (size_t)(src - row0) * 16;
+                                        unpack8_add(*reinterpret_cast<const uint4*>(sp), acc, a);
+                                        if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + (size_t)DP * 256), acc, a);
+                                    } else {
+                                        float hv[8];
+                                        load8_guarded_cg(p.g_in + (size_t)src * D, kc * 8, D, hv);
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(a, hv[j], acc[j]);
+                                    }
+                                }
+                            }
+                        }
+                        store_operand_chunk(gdst, DP, kc, row, acc);
+                    }
+                    publish_g(b);
+                    stamp();   // gather of one type done
+                }
+                if (!ok) break;
+                const bool have_msgs = nty > 0;
+                // all G1 MMAs complete (last use of each gather buffer) before opX is rewritten / the accumulators are read
+                if (nty >= 2) wait_g1((nty - 2) & 1);
+                if (nty >= 1) wait_g1((nty - 1) & 1);
+                if (!ok) break;
+                stamp();   // G1 done (agg accumulators ready)
+                // ------------------------------------------------------------ agg epilogue: + indeg.B, / (deg + 1e-7) -> opX
+                {
+                    const float inv_den = (p.use_avg && row_ok) ? __fdividef(1.0f, p.denom[grow]) : 1.0f;
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float v[8];
+                        if (have_msgs) tmem_ld8(TM_ACC + lane_addr + kc * 8, v);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+                        }
+                        if (p.use_bias) {
+                            for (int t = 0; t < T; ++t) {
+                                const float ind = p.indeg[(size_t)grow * T + t];
+                                float b[8];
+                                load8_guarded(ly.edge_b + (size_t)t * D, kc * 8, D, b);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(ind, b[j], v[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = row_ok ? v[j] * inv_den : 0.0f;
+                        if (p.save && row_ok) store8_guarded(p.save_buf.agg + save_off, kc * 8, D, v);
+                        store_operand_chunk(opX, DP, kc, row, v);
+                    }
+                    publish();
+                }
+                stamp();   // agg epilogue done
+                if (gru) {
+                    // -------------------------------------------------------- r ready: r*h -> opA  (u and the candidate's agg part keep the tensor core busy meanwhile)
+                    wait_mma(); if (!ok) break;
+                    stamp();   // gates ready
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float g[8], h[8], b[8], rh[8];
+                        tmem_ld8_nowait(TM_GATE + lane_addr + kc * 8, g);
+                        tmem_ld8_nowait(TM_H + lane_addr + kc * 8, h);
+                        lds8(sBias + kc * 8, b);
+                        if (ly.nres > 0) {
+                            float rp[8];
+                            lds8(res_pre + kc * 8, rp);   // generic load (global)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) b[j] += rp[j];
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { g[j] = sigmoid_fast(g[j] + b[j]); rh[j] = g[j] * h[j]; }
+                        if (p.save && row_ok) {
+                            store8_guarded(p.save_buf.r + save_off, kc * 8, D, g);
+                            store8_guarded(p.save_buf.h_in + save_off, kc * 8, D, h);
+                        }
+                        store_operand_chunk(opA, DP, kc, row, rh);
+                    }
+                    publish();
+                    stamp();   // r*h epilogue done
+                }
+                // ------------------------------------------------------------ candidate ready: new state
+                wait_mma(); if (!ok) break;
+                stamp();   // candidate ready
+                {
+                    const bool last_of_layer = (s == ly.steps - 1);
+                    float* outp = LOCAL ? (last_of_layer ? p.state_w[l + 1] : nullptr) : p.g_out;
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float c[8], h[8], u[8], bc[8], hn[8];
+                        tmem_ld8_nowait(TM_ACC + lane_addr + kc * 8, c);
+                        lds8(sBias + 2 * DP + kc * 8, bc);
+                        if (gru) {
+                            float bu[8];
+                            tmem_ld8_nowait(TM_GATE + lane_addr + DP + kc * 8, u);
+                            tmem_ld8_nowait(TM_H + lane_addr + kc * 8, h);
+                            lds8(sBias + DP + kc * 8, bu);
+                            if (ly.nres > 0) {
+                                float rp[8];
+                                lds8(res_pre + DP + kc * 8, rp);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) bu[j] += rp[j];
+                                lds8(res_pre + 2 * DP + kc * 8, rp);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) bc[j] += rp[j];
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                u[j] = sigmoid_fast(u[j] + bu[j]);
+                                c[j] = act_fast(c[j] + bc[j], p.act);
+                                hn[j] = fmaf(u[j], h[j] - c[j], c[j]);   // u*h + (1-u)*c
+                            }
+                            if (p.save && row_ok) {
+                                store8_guarded(p.save_buf.u + save_off, kc * 8, D, u);
+                                store8_guarded(p.save_buf.c + save_off, kc * 8, D, c);
+                            }
+                        } else {
+                            if (p.save) tmem_ld8_nowait(TM_H + lane_addr + kc * 8, h);
+                            if (ly.nres > 0) {
+                                float rp[8];
+                                lds8(res_pre + 2 * DP + kc * 8, rp);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) bc[j] += rp[j];
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) hn[j] = act_fast(c[j] + bc[j], p.act);
+                            if (p.save && row_ok) store8_guarded(p.save_buf.h_in + save_off, kc * 8, D, h);
+                        }
+                        tmem_st8(TM_H + lane_addr + kc * 8, hn);
+                        store_operand_chunk(opH, DP, kc, row, hn);
+                        if (outp && row_ok) store8_guarded(outp + (size_t)grow * D, kc * 8, D, hn);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    workers_sync();   // opH complete before anyone gathers from it
+                    stamp();   // state update done
+                }
+            }  // steps
+            if (LOCAL && ok && ly.steps == 0) {   // a layer without timesteps aliases the previous state (sparse:152)
+                for (int kc = cg; kc < NKC; kc += NCG) {
+                    float h[8];
+                    tmem_ld8(TM_H + lane_addr + kc * 8, h);
+                    if (row_ok) store8_guarded(p.state_w[l + 1] + (size_t)grow * D, kc * 8, D, h);
+                }
+            }
+            if (LOCAL && l + 1 < l_end) { __threadfence(); workers_sync(); }   // layer output visible before it is read as a residual
+        }  // layers
+        if (!ok && lane == 0) atomicExch(p.error_flag, 1);
+    } else if (warp == WARP_MMA) {
+        // =============================================================================== MMA ISSUER
+        // The whole warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.
+        // (A single-lane `if (lane == 0)` loop makes nvcc wrap every MMA in a lane-serialising ELECT loop and costs
+        // ~640 cycles per K-step; this form issues at the tensor pipe's ~68-cycle-per-instruction floor.)
+        {
+            const bool x3 = p.nparts == 3;
+            const bool fake = p.fake_weights != 0;
+            const uint32_t nstg = (uint32_t)nst;
+            const uint32_t a_lo16 = ((uint32_t)DP * 256u) >> 4;   // hi -> lo part of an A operand (16-byte units)
+            const uint32_t b_lo16 = ((uint32_t)DP * 32u) >> 4;    // hi -> lo part of a weight stage
+            const uint32_t stage16 = STAGE_B >> 4;
+            const uint64_t descA = make_desc(0, 2048, 128);
+            const uint64_t descB = make_desc(smem_u32(ring), 16u * (uint32_t)DP, 128);
+            const uint32_t opH16 = smem_u32(opH) >> 4, opX16 = smem_u32(opX) >> 4, opA16 = smem_u32(opA) >> 4;
+            const uint32_t full0 = smem_u32(&bar_w_full[0]), empty0 = smem_u32(&bar_w_empty[0]);
+            const uint32_t idesc = make_idesc_bf16(DP);
+            const bool dbg_on = p.dbg && tile == 0 && lane == 0;
+            long long dbg_wfull = 0, dbg_ready = 0;
+            const long long dbg_t0 = clock64();
+            uint32_t ph_ready = 0, ph_g = 0, stage = 0, full_par = 0;
+            bool ok = true;
+            // acc(tm_d) (+)= A(op) . B(next NKS weight stages): NKS K-steps of 1 or 3 MMAs
+            int dbg_g = 0;
+            auto gemm = [&](uint32_t op16, uint32_t tm_d, uint32_t& accum) {
+                if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
+                uint64_t ad = descA | (uint64_t)op16;
+#pragma unroll 1
+                for (int ks = 0; ks < NKS && ok; ++ks) {
+                    if (!(fake && full_par)) {
+                        const uint32_t fb = full0 + stage * 8u;
+                        if (!mbar_try(fb, full_par)) {
+                            const long long w0 = dbg_on ? clock64() : 0;
+                            if (!mbar_wait_slow(fb, full_par, abortp)) ok = false;
+                            if (dbg_on) dbg_wfull += clock64() - w0;
+                        }
+                    }
+                    ok = __all_sync(0xffffffffu, ok);
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint64_t bd = descB + (uint64_t)(stage * stage16);
+                    if (elect_one()) {
+                        umma_bf16(tm_d, ad, bd, idesc, accum);
+                        if (x3) {
+                            umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
+                            umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
+                        }
+                        if (!fake)   // stage reusable once these MMAs have read it
+                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + stage * 8u) : "memory");
+                    }
+                    __syncwarp();
+                    accum = 1u;
+                    ad += 256;   // next K-step of the A operand: 4096 bytes
+                    if (++stage == nstg) { stage = 0; full_par ^= 1u; }
+                }
+            };
+            auto commit_to = [&](uint64_t* bar) { if (ok) { if (elect_one()) umma_commit(bar); __syncwarp(); } };
+            auto wait_bar = [&](uint32_t rb, uint32_t par) {
+                if (!ok) return;
+                if (!mbar_try(rb, par)) {
+                    const long long w0 = dbg_on ? clock64() : 0;
+                    if (!mbar_wait_slow(rb, par, abortp)) ok = false;
+                    if (dbg_on) dbg_ready += clock64() - w0;
+                }
+                ok = __all_sync(0xffffffffu, ok);
+                tc_fence_after();
+            };
+            auto wait_ready = [&]() { wait_bar(smem_u32(&bar_a_ready), ph_ready & 1); ++ph_ready; };
+            auto wait_g_ready = [&](int b) { wait_bar(smem_u32(&bar_g_ready[b]), (ph_g >> b) & 1u); ph_g ^= 1u << b; };
+            for (int l = l_begin; l < l_end && ok; ++l) {
+                const TcLayer& ly = p.layer[l];
+                const int s_begin = LOCAL ? 0 : p.g_step;
+                const int s_end = LOCAL ? ly.steps : p.g_step + 1;
+                const int nres = ly.nres;
+                const bool gru = p.cell == CELL_GRU;
+                if (nres > 0 && s_end > s_begin) {
+                    uint32_t f_r = 0, f_u = 0, f_c = 0;
+                    for (int i = 0; i < nres && ok; ++i) {
+                        wait_ready();
+                        if (gru) { gemm(opA16, TM_GATE, f_r); gemm(opA16, TM_GATE + DP, f_u); }
+                        gemm(opA16, TM_ACC, f_c);
+                        commit_to(&bar_mma_done);
+                    }
+                }
+                for (int s = s_begin; s < s_end && ok; ++s) {
+                    uint32_t f_agg = 0;
+                    int nty = 0;
+                    for (int t = 0; t < T && ok; ++t) {
+                        if (!((tmask >> t) & 1u)) continue;
+                        wait_g_ready(nty & 1);
+                        gemm((nty & 1) ? opX16 : opA16, TM_ACC, f_agg);
+                        commit_to(&bar_g1_done[nty & 1]);
+                        ++nty;
+                    }
+                    wait_ready();                                   // agg operand (opX) ready
+                    uint32_t f_c = 0;
+                    if (gru) {
+                        uint32_t f_r = 0, f_u = 0;
+                        gemm(opX16, TM_GATE, f_r); gemm(opH16, TM_GATE, f_r);
+                        commit_to(&bar_mma_done);                   // r ready
+                        gemm(opX16, TM_GATE + DP, f_u); gemm(opH16, TM_GATE + DP, f_u);
+                        gemm(opX16, TM_ACC, f_c);
+                        wait_ready();                               // r*h operand (opA) ready
+                        gemm(opA16, TM_ACC, f_c);
+                    } else {
+                        gemm(opX16, TM_ACC, f_c); gemm(opH16, TM_ACC, f_c);
+                    }
+                    commit_to(&bar_mma_done);                       // candidate ready
+                }
+            }
+            if (!ok && lane == 0) atomicExch(p.error_flag, 2);
+            if (dbg_on) { p.dbg[60] = dbg_wfull; p.dbg[61] = dbg_ready; p.dbg[62] = clock64() - dbg_t0; }
+        }
+    } else {
+        // =============================================================================== WEIGHT PRODUCER
+        if (lane == 0) {
+            uint32_t stage = 0, lap = 0;
+            bool ok = true;
+            // stream one DP x DP weight block (NKS stages) starting at K-step index ks0 of a pre-tiled matrix
+            auto push_block = [&](const uint8_t* mat, int ks0) {
+                for (int ks = 0; ks < NKS && ok; ++ks) {
+                    if (p.fake_weights && lap > 0) { if (++stage == (uint32_t)nst) { stage = 0; ++lap; } continue; }   // timing experiment only
+                    // a stage is free once the MMAs that read its previous contents have completed (first lap: free)
+                    if (lap > 0 && !mbar_wait(&bar_w_empty[stage], (lap - 1) & 1, abortp)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&bar_w_full[stage], STAGE_B);
+                    bulk_copy_g2s(ring + stage * STAGE_B, mat + (size_t)(ks0 + ks) * STAGE_B, STAGE_B, &bar_w_full[stage]);
+                    if (++stage == (uint32_t)nst) { stage = 0; ++lap; }
+                }
+            };
+            for (int l = l_begin; l < l_end && ok; ++l) {
+                const TcLayer& ly = p.layer[l];
+                const int s_begin = LOCAL ? 0 : p.g_step;
+                const int s_end = LOCAL ? ly.steps : p.g_step + 1;
+                const bool gru = p.cell == CELL_GRU;
+                const int kx = ly.nres * NKS, kh = (ly.nres + 1) * NKS;
+                if (ly.nres > 0 && s_end > s_begin) {
+                    for (int i = 0; i < ly.nres && ok; ++i) {
+                        if (gru) { push_block(ly.w_gate_r, i * NKS); push_block(ly.w_gate_u, i * NKS); }
+                        push_block(ly.w_cand, i * NKS);
+                    }
+                }
+                for (int s = s_begin; s < s_end && ok; ++s) {
+                    for (int t = 0; t < T && ok; ++t) {
+                        if (!((tmask >> t) & 1u)) continue;
+                        push_block(ly.w_edge, t * NKS);
+                    }
+                    if (gru) {
+                        push_block(ly.w_gate_r, kx); push_block(ly.w_gate_r, kh);
+                        push_block(ly.w_gate_u, kx); push_block(ly.w_gate_u, kh);
+                    }
+                    push_block(ly.w_cand, kx); push_block(ly.w_cand, kh);
+                }
+            }
+            if (!ok) atomicExch(p.error_flag, 3);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == WARP_PROD) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weight pre-tiling
+// fp32 row-major W[(nseg*D) rows][src_ld cols]; the D columns starting at src_col0 are tiled  ->  per K-step s
+// (16 padded rows) one contiguous stage of 64*DP bytes
+//   byte(s, part, c, n, j) = s*(64*DP) + part*(32*DP) + c*(16*DP) + n*16 + j*2
+// holding bf16 part (0 = hi, 1 = lo) of W[row(s*16 + c*8 + j)][src_col0 + n]; padded rows/cols (>= D inside a
+// DP-wide segment / n >= D) are zero.
+__global__ void ggnn_tile_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int D, int DP, int nseg,
+                                         int src_ld, int src_col0) {
+    const int ksteps = nseg * DP / 16;
+    const long long total = (long long)ksteps * 2 * DP;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % DP);
+        const int c = (int)((idx / DP) % 2);
+        const int s = (int)(idx / (2 * DP));
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kp = s * 16 + c * 8 + j;
+            const int seg = kp / DP, kk = kp - seg * DP;
+            x[j] = (kk < D && n < D) ? W[(size_t)(seg * D + kk) * src_ld + src_col0 + n] : 0.0f;
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        uint8_t* base = out + (size_t)s * 64 * DP + (size_t)c * 16 * DP + (size_t)n * 16;
+        *reinterpret_cast<uint4*>(base) = hi;
+        *reinterpret_cast<uint4*>(base + (size_t)32 * DP) = lo;
+    }
+}
+
+}  // namespace tc
+}  // namespace ggnn

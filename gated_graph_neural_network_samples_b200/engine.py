@@ -175,6 +175,10 @@ class PropagationEngine:
         self._check(self.lib.ggnn_forward_host(self._h, h0.ctypes.data, out.ctypes.data, self._stream()))
         return out
 
+    def sync_check(self):
+        """Synchronise the stream and raise if a kernel reported an (always bounded) barrier timeout."""
+        self._check(self.lib.ggnn_sync_check(self._h, self._stream()))
+
     def set_save_for_backward(self, enable: bool):
         self._check(self.lib.ggnn_set_save_for_backward(self._h, int(bool(enable))))
 

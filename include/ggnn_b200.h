@@ -111,6 +111,9 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
 /* Same with HOST buffers: H2D copy of h0, propagation, D2H copy of the result, stream-synchronised. */
 int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
 
+/* Synchronises `stream` and reports asynchronous kernel-side failures (a bounded barrier wait that expired). */
+int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream);
+
 /* Gradient of the propagation (what optimizer.compute_gradients builds, chem_tensorflow.py:184).
  * Must follow a ggnn_forward on the same graph with save_for_backward enabled.
  * d_h_out: DEVICE [V, D]; grads: per layer, accumulated into; d_h0: DEVICE [V, D] or NULL. */
@@ -129,6 +132,9 @@ int ggnn_copy_layer_state(ggnn_engine* e, int32_t layer, float* dst, ggnn_stream
 /* Kernel launches issued by the last forward / backward call, and plan description text. */
 int ggnn_last_launch_count(const ggnn_engine* e);
 const char* ggnn_plan_description(const ggnn_engine* e);
+/* Profiling aid: with GGNN_TC_DEBUG_TIMING=1 tile 0 of the tensor-core kernel records clock64() at its phase
+ * boundaries; this copies the 64 stamps of the last launch to out64[64]. */
+int ggnn_debug_timestamps(ggnn_engine* e, int64_t* out64);
 
 #ifdef __cplusplus
 }

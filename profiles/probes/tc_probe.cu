@@ -180,6 +180,243 @@ static void run_umma(int N, int K, int reps) {
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dc); cudaFree(ds);
 }
 
+
+// ---------------------------------------------------------------------------------- issue-path cost of the MMA loop
+// mode 0: MMAs only (descriptors precomputed)   1: + tcgen05.commit every 3 MMAs   2: + try_wait on a completed mbarrier every 3 MMAs
+__global__ void __launch_bounds__(128) umma_issue_probe(int N, int nmma, int mode, long long* cycles, int* status) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar, bar2, bar3;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (7 * 4096 * 2 + 8 * 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar2)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar3)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar3)) : "memory");   // bar3: phase 0 complete
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_smem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(128, N, 1);
+        const uint64_t ad0 = make_smem_desc(smem_u32(smem), 128 * 16, 128);
+        const uint64_t bd0 = make_smem_desc(smem_u32(smem) + 7 * 4096 * 2, (uint32_t)N * 16, 128);
+        uint64_t ad = ad0, bd = bd0;
+        const long long t0 = clock64();
+        long long sink = 0;
+        for (int i = 0; i < nmma; i += 3) {
+            if (mode & 4) {   // fresh operand addresses every group (7 K-steps of A, 8 weight stages), like the engine
+                const uint32_t ks = (uint32_t)(i / 3) % 7u, stg = (uint32_t)(i / 3) % 8u;
+                ad = ad0 + ((ks * 4096u) >> 4);
+                bd = bd0 + ((stg * 7168u) >> 4);
+            }
+            if (mode & 8) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (mode & 16) sink += clock64();
+            if ((mode & 3) >= 2) {
+                uint32_t ok;
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(ok) : "r"(smem_u32(&bar3)), "r"(0u) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            umma<0>(tmem, ad, bd, idesc, 1u);
+            umma<0>(tmem, ad, bd + 2, idesc, 1u);
+            umma<0>(tmem, ad + 2, bd, idesc, 1u);
+            if ((mode & 3) >= 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar2)) : "memory");
+        }
+        const long long t1 = clock64();
+        if (sink == 12345) cycles[1] = sink;
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+        const bool ok = mbar_wait_bounded(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        cycles[0] = t1 - t0; cycles[1] = t2 - t0;
+        *status = ok ? 1 : 2;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+}
+
+static void run_issue_probe(int N, int nmma, int mode) {
+    long long* dc; int* ds;
+    CK(cudaMalloc(&dc, 16)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+    size_t smem = 7 * 4096 * 2 + 8 * 16384 + 256;
+    CK(cudaFuncSetAttribute(umma_issue_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_issue_probe<<<1, 128, smem>>>(N, nmma, mode, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("issue probe error %s\n", cudaGetErrorString(e)); exit(2); }
+    long long c[2]; int st;
+    CK(cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+    printf("issue probe N=%3d nmma=%4d mode=%d status=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", N, nmma, mode, st,
+           (double)c[0] / nmma, (double)c[1] / nmma);
+    cudaFree(dc); cudaFree(ds);
+}
+
+
+// ---------------------------------------------------------------------------------- MMA rate vs shared-memory layout
+// layout: 0 = no swizzle (LBO = rows*16, SBO = 128), 6 = SWIZZLE_32B (SBO 256), 4 = SWIZZLE_64B (SBO 512), 2 = SWIZZLE_128B (SBO 1024)
+// Operands hold constants, so only the fetch pattern differs.  A K-step advances the start address by the layout's
+// K-step stride; weight stages rotate over 8 slots; 3 MMAs per group (hi.hi, hi.lo, lo.hi pattern: A part +28 KB / B part +half stage).
+__global__ void __launch_bounds__(128) umma_layout_probe(int N, int nmma, int layout, long long* cycles, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (2 * 32768 + 8 * 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_smem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(128, N, 1);
+        uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstride, a_part = 32768, b_part = 8192;
+        if (layout == 0) { a_lbo = 2048; a_sbo = 128; b_lbo = (uint32_t)N * 16; b_sbo = 128; a_kstride = 4096; }
+        else if (layout == 6) { a_lbo = 16; a_sbo = 256; b_lbo = 16; b_sbo = 256; a_kstride = 4096; }
+        else if (layout == 4) { a_lbo = 16; a_sbo = 512; b_lbo = 16; b_sbo = 512; a_kstride = 32; }
+        else { a_lbo = 16; a_sbo = 1024; b_lbo = 16; b_sbo = 1024; a_kstride = 32; }
+        const uint64_t lt = (uint64_t)layout << 61;
+        const uint64_t ad0 = make_smem_desc(smem_u32(smem), a_lbo, a_sbo) | lt;
+        const uint64_t bd0 = make_smem_desc(smem_u32(smem) + 2 * 32768, b_lbo, b_sbo) | lt;
+        const long long t0 = clock64();
+        for (int i = 0; i < nmma; i += 3) {
+            const uint32_t g = (uint32_t)(i / 3);
+            const uint32_t ks = (layout == 4) ? (g % 2u) : (layout == 2) ? (g % 4u) : (g % 7u);
+            const uint64_t ad = ad0 + ((ks * a_kstride) >> 4);
+            const uint64_t bd = bd0 + (((g % 8u) * 16384u) >> 4);
+            umma<0>(tmem, ad, bd, idesc, 1u);
+            umma<0>(tmem, ad, bd + (b_part >> 4), idesc, 1u);
+            umma<0>(tmem, ad + (a_part >> 4), bd, idesc, 1u);
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+        const bool ok = mbar_wait_bounded(smem_u32(&bar), 0);
+        const long long t2 = clock64();
+        cycles[0] = t1 - t0; cycles[1] = t2 - t0;
+        *status = ok ? 1 : 2;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+}
+static void run_layout_probe(int N, int nmma, int layout) {
+    long long* dc; int* ds;
+    CK(cudaMalloc(&dc, 16)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+    size_t smem = 2 * 32768 + 8 * 16384 + 1024;
+    CK(cudaFuncSetAttribute(umma_layout_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_layout_probe<<<1, 128, smem>>>(N, nmma, layout, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("layout probe error %s\n", cudaGetErrorString(e)); exit(2); }
+    long long c[2]; int st;
+    CK(cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+    printf("layout probe N=%3d layout=%d status=%d: %.1f cyc/MMA\n", N, layout, st, (double)c[1] / nmma);
+    cudaFree(dc); cudaFree(ds);
+}
+
+
+// ---------------------------------------------------------------------------------- warp-converged issue with elect.sync
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred;
+}
+// mode 0: `if (threadIdx.x == 0)` single-lane loop (what the engine did)   1: whole warp runs the loop, elect.sync lane issues
+// N small on purpose (issue-bound): reports cycles per MMA.  try: 1 = also a try_wait on a completed barrier + commit per group
+__global__ void __launch_bounds__(128) umma_elect_probe(int N, int nmma, int mode, int with_sync, long long* cycles, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar, bar2, bar3;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (2 * 32768 + 8 * 16384) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar2)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar3)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar3)) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_smem)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem;
+    const uint32_t idesc = make_idesc(128, N, 1);
+    const uint64_t ad0 = make_smem_desc(smem_u32(smem), 2048, 128);
+    const uint64_t bd0 = make_smem_desc(smem_u32(smem) + 2 * 32768, (uint32_t)N * 16, 128);
+    long long t0 = 0, t1 = 0;
+    if (warp == 1) {
+        if (mode == 0) {
+            if ((tid & 31) == 0) {
+                t0 = clock64();
+                for (int i = 0; i < nmma; i += 3) {
+                    const uint32_t g = (uint32_t)(i / 3);
+                    if (with_sync) { uint32_t okk; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(okk) : "r"(smem_u32(&bar3)), "r"(0u) : "memory"); }
+                    const uint64_t ad = ad0 + (((g % 7u) * 4096u) >> 4), bd = bd0 + (((g % 8u) * 16384u) >> 4);
+                    umma<0>(tmem, ad, bd, idesc, 1u);
+                    umma<0>(tmem, ad, bd + (8192 >> 4), idesc, 1u);
+                    umma<0>(tmem, ad + (32768 >> 4), bd, idesc, 1u);
+                    if (with_sync) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar2)) : "memory");
+                }
+                t1 = clock64();
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+            }
+        } else {
+            t0 = clock64();
+            for (int i = 0; i < nmma; i += 3) {
+                const uint32_t g = (uint32_t)(i / 3);
+                if (with_sync) { uint32_t okk; asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(okk) : "r"(smem_u32(&bar3)), "r"(0u) : "memory"); }
+                const uint64_t ad = ad0 + (((g % 7u) * 4096u) >> 4), bd = bd0 + (((g % 8u) * 16384u) >> 4);
+                if (elect_one()) {
+                    umma<0>(tmem, ad, bd, idesc, 1u);
+                    umma<0>(tmem, ad, bd + (8192 >> 4), idesc, 1u);
+                    umma<0>(tmem, ad + (32768 >> 4), bd, idesc, 1u);
+                    if (with_sync) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar2)) : "memory");
+                }
+                __syncwarp();
+            }
+            t1 = clock64();
+            if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+        }
+    }
+    const bool ok = mbar_wait_bounded(smem_u32(&bar), 0);
+    if (tid == 32) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; *status = ok ? 1 : 2; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256) : "memory");
+}
+static void run_elect_probe(int N, int nmma, int mode, int with_sync) {
+    long long* dc; int* ds;
+    CK(cudaMalloc(&dc, 16)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+    size_t smem = 2 * 32768 + 8 * 16384 + 16384 + 1024;
+    CK(cudaFuncSetAttribute(umma_elect_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_elect_probe<<<1, 128, smem>>>(N, nmma, mode, with_sync, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("elect probe error %s\n", cudaGetErrorString(e)); exit(2); }
+    long long c[2]; int st;
+    CK(cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+    printf("elect probe N=%3d mode=%d sync=%d status=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA\n", N, mode, with_sync, st, (double)c[0] / nmma, (double)c[1] / nmma);
+    cudaFree(dc); cudaFree(ds);
+}
+
 // ---------------------------------------------------------------------------------- legacy mma.sync / FFMA throughput
 __global__ void __launch_bounds__(256) mma_sync_bf16_tput(float* out, int iters) {
     float c[8][4];
@@ -243,6 +480,9 @@ int main() {
     run_umma<0>(256, 128, 64);
     run_umma<1>(112, 104, 64);
     run_umma<1>(256, 64, 64);
+    for (int N : {16, 112}) for (int mode : {0, 1}) for (int ws : {0, 1}) run_elect_probe(N, 768, mode, ws);
+    return 0;
+    run_issue_probe(112, 21, 14); run_issue_probe(112, 63, 14);
     float* d; CK(cudaMalloc(&d, 4));
     const int sms = p.multiProcessorCount, iters = 4096;
     for (int bps = 1; bps <= 2; ++bps) {

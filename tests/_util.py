@@ -30,7 +30,7 @@ def engine_sparse(params, T, weights, adj, indeg, h0, precision="fp32", return_e
     eng.set_weights(to_cuda_weights(weights))
     eng.set_graph_sparse(adj, indeg)
     out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0, dtype=np.float32)).cuda())
-    torch.cuda.synchronize()
+    eng.sync_check()
     res = out.cpu().numpy()
     return (res, eng) if return_engine else res
 
@@ -53,7 +53,7 @@ def engine_dense(dparams, T, w, adjm, h0, precision="fp32"):
     eng.set_weights(to_cuda_weights([w]))
     eng.set_graph_dense(adjm)
     out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0.reshape(b * v, D), dtype=np.float32)).cuda())
-    torch.cuda.synchronize()
+    eng.sync_check()
     return out.cpu().numpy().reshape(b, v, D)
 
 
