@@ -1,0 +1,114 @@
+"""``DenseGGNNChemModel`` (chem_tensorflow_dense.py:52-265) on the B200 engine: same hooks, params and feed slots.
+The dense model is the engine's dense-adjacency mode: one layer of ``num_timesteps`` steps, A_t . (h W_t + b_t)
+computed as (A_t h) W_t + rowsum(A_t) b_t, GRU/tanh, padded rows updated like real ones (dense:100-116)."""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import packing
+from .chem_model import ChemModel
+from .chem_sparse import _propagation_function
+from .engine import PropagationEngine
+from .utils import glorot_init
+from .workloads import dense_engine_params
+
+
+class DenseGGNNChemModel(ChemModel):
+    @classmethod
+    def default_params(cls):
+        params = dict(super().default_params())
+        params.update({'batch_size': 256, 'graph_state_dropout_keep_prob': 1., 'task_sample_ratios': {},   # dense:59-65
+                       'use_edge_bias': True, 'edge_weight_dropout_keep_prob': 1})
+        return params
+
+    def prepare_specific_graph_model(self) -> None:   # dense:68-91
+        import torch
+        h_dim, T = self.params['hidden_size'], self.num_edge_types
+        for k in ('graph_state_keep_prob', 'edge_weight_dropout_keep_prob', 'initial_node_representation', 'node_mask',
+                  'num_vertices', 'adjacency_matrix'):
+            self.placeholders[k] = k
+        dev = self.device
+
+        def var(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev).requires_grad_(True)
+
+        self.weights['edge_weights'] = var(glorot_init([T, h_dim, h_dim]))                       # dense:84
+        if self.params['use_edge_bias']:
+            self.weights['edge_biases'] = var(np.zeros([T, 1, h_dim]))                           # dense:86
+        self.weights['node_gru'] = {'gate_kernel': var(glorot_init([2 * h_dim, 2 * h_dim])), 'gate_bias': var(np.ones(2 * h_dim)),
+                                    'cand_kernel': var(glorot_init([2 * h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
+        self.engine = PropagationEngine(dense_engine_params(self.params), T, device=self.device.index or 0, precision=self.precision)
+        self._propagation = _propagation_function()
+
+    def graph_model_variables(self):
+        out = [("graph_model/edge_weights", self.weights['edge_weights'])]
+        if 'edge_biases' in self.weights:
+            out.append(("graph_model/edge_biases", self.weights['edge_biases']))
+        out += [("graph_model/gru_scope/%s" % k, v) for k, v in self.weights['node_gru'].items()]
+        return out
+
+    def compute_final_node_representations(self):     # dense:93-117
+        import torch
+        feed = self.feed
+        T, D = self.num_edge_types, self.params['hidden_size']
+        adj = np.asarray(feed[self.placeholders['adjacency_matrix']], dtype=np.float32)          # [b, e, v, v]
+        b, v = adj.shape[0], adj.shape[2]
+        self.engine.set_save_for_backward(torch.is_grad_enabled())
+        self.engine.set_graph_dense(adj)
+        keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
+        if keep < 1.0 or float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0)) < 1.0:
+            # the dense reference draws a fresh weight-dropout mask per timestep and type (dense:104); not supported
+            raise Exception("dropout inside the dense propagation is not supported by the B200 engine")
+        flat, lay = [self.weights['edge_weights']], {'edge_weights': 0}
+        if 'edge_biases' in self.weights:
+            lay['edge_biases'] = len(flat); flat.append(self.weights['edge_biases'].view(T, D))
+        for k, t in self.weights['node_gru'].items():
+            lay[k] = len(flat); flat.append(t)
+        h0 = self.initial_node_representation_tensor().reshape(b * v, D)                         # dense:97
+        out = self._propagation.apply(self.engine, [lay], h0, *flat)
+        return out.reshape(b, v, D)                                                              # dense:116
+
+    def gated_regression(self, last_h, regression_gate, regression_transform):   # dense:119-129
+        import torch
+        D = self.params['hidden_size']
+        h0 = self.initial_node_representation_tensor()
+        gate_input = torch.cat([last_h, h0], dim=2).reshape(-1, 2 * D)
+        gated = torch.sigmoid(regression_gate(gate_input)) * regression_transform(last_h.reshape(-1, D))
+        gated = gated.reshape(last_h.shape[0], last_h.shape[1])
+        mask = torch.as_tensor(np.asarray(self.feed[self.placeholders['node_mask']], dtype=np.float32), device=self.device)
+        self.output = (gated * mask).sum(dim=1)
+        return self.output
+
+    def process_raw_graphs(self, raw_data: Sequence[Any], is_training_data: bool, bucket_sizes=None) -> Any:   # dense:132-164
+        if bucket_sizes is None:
+            bucket_sizes = packing.DEFAULT_BUCKET_SIZES
+        bucketed = defaultdict(list)
+        for d in raw_data:
+            bucketed[packing.choose_bucket(d['graph'], bucket_sizes)].append(d)
+        if is_training_data:
+            for _, bucket in bucketed.items():
+                np.random.shuffle(bucket)
+        bucket_at_step = [[idx for _ in range(len(b) // self.params['batch_size'])] for idx, b in bucketed.items()]
+        bucket_at_step = [x for y in bucket_at_step for x in y]
+        return (bucketed, bucket_sizes, bucket_at_step)
+
+    def make_minibatch_iterator(self, data, is_training: bool):   # dense:194-228
+        bucketed, bucket_sizes, bucket_at_step = data
+        if is_training:
+            np.random.shuffle(bucket_at_step)
+            for _, b in bucketed.items():
+                np.random.shuffle(b)
+        counters = defaultdict(int)
+        keep = self.params['graph_state_dropout_keep_prob'] if is_training else 1.
+        for bucket in bucket_at_step:
+            start = counters[bucket] * self.params['batch_size']
+            elements = bucketed[bucket][start:start + self.params['batch_size']]
+            feed = packing.pack_dense_batch(elements, int(bucket_sizes[bucket]), self.params['hidden_size'], self.num_edge_types,
+                                            self.params['task_ids'], self.params['tie_fwd_bkwd'])
+            feed['graph_state_keep_prob'] = keep
+            feed['edge_weight_dropout_keep_prob'] = keep
+            counters[bucket] += 1
+            yield feed

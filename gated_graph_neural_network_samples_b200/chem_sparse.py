@@ -1,0 +1,181 @@
+"""``SparseGGNNChemModel`` with the reference's hook names, parameter keys and feed-dict slots
+(chem_tensorflow_sparse.py:36-376), its propagation replaced by the B200 engine.
+
+    prepare_specific_graph_model()        sparse:63-115   -> creates the trainables + the engine handle
+    compute_final_node_representations()  sparse:117-218  -> ggnn_set_graph_sparse + ggnn_forward (C ABI)
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import packing
+from .chem_model import ChemModel
+from .engine import PropagationEngine, residual_inputs_of_layer
+from .utils import glorot_init
+
+GGNNWeights = namedtuple('GGNNWeights', ['edge_weights', 'edge_biases', 'edge_type_attention_weights', 'rnn_cells'])
+
+
+def _propagation_function():
+    import torch
+
+    class Propagation(torch.autograd.Function):
+        """Autograd node around the C ABI: forward = ggnn_forward, backward = ggnn_backward."""
+
+        @staticmethod
+        def forward(ctx, engine, layout, h0, *flat):
+            layers = [{k: flat[i] for k, i in lay.items()} for lay in layout]
+            need = any(t.requires_grad for t in flat) or h0.requires_grad
+            engine.set_weights([{k: v.detach().contiguous() for k, v in lw.items()} for lw in layers])
+            engine.set_save_for_backward(need)
+            out = engine.forward(h0.detach().contiguous())
+            ctx.engine, ctx.layout, ctx.shapes = engine, layout, [t.shape for t in flat]
+            ctx.h0_needs = h0.requires_grad
+            ctx.keepalive = (h0, out, flat)   # the engine reads these buffers again in ggnn_backward
+            return out
+
+        @staticmethod
+        def backward(ctx, d_out):
+            grads_flat = [torch.zeros(s, dtype=torch.float32, device=d_out.device) for s in ctx.shapes]
+            grads = [{k: grads_flat[i] for k, i in lay.items()} for lay in ctx.layout]
+            d_h0 = torch.zeros_like(d_out) if ctx.h0_needs else None
+            ctx.engine.backward(d_out.contiguous(), grads, d_h0)
+            return (None, None, d_h0) + tuple(grads_flat)
+
+    return Propagation
+
+
+class SparseGGNNChemModel(ChemModel):
+    def __init__(self, args):
+        super().__init__(args)
+
+    @classmethod
+    def default_params(cls):
+        params = dict(super().default_params())
+        params.update({  # sparse:43-60
+            'batch_size': 100000,
+            'use_edge_bias': False,
+            'use_propagation_attention': False,
+            'use_edge_msg_avg_aggregation': True,
+            'residual_connections': {"2": [0], "4": [0, 2]},
+            'layer_timesteps': [2, 2, 1, 2, 1],
+            'graph_rnn_cell': 'GRU',
+            'graph_rnn_activation': 'tanh',
+            'graph_state_dropout_keep_prob': 1.,
+            'task_sample_ratios': {},
+            'edge_weight_dropout_keep_prob': .8,
+        })
+        return params
+
+    # ------------------------------------------------------------------ hook 1 (sparse:63-115)
+    def prepare_specific_graph_model(self) -> None:
+        import torch
+        h_dim = self.params['hidden_size']
+        T = self.num_edge_types
+        for k in ('initial_node_representation', 'num_incoming_edges_per_type', 'graph_nodes_list',
+                  'graph_state_keep_prob', 'edge_weight_dropout_keep_prob'):
+            self.placeholders[k] = k
+        self.placeholders['adjacency_lists'] = ['adjacency_e%s' % e for e in range(T)]           # sparse:67-68
+        activation_name = self.params['graph_rnn_activation'].lower()
+        if activation_name not in ('tanh', 'relu'):
+            raise Exception("Unknown activation function type '%s'." % activation_name)          # sparse:81
+        cell_type = self.params['graph_rnn_cell'].lower()
+        if cell_type not in ('gru', 'rnn'):
+            raise Exception("Unknown RNN cell type '%s'." % cell_type)                           # sparse:112 (CudnnCompatibleGRUCell: see DESIGN.md)
+        dev = self.device
+
+        def var(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev).requires_grad_(True)
+
+        self.gnn_weights = GGNNWeights([], [], [], [])
+        for layer_idx in range(len(self.params['layer_timesteps'])):
+            self.gnn_weights.edge_weights.append(var(glorot_init([T * h_dim, h_dim])))           # sparse:88 (stacked-shape fan)
+            if self.params['use_edge_bias']:
+                self.gnn_weights.edge_biases.append(var(np.zeros([T, h_dim])))                   # sparse:99
+            din = h_dim * (1 + len(residual_inputs_of_layer(self.params, layer_idx)))
+            if cell_type == 'gru':   # TF-1.3 GRUCell variables: gates kernel/bias (bias init 1.0), candidate kernel/bias
+                cell = {'gate_kernel': var(glorot_init([din + h_dim, 2 * h_dim])), 'gate_bias': var(np.ones(2 * h_dim)),
+                        'cand_kernel': var(glorot_init([din + h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
+            else:                    # BasicRNNCell
+                cell = {'cand_kernel': var(glorot_init([din + h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
+            self.gnn_weights.rnn_cells.append(cell)
+        self.engine = PropagationEngine(self.params, T, device=self.device.index or 0, precision=self.precision)
+        self._propagation = _propagation_function()
+
+    def graph_model_variables(self):
+        out = []
+        for l, w in enumerate(self.gnn_weights.edge_weights):
+            out.append(("graph_model/gnn_layer_%i/gnn_edge_weights_%i" % (l, l), w))
+        for l, b in enumerate(self.gnn_weights.edge_biases):
+            out.append(("graph_model/gnn_layer_%i/gnn_edge_biases_%i" % (l, l), b))
+        for l, cell in enumerate(self.gnn_weights.rnn_cells):
+            for k, v in cell.items():
+                out.append(("graph_model/gnn_layer_%i/cell/%s" % (l, k), v))
+        return out
+
+    # ------------------------------------------------------------------ hook 2 (sparse:117-218)
+    def compute_final_node_representations(self):
+        import torch
+        feed = self.feed
+        T, D = self.num_edge_types, self.params['hidden_size']
+        adjacency_lists = [feed[k] for k in self.placeholders['adjacency_lists']]
+        self.engine.set_save_for_backward(torch.is_grad_enabled())   # before set_graph: the source-keyed CSR is built there
+        self.engine.set_graph_sparse(adjacency_lists, feed[self.placeholders['num_incoming_edges_per_type']])
+        if float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0)) < 1.0:
+            raise Exception("graph_state_dropout_keep_prob < 1 is not supported by the B200 engine")   # DropoutWrapper, sparse:113-114
+        keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
+        flat, layout = [], []
+        for l in range(len(self.params['layer_timesteps'])):
+            w = self.gnn_weights.edge_weights[l].view(T, D, D)                                   # sparse:90
+            if keep < 1.0:   # one mask per layer per run, shared by the layer's timesteps (sparse:91)
+                w = torch.nn.functional.dropout(w, p=1.0 - keep, training=True)
+            lay = {'edge_weights': len(flat)}
+            flat.append(w)
+            if self.params['use_edge_bias']:
+                lay['edge_biases'] = len(flat); flat.append(self.gnn_weights.edge_biases[l])
+            for k, v in self.gnn_weights.rnn_cells[l].items():
+                lay[k] = len(flat); flat.append(v)
+            layout.append(lay)
+        h0 = self.initial_node_representation_tensor()
+        return self._propagation.apply(self.engine, layout, h0, *flat)                           # [V, D]
+
+    # ------------------------------------------------------------------ readout (sparse:220-231) -- torch plumbing, SURVEY 8f-1
+    def gated_regression(self, last_h, regression_gate, regression_transform):
+        import torch
+        h0 = self.initial_node_representation_tensor()
+        gate_input = torch.cat([last_h, h0], dim=-1)
+        gated_outputs = torch.sigmoid(regression_gate(gate_input)) * regression_transform(last_h)   # [v, 1]
+        gnl = torch.as_tensor(np.asarray(self.feed[self.placeholders['graph_nodes_list']]), device=self.device, dtype=torch.long)
+        num_graphs = int(self.feed[self.placeholders['num_graphs']])
+        out = torch.zeros(num_graphs, 1, device=self.device).index_add_(0, gnl, gated_outputs)   # unsorted_segment_sum
+        self.output = out.squeeze(-1)
+        return self.output
+
+    # ------------------------------------------------------------------ data (sparse:234-350) via packing.py
+    def process_raw_graphs(self, raw_data: Sequence[Any], is_training_data: bool) -> Any:
+        processed = packing.process_raw_graphs_sparse(raw_data, self.params['task_ids'], self.params['tie_fwd_bkwd'])
+        if is_training_data:
+            np.random.shuffle(processed)                                                         # sparse:244
+            for task_id in self.params['task_ids']:
+                ratio = self.params['task_sample_ratios'].get(str(task_id))
+                if ratio is not None:
+                    for ex_id in range(int(len(processed) * ratio), len(processed)):
+                        processed[ex_id]['labels'][task_id] = None
+        return processed
+
+    def make_minibatch_iterator(self, data: Any, is_training: bool):
+        if is_training:
+            np.random.shuffle(data)                                                              # sparse:281-282
+        state_keep = self.params['graph_state_dropout_keep_prob'] if is_training else 1.
+        edge_keep = self.params['edge_weight_dropout_keep_prob'] if is_training else 1.
+        for b in packing.iter_sparse_minibatches(data, self.params['batch_size'], self.params['hidden_size'], self.num_edge_types):
+            feed = {k: b[k] for k in ('initial_node_representation', 'num_incoming_edges_per_type', 'graph_nodes_list',
+                                      'target_values', 'target_mask', 'num_graphs')}
+            feed['graph_state_keep_prob'] = state_keep
+            feed['edge_weight_dropout_keep_prob'] = edge_keep
+            for e, key in enumerate(self.placeholders['adjacency_lists']):
+                feed[key] = b['adjacency_lists'][e]
+            yield feed

@@ -17,6 +17,7 @@
 
 #include "../../include/ggnn_b200.h"
 #include "ggnn_common.cuh"
+#include "ggnn_bwd.cuh"
 #include "ggnn_fwd_ffma.cuh"
 #include "ggnn_fwd_tc.cuh"
 
@@ -92,6 +93,9 @@ struct ggnn_engine {
     DevBuf graph_buf;   // packed: row_ptr | csr_src | csr_msg | indeg | denom | tile_start | tile_mask | (dense adj)
     HostPinned graph_stage;
     size_t off_row_ptr = 0, off_src = 0, off_msg = 0, off_indeg = 0, off_denom = 0, off_tiles = 0, off_mask = 0, off_adj = 0;
+    size_t off_trow = 0, off_ttgt = 0;   // source-keyed CSR (rows source*T+type -> targets), built when save_for_backward is on
+    bool has_transpose = false;
+    int64_t edges_of_type[32] = {0};
     DevBuf state_buf;   // intermediate layer states (L-1) + 2 ping-pong step buffers, each [V][D]
     DevBuf save_bufs;   // 5 x total_steps x [V][D]
     DevBuf io_buf;      // h0 / h_out staging for ggnn_forward_host
@@ -257,8 +261,140 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
 
 }  // namespace
 
-static int ggnn_backward_impl(ggnn_engine* e, const float*, const ggnn_layer_grads*, int32_t, float*, ggnn_stream_t) {
-    return e->fail(GGNN_EUNSUPPORTED, "ggnn_backward is not built in this revision");
+// ------------------------------------------------------------------------------------------ backward (host orchestration)
+static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* grads, int32_t num_layers,
+                              float* d_h0, ggnn_stream_t stream) {
+    using namespace ggnn::bwd;
+    if (!e->graph_set || !e->weights_set) return e->fail(GGNN_ESTATE, "no graph / weights set");
+    if (!e->saved_valid) return e->fail(GGNN_ESTATE, "ggnn_backward needs a preceding ggnn_forward with save_for_backward enabled");
+    if (!e->has_transpose) return e->fail(GGNN_ESTATE, "enable save_for_backward BEFORE ggnn_set_graph_sparse (the source-keyed CSR is built there)");
+    if (!grads || num_layers != e->L || (!d_h_out && e->V > 0)) return e->fail(GGNN_EINVAL, "bad backward arguments");
+    CU_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    e->last_launches = 0;
+    const int V = e->V, D = e->D, T = e->T, L = e->L;
+    if (V == 0) return GGNN_OK;
+    const size_t vd = (size_t)V * D;
+    int maxres = 0;
+    for (int l = 0; l < L; ++l) maxres = std::max(maxres, e->nres[l]);
+    const int ldx_max = D * (maxres + 2);
+    // ---- scratch
+    size_t off = 0;
+    auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
+    const size_t o_dstate = take(vd * (L + 1)), o_dha = take(vd), o_dhb = take(vd), o_dpc = take(vd), o_dpg = take(2 * vd);
+    const size_t o_dxc = take((size_t)V * ldx_max), o_dxg = take((size_t)V * ldx_max), o_rh = take(vd), o_dxp = take(vd), o_at = take(vd), o_gt = take(vd);
+    const size_t o_ptrs = off; off += 256;
+    CU_TRY(e, e->bwd_buf.reserve(off));
+    char* bb = (char*)e->bwd_buf.ptr;
+    float* dstate = (float*)(bb + o_dstate);
+    float *dha = (float*)(bb + o_dha), *dhb = (float*)(bb + o_dhb), *dpc = (float*)(bb + o_dpc), *dpg = (float*)(bb + o_dpg);
+    float *dxc = (float*)(bb + o_dxc), *dxg = (float*)(bb + o_dxg), *rh = (float*)(bb + o_rh), *dxp = (float*)(bb + o_dxp);
+    float *At = (float*)(bb + o_at), *Gt = (float*)(bb + o_gt);
+    float** d_ptrs = (float**)(bb + o_ptrs);
+    CU_TRY(e, cudaMemsetAsync(dstate, 0, vd * L * sizeof(float), st));
+    CU_TRY(e, cudaMemcpyAsync(dstate + vd * L, d_h_out, vd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // forward values of node_states_per_layer
+    std::vector<const float*> fstate(L + 1);
+    fstate[0] = e->last_h0; fstate[L] = e->last_out;
+    for (int l = 1; l < L; ++l) fstate[l] = (const float*)e->state_buf.ptr + (size_t)(l - 1) * vd;
+    const float* sv = (const float*)e->save_bufs.ptr;
+    const size_t per = vd * (size_t)std::max(e->total_steps, 1);
+    const float *sv_h = sv, *sv_x = sv + per, *sv_r = sv + 2 * per, *sv_u = sv + 3 * per, *sv_c = sv + 4 * per;
+    char* g = (char*)e->graph_buf.ptr;
+    const int* row_ptr = (const int*)(g + e->off_row_ptr);
+    const int* csr_src = (const int*)(g + e->off_src);
+    const int* trow = (const int*)(g + e->off_trow);
+    const int* ttgt = (const int*)(g + e->off_ttgt);
+    const float* dadj = (const float*)(g + e->off_adj);
+    const float* indeg = (const float*)(g + e->off_indeg);
+    const float* denom = (const float*)(g + e->off_denom);
+    const long long n = (long long)vd;
+    const int eb = (int)std::min<long long>((n + 255) / 256, 4096);
+    auto gemm_nt = [&](bool acc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
+        dim3 grid((N + 63) / 64, (M + 63) / 64);
+        if (acc) gemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+        else gemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+        ++e->last_launches;
+    };
+    auto gemm_tn = [&](const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
+        if (!C) return;
+        const int splits = std::max(1, std::min(128, (M + 255) / 256));
+        const int rps = ((M + splits - 1) / splits + 15) / 16 * 16;
+        dim3 grid((N + 63) / 64, (K + 63) / 64, (M + rps - 1) / rps);
+        gemm_tn_atomic_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rps);
+        ++e->last_launches;
+    };
+    auto colsum = [&](const float* src, int ld, const float* w, int wstride, float* dst, int M, int N) {
+        if (!dst) return;
+        const int rpb = 512;
+        dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
+        colsum_atomic_kernel<<<grid, 256, 0, st>>>(src, ld, w, wstride, dst, M, N, rpb);
+        ++e->last_launches;
+    };
+    const int nodes_blocks = (V + 7) / 8;
+    for (int l = L - 1; l >= 0; --l) {
+        const int R = e->nres[l], din = D * (1 + R), ldx = din + D;
+        const ggnn_layer_weights& w = e->w[l];
+        const ggnn_layer_grads& gw = grads[l];
+        if (R > 0) {
+            float* hp[MAX_RES];
+            for (int i = 0; i < R; ++i) hp[i] = dstate + (size_t)e->res[l][i] * vd;
+            CU_TRY(e, cudaMemcpyAsync(d_ptrs, hp, sizeof(float*) * R, cudaMemcpyHostToDevice, st));
+        }
+        float* dhn = dstate + (size_t)(l + 1) * vd;   // gradient wrt the state leaving the current step
+        float* dh_new = dha;
+        for (int s = e->steps[l] - 1; s >= 0; --s) {
+            const size_t so = (size_t)(e->step_base[l] + s) * vd;
+            const float *h = sv_h + so, *x = sv_x + so;
+            auto seg_src = [&](int i) -> const float* { return i < R ? fstate[e->res[l][i]] : (i == R ? x : nullptr); };
+            if (e->cell == CELL_GRU) {
+                const float *r = sv_r + so, *u = sv_u + so, *c = sv_c + so;
+                gru_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, h, r, u, c, dpc, dpg, dh_new, rh, n, D, e->act); ++e->last_launches;
+                gemm_nt(false, dpc, D, w.cand_kernel, D, dxc, ldx, V, ldx, D);
+                for (int i = 0; i <= R + 1; ++i)
+                    gemm_tn(i <= R ? seg_src(i) : rh, D, dpc, D, gw.cand_kernel ? gw.cand_kernel + (size_t)i * D * D : nullptr, D, V, D, D);
+                colsum(dpc, D, nullptr, 0, gw.cand_bias, V, D);
+                gru_bwd2_kernel<<<eb, 256, 0, st>>>(dxc, ldx, (R + 1) * D, h, r, dpg, dh_new, n, D); ++e->last_launches;
+                gemm_nt(false, dpg, 2 * D, w.gate_kernel, 2 * D, dxg, ldx, V, ldx, 2 * D);
+                for (int i = 0; i <= R + 1; ++i)
+                    gemm_tn(i <= R ? seg_src(i) : h, D, dpg, 2 * D, gw.gate_kernel ? gw.gate_kernel + (size_t)i * D * 2 * D : nullptr, 2 * D, V, 2 * D, D);
+                colsum(dpg, 2 * D, nullptr, 0, gw.gate_bias, V, 2 * D);
+                split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, dxg, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 0, 1, 1, n, D);
+                ++e->last_launches;
+            } else {
+                const float* hnew = (s == e->steps[l] - 1) ? fstate[l + 1] : sv_h + so + vd;
+                rnn_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, hnew, dpc, n, e->act); ++e->last_launches;
+                gemm_nt(false, dpc, D, w.cand_kernel, D, dxc, ldx, V, ldx, D);
+                for (int i = 0; i <= R + 1; ++i)
+                    gemm_tn(i <= R ? seg_src(i) : h, D, dpc, D, gw.cand_kernel ? gw.cand_kernel + (size_t)i * D * D : nullptr, D, V, D, D);
+                colsum(dpc, D, nullptr, 0, gw.cand_bias, V, D);
+                split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, nullptr, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 1, 0, 0, n, D);
+                ++e->last_launches;
+            }
+            // ---- messages
+            for (int t = 0; t < T; ++t) {
+                if (e->use_bias) colsum(dxp, D, indeg + t, T, gw.edge_biases ? gw.edge_biases + (size_t)t * D : nullptr, V, D);
+                if (e->edges_of_type[t] == 0) continue;
+                if (e->gather_mode == GATHER_SPARSE) {
+                    csr_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(row_ptr, csr_src, h, At, V, D, T, t);
+                    csr_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(trow, ttgt, dxp, Gt, V, D, T, t);
+                } else {
+                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, h, At, V, D, T, t, e->dense_v, 0);
+                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, dxp, Gt, V, D, T, t, e->dense_v, 1);
+                }
+                e->last_launches += 2;
+                gemm_tn(At, D, dxp, D, gw.edge_weights ? gw.edge_weights + (size_t)t * D * D : nullptr, D, V, D, D);
+                gemm_nt(true, Gt, D, w.edge_weights + (size_t)t * D * D, D, dh_new, D, V, D, D);
+            }
+            dhn = dh_new;
+            dh_new = (dh_new == dha) ? dhb : dha;
+        }
+        if (e->steps[l] > 0) { add_inplace_kernel<<<eb, 256, 0, st>>>(dstate + (size_t)l * vd, dhn, n); ++e->last_launches; }
+        else { add_inplace_kernel<<<eb, 256, 0, st>>>(dstate + (size_t)l * vd, dstate + (size_t)(l + 1) * vd, n); ++e->last_launches; }
+    }
+    if (d_h0) CU_TRY(e, cudaMemcpyAsync(d_h0, dstate, vd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU_TRY(e, cudaGetLastError());
+    return GGNN_OK;
 }
 
 // ------------------------------------------------------------------------------------------ C ABI
@@ -422,6 +558,12 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     e->off_tiles = off;   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
     e->off_mask = off;    off = align_up(off + sizeof(unsigned) * (size_t)std::max(ntiles, 1), 16);
     e->off_adj = off;
+    e->has_transpose = e->save;
+    if (e->has_transpose) {
+        e->off_trow = off; off = align_up(off + sizeof(int) * ((size_t)V * T + 1), 16);
+        e->off_ttgt = off; off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
+    }
+    for (int t = 0; t < T; ++t) e->edges_of_type[t] = num_edges[t];
     CU_TRY(e, e->graph_stage.reserve(off));
     char* base = (char*)e->graph_stage.ptr;
     int* row_ptr = (int*)(base + e->off_row_ptr);
@@ -447,6 +589,18 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
                 csr_msg[slot] = m;
             }
         }
+    }
+    if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
+        int* trow = (int*)(base + e->off_trow);
+        int* ttgt = (int*)(base + e->off_ttgt);
+        std::vector<int> cnt((size_t)V * T + 1, 0);
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < num_edges[t]; ++i) ++cnt[(size_t)adj[t][2 * i] * T + t + 1];
+        trow[0] = 0;
+        for (size_t k = 1; k <= (size_t)V * T; ++k) trow[k] = trow[k - 1] + cnt[k];
+        for (size_t k = 0; k < (size_t)V * T; ++k) cnt[k] = trow[k];
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < num_edges[t]; ++i) ttgt[cnt[(size_t)adj[t][2 * i] * T + t]++] = adj[t][2 * i + 1];
     }
     for (int v = 0; v < V; ++v) {
         float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
@@ -481,6 +635,8 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
     const int V = b * v;
     e->V = V; e->M = 0; e->gather_mode = GATHER_DENSE; e->dense_v = v;
+    e->has_transpose = true;   // the dense adjacency is its own transpose source
+    for (int t = 0; t < T; ++t) e->edges_of_type[t] = 1;
     std::vector<int> cuts;
     for (int g = 0; g <= b; ++g) cuts.push_back(g * v);
     if (b == 0) cuts.assign(1, 0);

@@ -292,14 +292,15 @@ def stable_target_csr(adjacency_lists, V):
 # fp32 PyTorch-CPU restatement at the TF graph's op granularity -- the timed "reference CPU path"
 # ----------------------------------------------------------------------------------------------
 def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, weights, params,
-                             return_all_layers=False):
+                             return_all_layers=False, dtype=None):
     """Same ops and materialisations as sparse:159-216 with torch CPU fp32 kernels:
     index_select (embedding_lookup) -> matmul -> cat -> index_add_ (unsorted_segment_sum) -> matmul bias
     -> divide -> cat -> explicit GRUCell/BasicRNNCell arithmetic.  Inputs may be NumPy or torch."""
     import torch
+    dtype = dtype or torch.float32   # float64 + requires_grad tensors give the autograd reference for the backward tests
     t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-    h0 = t(h0).float()
-    indeg = t(num_incoming_edges_per_type).float()
+    h0 = t(h0).to(dtype)
+    indeg = t(num_incoming_edges_per_type).to(dtype)
     adjs = [t(np.asarray(a).reshape(-1, 2) if not isinstance(a, torch.Tensor) else a).long() for a in adjacency_lists]
     V, D = h0.shape
     act_name = params.get("graph_rnn_activation", "tanh").lower()
@@ -308,7 +309,7 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
     message_targets = torch.cat([a[:, 1] for a in adjs])
     states = [h0]
     for layer_idx, num_timesteps in enumerate(params["layer_timesteps"]):
-        w = {k: t(v).float() for k, v in weights[layer_idx].items()}
+        w = {k: t(v).to(dtype) for k, v in weights[layer_idx].items()}
         residual_states = [states[i] for i in residual_inputs_of_layer(params, layer_idx)]
         states.append(states[-1])
         for _ in range(num_timesteps):
@@ -318,7 +319,7 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
                 edge_source_states = torch.index_select(h, 0, a[:, 0])
                 msgs.append(torch.matmul(edge_source_states, w["edge_weights"][e]))
             messages = torch.cat(msgs, dim=0)
-            incoming = torch.zeros(V, D).index_add_(0, message_targets, messages)
+            incoming = torch.zeros(V, D, dtype=dtype).index_add_(0, message_targets, messages)
             if params.get("use_edge_bias", False):
                 incoming = incoming + torch.matmul(indeg, w["edge_biases"].reshape(-1, D))
             if params.get("use_edge_msg_avg_aggregation", False):
@@ -334,13 +335,14 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
     return states if return_all_layers else states[-1]
 
 
-def dense_propagation_torch(h0, adjacency_matrix, weights, params):
+def dense_propagation_torch(h0, adjacency_matrix, weights, params, dtype=None):
     """dense:100-115 with torch CPU fp32 kernels (matmul / batched matmul / GRUCell arithmetic)."""
     import torch
+    dtype = dtype or torch.float32
     t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-    h0 = t(h0).float()
-    A = t(adjacency_matrix).float().permute(1, 0, 2, 3).contiguous()               # dense:80
-    w = {k: t(v).float() for k, v in weights.items()}
+    h0 = t(h0).to(dtype)
+    A = t(adjacency_matrix).to(dtype).permute(1, 0, 2, 3).contiguous()             # dense:80
+    w = {k: t(v).to(dtype) for k, v in weights.items()}
     b, v, D = h0.shape
     T = A.shape[0]
     h = h0.reshape(-1, D)
