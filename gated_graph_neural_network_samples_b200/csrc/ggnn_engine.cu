@@ -106,7 +106,7 @@ struct ggnn_engine {
     DevBuf dbg_buf;     // optional phase timestamps (GGNN_TC_DEBUG_TIMING=1)
     bool weights_dirty = true;
     int DP = 0;         // hidden size padded to a multiple of 16 (tensor-core path)
-    size_t tc_off_edge[MAX_LAYERS] = {0}, tc_off_gate_r[MAX_LAYERS] = {0}, tc_off_gate_u[MAX_LAYERS] = {0}, tc_off_cand[MAX_LAYERS] = {0};
+    size_t tc_off_edge[MAX_LAYERS] = {0}, tc_off_gate[MAX_LAYERS] = {0}, tc_off_cand[MAX_LAYERS] = {0};
     const float* last_h0 = nullptr;
     float* last_out = nullptr;
     bool save = false;
@@ -746,8 +746,7 @@ static int tc_prepare_weights(ggnn_engine* e, cudaStream_t st) {
     for (int l = 0; l < e->L; ++l) {
         const int nseg = e->nres[l] + 2;
         e->tc_off_edge[l] = off; off += (size_t)T * NKS * 64 * DP;
-        e->tc_off_gate_r[l] = off; off += (size_t)nseg * NKS * 64 * DP;
-        e->tc_off_gate_u[l] = off; off += (size_t)nseg * NKS * 64 * DP;
+        e->tc_off_gate[l] = off; off += (size_t)nseg * NKS * 128 * DP;
         e->tc_off_cand[l] = off; off += (size_t)nseg * NKS * 64 * DP;
     }
     if (off > e->tc_weights.cap) e->weights_dirty = true;
@@ -756,18 +755,15 @@ static int tc_prepare_weights(ggnn_engine* e, cudaStream_t st) {
     uint8_t* base = (uint8_t*)e->tc_weights.ptr;
     for (int l = 0; l < e->L; ++l) {
         const int nseg = e->nres[l] + 2;
-        auto launch = [&](const float* W, uint8_t* out, int segs, int src_ld, int src_col0) {
-            const long long total = (long long)segs * NKS * 2 * DP;
+        auto launch = [&](const float* W, uint8_t* out, int segs, int blks, int src_ld, int col0) {
+            const long long total = (long long)segs * NKS * 2 * blks * DP;
             const int blocks = (int)std::min<long long>((total + 255) / 256, 1024);
-            tc::ggnn_tile_weights_kernel<<<blocks, 256, 0, st>>>(W, out, D, DP, segs, src_ld, src_col0);
+            tc::ggnn_tile_weights_kernel<<<blocks, 256, 0, st>>>(W, out, D, DP, segs, blks, src_ld, col0);
             ++e->last_launches;
         };
-        launch(e->w[l].edge_weights, base + e->tc_off_edge[l], T, D, 0);
-        if (e->cell == CELL_GRU) {
-            launch(e->w[l].gate_kernel, base + e->tc_off_gate_r[l], nseg, 2 * D, 0);
-            launch(e->w[l].gate_kernel, base + e->tc_off_gate_u[l], nseg, 2 * D, D);
-        }
-        launch(e->w[l].cand_kernel, base + e->tc_off_cand[l], nseg, D, 0);
+        launch(e->w[l].edge_weights, base + e->tc_off_edge[l], T, 1, D, 0);
+        if (e->cell == CELL_GRU) launch(e->w[l].gate_kernel, base + e->tc_off_gate[l], nseg, 2, 2 * D, 0);
+        launch(e->w[l].cand_kernel, base + e->tc_off_cand[l], nseg, 1, D, 0);
     }
     CU_TRY(e, cudaGetLastError());
     e->weights_dirty = false;
@@ -801,6 +797,7 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     if (avail < 3 * opb + bias_b + 2 * stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
     p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - 3 * opb - bias_b) / stage);
     if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(2, std::min(p.nstages, atoi(ns)));
+    if (p.nstages < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the weight ring (DP=%d)", DP);
     p.fake_weights = getenv("GGNN_TC_FAKE_WEIGHTS") ? 1 : 0;
     const size_t smem = 3 * opb + bias_b + (size_t)p.nstages * stage;
     char* g = (char*)e->graph_buf.ptr;
@@ -821,8 +818,7 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     uint8_t* wb = (uint8_t*)e->tc_weights.ptr;
     for (int l = 0; l < e->L; ++l) {
         tc::TcLayer& ld = p.layer[l];
-        ld.w_edge = wb + e->tc_off_edge[l]; ld.w_gate_r = wb + e->tc_off_gate_r[l]; ld.w_gate_u = wb + e->tc_off_gate_u[l];
-        ld.w_cand = wb + e->tc_off_cand[l];
+        ld.w_edge = wb + e->tc_off_edge[l]; ld.w_gate = wb + e->tc_off_gate[l]; ld.w_cand = wb + e->tc_off_cand[l];
         ld.edge_b = e->w[l].edge_biases; ld.gate_b = e->w[l].gate_bias; ld.cand_b = e->w[l].cand_bias;
         ld.steps = e->steps[l]; ld.nres = e->nres[l];
         for (int i = 0; i < MAX_RES; ++i) ld.res[i] = e->res[l][i];

@@ -35,8 +35,8 @@ constexpr int MAX_STAGES = 8;
 struct TcLayer {
     // pre-split (bf16 hi/lo), pre-tiled weights: one 64*DP-byte stage per K-step (16 rows) of a [K x DP] block
     const uint8_t* w_edge;    // [T*DP/16]       W_t, t-major
-    const uint8_t* w_gate_r;  // [(R+2)*DP/16]   K_g columns [0,D)   rows: residual segments..., agg, h
-    const uint8_t* w_gate_u;  // [(R+2)*DP/16]   K_g columns [D,2D)
+    const uint8_t* w_gate;    // [(R+2)*DP/16] x 2 slots: K_g as one N = 2*DP operand (cols r | u): hi slot then lo slot per K-step
+                              //                 rows: residual segments..., agg, h
     const uint8_t* w_cand;    // [(R+2)*DP/16]   K_c (RNN: the only kernel)
     const float* edge_b;    // fp32 originals (unpadded)
     const float* gate_b;
@@ -94,17 +94,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
     return ok != 0;
 }
 __device__ __noinline__ bool mbar_wait_slow(uint32_t addr, uint32_t parity, volatile int* abort_flag) {
-    long long t0 = 0;
-    for (int it = 0;; ++it) {
+    const long long t0 = clock64();
+    for (unsigned it = 1;; ++it) {
         uint32_t ok;
-        // the hardware suspends the thread (up to the hint, in ns) instead of spinning; it wakes on phase completion
+        // the hardware suspends the thread (up to the hint, in ns) instead of spinning; it wakes on barrier events
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (ok) return true;
-        if (*abort_flag) return false;
-        __nanosleep(64);   // keep waiting warps off the issue ports: the MMA-issuing thread shares an SM sub-partition with them
-        if (it == 0) t0 = clock64();
-        else if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return false; }
+        if ((it & 63u) == 0u) {   // keep the common iteration tiny: pollers share issue slots with the MMA warp
+            if (*abort_flag) return false;
+            if (clock64() - t0 > 2000000000LL) { *abort_flag = 1; return false; }
+        }
     }
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort_flag) {
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         mbar_init(&bar_g1_done[1], 1);
         mbar_init(&bar_g_ready[0], NUM_WORKERS / 32);
         mbar_init(&bar_g_ready[1], NUM_WORKERS / 32);
-        mbar_init(&bar_workers, NUM_WORKERS / 32);
+        mbar_init(&bar_workers, 1);   // (unused: workers rendezvous on named barrier 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_PROD) {
@@ -293,17 +293,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         const int grow = row_ok ? row0 + row : row0; // global node id (clamped for padding rows)
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint32_t ph_done = 0;                         // parity of bar_mma_done
-        uint32_t ph_wk = 0;                           // parity of bar_workers
         bool ok = true;
         uint32_t ph_g1 = 0;                           // bit b = parity of bar_g1_done[b]
+        // All-worker rendezvous on hardware named barrier 1 (blocked warps issue nothing).  Waiting for the MMA warp is
+        // done by worker warp 0 alone (one poller instead of sixteen); the others block on the named barrier behind it.
+        // On a timeout the poller raises s_abort BEFORE the rendezvous, so every worker leaves together.
         auto workers_sync = [&]() {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_workers);
-            if (!mbar_wait(&bar_workers, ph_wk & 1, abortp)) ok = false;
-            ++ph_wk;
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory");
+            if (*abortp) ok = false;
         };
-        auto wait_mma = [&]() { if (ok) { ok = mbar_wait(&bar_mma_done, ph_done & 1, abortp); ++ph_done; if (ok) tc_fence_after(); } };
-        auto wait_g1 = [&](int b) { if (ok) { ok = mbar_wait(&bar_g1_done[b], (ph_g1 >> b) & 1u, abortp); ph_g1 ^= 1u << b; if (ok) tc_fence_after(); } };
+        auto wait_on = [&](uint64_t* bar, uint32_t parity) {
+            if (warp == 0 && ok) { if (!mbar_wait(bar, parity, abortp)) *abortp = 1; }
+            asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory");
+            if (*abortp) ok = false;
+            if (ok) tc_fence_after();
+        };
+        auto wait_mma = [&]() { wait_on(&bar_mma_done, ph_done & 1); ++ph_done; };
+        auto wait_g1 = [&](int b) { wait_on(&bar_g1_done[b], (ph_g1 >> b) & 1u); ph_g1 ^= 1u << b; };
         // every lane orders its own smem/TMEM writes, then one lane per warp signals the MMA thread
         auto publish = [&]() { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_a_ready); };
         auto publish_g = [&](int b) { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_g_ready[b]); };
@@ -396,7 +402,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                         float acc[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-                        if (p.gather_mode == GATHER_SPARSE) {
+                        if (LOCAL && csr_smem) {
+                            // fast path: local source indices from shared memory, two messages in flight
+                            const uint8_t* colbase = opH + (size_t)kc * 2048;
+                            const uint32_t lo_off = (uint32_t)DP * 256u;
+                            int m = beg;
+                            if (p.nparts == 3) {
+                                for (; m + 1 < end; m += 2) {
+                                    const uint8_t* s0 = colbase + (size_t)sSrc[m] * 16;
+                                    const uint8_t* s1 = colbase + (size_t)sSrc[m + 1] * 16;
+                                    const uint4 h0 = *reinterpret_cast<const uint4*>(s0), l0 = *reinterpret_cast<const uint4*>(s0 + lo_off);
+                                    const uint4 h1 = *reinterpret_cast<const uint4*>(s1), l1 = *reinterpret_cast<const uint4*>(s1 + lo_off);
+                                    unpack8_add(h0, acc, 1.0f); unpack8_add(h1, acc, 1.0f);
+                                    unpack8_add(l0, acc, 1.0f); unpack8_add(l1, acc, 1.0f);
+                                }
+                                if (m < end) {
+                                    const uint8_t* s0 = colbase + (size_t)sSrc[m] * 16;
+                                    unpack8_add(*reinterpret_cast<const uint4*>(s0), acc, 1.0f);
+                                    unpack8_add(*reinterpret_cast<const uint4*>(s0 + lo_off), acc, 1.0f);
+                                }
+                            } else {
+                                for (; m < end; ++m) unpack8_add(*reinterpret_cast<const uint4*>(colbase + (size_t)sSrc[m] * 16), acc, 1.0f);
+                            }
+                        } else if (p.gather_mode == GATHER_SPARSE) {
                             for (int m = beg; m < end; ++m) {
                                 if (LOCAL) {
                                     const int sl = csr_smem ? (int)sSrc[m] : (p.csr_src[m] - row0);
@@ -577,7 +605,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             const uint32_t b_lo16 = ((uint32_t)DP * 32u) >> 4;    // hi -> lo part of a weight stage
             const uint32_t stage16 = STAGE_B >> 4;
             const uint64_t descA = make_desc(0, 2048, 128);
-            const uint64_t descB = make_desc(smem_u32(ring), 16u * (uint32_t)DP, 128);
             const uint32_t opH16 = smem_u32(opH) >> 4, opX16 = smem_u32(opX) >> 4, opA16 = smem_u32(opA) >> 4;
             const uint32_t full0 = smem_u32(&bar_w_full[0]), empty0 = smem_u32(&bar_w_empty[0]);
             const uint32_t idesc = make_idesc_bf16(DP);
@@ -586,38 +613,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             const long long dbg_t0 = clock64();
             uint32_t ph_ready = 0, ph_g = 0, stage = 0, full_par = 0;
             bool ok = true;
-            // acc(tm_d) (+)= A(op) . B(next NKS weight stages): NKS K-steps of 1 or 3 MMAs
+            // acc(tm_d) (+)= A(op) . B(next weight stages): NKS K-steps of 1 or 3 MMAs each.
+            //   narrow (N = DP):   one ring slot per K-step holds [hi | lo] halves of the DP-wide weight block
+            //   wide   (N = 2*DP): two ring slots per K-step: slot s = hi part, slot s+1 = lo part of the [r | u] gate block
+            // Two K-steps are issued per loop iteration (one elect / fence / reconvergence for both): the issue path is a
+            // single warp's serial code and its fixed per-iteration cost is what bounds the small (N = DP) MMAs.
             int dbg_g = 0;
-            auto gemm = [&](uint32_t op16, uint32_t tm_d, uint32_t& accum) {
-                if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
-                uint64_t ad = descA | (uint64_t)op16;
-#pragma unroll 1
-                for (int ks = 0; ks < NKS && ok; ++ks) {
-                    if (!(fake && full_par)) {
-                        const uint32_t fb = full0 + stage * 8u;
-                        if (!mbar_try(fb, full_par)) {
-                            const long long w0 = dbg_on ? clock64() : 0;
-                            if (!mbar_wait_slow(fb, full_par, abortp)) ok = false;
-                            if (dbg_on) dbg_wfull += clock64() - w0;
-                        }
-                    }
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint32_t ring16 = __shfl_sync(0xffffffffu, smem_u32(ring) >> 4, 0);
+            const uint64_t descB1 = make_desc(0, 16u * (uint32_t)DP, 128);   // N = DP   operand: K-chunk stride 16*DP
+            const uint64_t descB2 = make_desc(0, 32u * (uint32_t)DP, 128);   // N = 2*DP operand: K-chunk stride 32*DP
+            const uint32_t idesc2 = make_idesc_bf16(2 * DP);
+            auto wait_full = [&](uint32_t st_, uint32_t par_) {
+                if (fake && par_) return;
+                const uint32_t fb = full0 + st_ * 8u;
+                if (!mbar_try(fb, par_)) {
+                    const long long w0 = dbg_on ? clock64() : 0;
+                    if (!mbar_wait_slow(fb, par_, abortp)) ok = false;
+                    if (dbg_on) dbg_wfull += clock64() - w0;
                     ok = __all_sync(0xffffffffu, ok);
-                    if (!ok) break;
+                }
+            };
+            auto commit_empty = [&](uint32_t st_) {
+                if (!fake) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + st_ * 8u) : "memory");
+            };
+            auto gemm = [&](uint32_t op16, uint32_t tm_col, uint32_t& accum, bool wide) {
+                if (!ok) return;
+                if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
+                uint32_t a16 = op16;
+                const uint32_t tm_d = tmem_u + tm_col;
+                const uint32_t slots = wide ? 2u : 1u;
+#pragma unroll 1
+                for (int ks = 0; ks < NKS; ks += ((2u * slots <= nstg) ? 2 : 1)) {
+                    const bool two = (ks + 1 < NKS) && (2u * slots <= nstg);
+                    // ring slots of this pair of K-steps (and their parities)
+                    uint32_t s[4], par[4];
+                    uint32_t st_ = stage, pr_ = full_par;
+                    const int nslots = (int)slots * (two ? 2 : 1);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        s[i] = st_; par[i] = pr_;
+                        if (i < nslots) { if (++st_ == nstg) { st_ = 0; pr_ ^= 1u; } }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (i < nslots) wait_full(s[i], par[i]);
+                    if (!ok) return;
                     tc_fence_after();
-                    const uint64_t bd = descB + (uint64_t)(stage * stage16);
                     if (elect_one()) {
-                        umma_bf16(tm_d, ad, bd, idesc, accum);
-                        if (x3) {
-                            umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
-                            umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (h == 1 && !two) break;
+                            const uint64_t ad = descA | (uint64_t)(a16 + (uint32_t)h * 256u);
+                            if (!wide) {
+                                const uint64_t bd = descB1 | (uint64_t)(ring16 + s[h] * stage16);
+                                umma_bf16(tm_d, ad, bd, idesc, (h == 0) ? accum : 1u);
+                                if (x3) {
+                                    umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
+                                    umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
+                                }
+                                commit_empty(s[h]);
+                            } else {
+                                const uint64_t bh = descB2 | (uint64_t)(ring16 + s[2 * h] * stage16);
+                                const uint64_t bl = descB2 | (uint64_t)(ring16 + s[2 * h + 1] * stage16);
+                                umma_bf16(tm_d, ad, bh, idesc2, (h == 0) ? accum : 1u);
+                                if (x3) {
+                                    umma_bf16(tm_d, ad, bl, idesc2, 1u);
+                                    umma_bf16(tm_d, ad + a_lo16, bh, idesc2, 1u);
+                                }
+                                commit_empty(s[2 * h]);
+                                commit_empty(s[2 * h + 1]);
+                            }
                         }
-                        if (!fake)   // stage reusable once these MMAs have read it
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + stage * 8u) : "memory");
                     }
                     __syncwarp();
                     accum = 1u;
-                    ad += 256;   // next K-step of the A operand: 4096 bytes
-                    if (++stage == nstg) { stage = 0; full_par ^= 1u; }
+                    a16 += two ? 512u : 256u;   // one or two K-steps of the A operand (4096 bytes each)
+                    stage = st_; full_par = pr_;
                 }
             };
             auto commit_to = [&](uint64_t* bar) { if (ok) { if (elect_one()) umma_commit(bar); __syncwarp(); } };
@@ -640,11 +711,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 const int nres = ly.nres;
                 const bool gru = p.cell == CELL_GRU;
                 if (nres > 0 && s_end > s_begin) {
-                    uint32_t f_r = 0, f_u = 0, f_c = 0;
+                    uint32_t f_r = 0, f_c = 0;
                     for (int i = 0; i < nres && ok; ++i) {
                         wait_ready();
-                        if (gru) { gemm(opA16, TM_GATE, f_r); gemm(opA16, TM_GATE + DP, f_u); }
-                        gemm(opA16, TM_ACC, f_c);
+                        if (gru) gemm(opA16, 2u * DP, f_r, true);
+                        gemm(opA16, (uint32_t)DP, f_c, false);
                         commit_to(&bar_mma_done);
                     }
                 }
@@ -654,22 +725,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
                         wait_g_ready(nty & 1);
-                        gemm((nty & 1) ? opX16 : opA16, TM_ACC, f_agg);
+                        gemm((nty & 1) ? opX16 : opA16, (uint32_t)DP, f_agg, false);
                         commit_to(&bar_g1_done[nty & 1]);
                         ++nty;
                     }
                     wait_ready();                                   // agg operand (opX) ready
                     uint32_t f_c = 0;
                     if (gru) {
-                        uint32_t f_r = 0, f_u = 0;
-                        gemm(opX16, TM_GATE, f_r); gemm(opH16, TM_GATE, f_r);
-                        commit_to(&bar_mma_done);                   // r ready
-                        gemm(opX16, TM_GATE + DP, f_u); gemm(opH16, TM_GATE + DP, f_u);
-                        gemm(opX16, TM_ACC, f_c);
+                        uint32_t f_g = 0;
+                        gemm(opX16, 2u * DP, f_g, true); gemm(opH16, 2u * DP, f_g, true);   // [r | u] in one N = 2*DP MMA stream
+                        commit_to(&bar_mma_done);                   // gates ready
+                        gemm(opX16, (uint32_t)DP, f_c, false);      // candidate, agg part: overlaps the r*h epilogue
                         wait_ready();                               // r*h operand (opA) ready
-                        gemm(opA16, TM_ACC, f_c);
+                        gemm(opA16, (uint32_t)DP, f_c, false);
                     } else {
-                        gemm(opX16, TM_ACC, f_c); gemm(opH16, TM_ACC, f_c);
+                        gemm(opX16, (uint32_t)DP, f_c, false); gemm(opH16, (uint32_t)DP, f_c, false);
                     }
                     commit_to(&bar_mma_done);                       // candidate ready
                 }
@@ -693,6 +763,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     if (++stage == (uint32_t)nst) { stage = 0; ++lap; }
                 }
             };
+            // a gate block: 2 slots (hi part, lo part of the N = 2*DP operand) per K-step
+            auto push_wide = [&](const uint8_t* mat, int ks0) {
+                for (int i = 0; i < 2 * NKS && ok; ++i) {
+                    if (p.fake_weights && lap > 0) { if (++stage == (uint32_t)nst) { stage = 0; ++lap; } continue; }
+                    if (lap > 0 && !mbar_wait(&bar_w_empty[stage], (lap - 1) & 1, abortp)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&bar_w_full[stage], STAGE_B);
+                    bulk_copy_g2s(ring + stage * STAGE_B, mat + (size_t)(2 * ks0 + i) * STAGE_B, STAGE_B, &bar_w_full[stage]);
+                    if (++stage == (uint32_t)nst) { stage = 0; ++lap; }
+                }
+            };
             for (int l = l_begin; l < l_end && ok; ++l) {
                 const TcLayer& ly = p.layer[l];
                 const int s_begin = LOCAL ? 0 : p.g_step;
@@ -701,7 +781,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 const int kx = ly.nres * NKS, kh = (ly.nres + 1) * NKS;
                 if (ly.nres > 0 && s_end > s_begin) {
                     for (int i = 0; i < ly.nres && ok; ++i) {
-                        if (gru) { push_block(ly.w_gate_r, i * NKS); push_block(ly.w_gate_u, i * NKS); }
+                        if (gru) push_wide(ly.w_gate, i * NKS);
                         push_block(ly.w_cand, i * NKS);
                     }
                 }
@@ -710,10 +790,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                         if (!((tmask >> t) & 1u)) continue;
                         push_block(ly.w_edge, t * NKS);
                     }
-                    if (gru) {
-                        push_block(ly.w_gate_r, kx); push_block(ly.w_gate_r, kh);
-                        push_block(ly.w_gate_u, kx); push_block(ly.w_gate_u, kh);
-                    }
+                    if (gru) { push_wide(ly.w_gate, kx); push_wide(ly.w_gate, kh); }
                     push_block(ly.w_cand, kx); push_block(ly.w_cand, kh);
                 }
             }
@@ -728,31 +805,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------ weight pre-tiling
-// fp32 row-major W[(nseg*D) rows][src_ld cols]; the D columns starting at src_col0 are tiled  ->  per K-step s
-// (16 padded rows) one contiguous stage of 64*DP bytes
-//   byte(s, part, c, n, j) = s*(64*DP) + part*(32*DP) + c*(16*DP) + n*16 + j*2
-// holding bf16 part (0 = hi, 1 = lo) of W[row(s*16 + c*8 + j)][src_col0 + n]; padded rows/cols (>= D inside a
-// DP-wide segment / n >= D) are zero.
-__global__ void ggnn_tile_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int D, int DP, int nseg,
+// fp32 row-major W[(nseg*D) rows][src_ld cols], columns [src_col0, src_col0 + nblk*D)  ->  per K-step s (16 padded rows) nblk consecutive ring slots of
+// 64*DP bytes.  Np = nblk*DP output rows (column block b of the source lands at n = b*DP + col, zero padded):
+//   nblk == 1:  slot = [hi part | lo part], part = 2 K-chunks x DP rows x 16 B            (one DP-wide weight block)
+//   nblk == 2:  slot 0 = hi part, slot 1 = lo part, part = 2 K-chunks x 2*DP rows x 16 B  (the [r | u] gate block)
+// element: byte(s, part, c, n, j) = s*nblk*64*DP + part*(32*Np) + c*(16*Np) + n*16 + j*2 = bf16 part of W[row(s*16+c*8+j)][col(n)]
+__global__ void ggnn_tile_weights_kernel(const float* __restrict__ W, uint8_t* __restrict__ out, int D, int DP, int nseg, int nblk,
                                          int src_ld, int src_col0) {
+    const int Np = nblk * DP;
     const int ksteps = nseg * DP / 16;
-    const long long total = (long long)ksteps * 2 * DP;
+    const long long total = (long long)ksteps * 2 * Np;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(idx % DP);
-        const int c = (int)((idx / DP) % 2);
-        const int s = (int)(idx / (2 * DP));
+        const int n = (int)(idx % Np);
+        const int c = (int)((idx / Np) % 2);
+        const int s = (int)(idx / (2 * Np));
+        const int blk = n / DP, nn = n - blk * DP;
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int kp = s * 16 + c * 8 + j;
             const int seg = kp / DP, kk = kp - seg * DP;
-            x[j] = (kk < D && n < D) ? W[(size_t)(seg * D + kk) * src_ld + src_col0 + n] : 0.0f;
+            x[j] = (kk < D && nn < D) ? W[(size_t)(seg * D + kk) * src_ld + src_col0 + blk * D + nn] : 0.0f;
         }
         uint4 hi, lo;
         split8(x, hi, lo);
-        uint8_t* base = out + (size_t)s * 64 * DP + (size_t)c * 16 * DP + (size_t)n * 16;
+        uint8_t* base = out + (size_t)s * nblk * 64 * DP + (size_t)c * 16 * Np + (size_t)n * 16;
         *reinterpret_cast<uint4*>(base) = hi;
-        *reinterpret_cast<uint4*>(base + (size_t)32 * DP) = lo;
+        *reinterpret_cast<uint4*>(base + (size_t)32 * Np) = lo;
     }
 }
 

@@ -417,6 +417,78 @@ static void run_elect_probe(int N, int nmma, int mode, int with_sync) {
     cudaFree(dc); cudaFree(ds);
 }
 
+
+// ---------------------------------------------------------------------------------- replicate the engine's exact operand geometry
+// variant bits: 1 = TMEM accumulator at column 112 (else 0); 2 = engine smem geometry (A lo part +28672, B stages 7168 apart at
+// 172032, B lo part +3584) else the aligned probe geometry; 4 = pseudo-random operand data instead of constants
+__global__ void __launch_bounds__(128) umma_geom_probe(int nmma, int variant, long long* cycles, int* status) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int N = 112;
+    for (int i = tid; i < 229376 / 4; i += 128) {
+        uint32_t v = 0x3c003c00u;
+        if (variant & 4) { uint32_t x = (uint32_t)i * 2654435761u; v = 0x3c003c00u ^ ((x >> 9) & 0x00ff00ffu) ^ ((x & 1u) << 15) ^ ((x & 2u) << 30); }
+        reinterpret_cast<uint32_t*>(smem)[i] = v;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_smem)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_smem + ((variant & 1) ? 112u : 0u);
+    const uint32_t idesc = make_idesc(128, N, 1);
+    const bool eng = (variant & 2) != 0;
+    const uint32_t a_lo = eng ? 28672u : 32768u, b_base = eng ? 172032u : 65536u, b_stage = eng ? 7168u : 16384u, b_lo = eng ? 3584u : 8192u;
+    const uint64_t ad0 = make_smem_desc(smem_u32(smem), 2048, 128);
+    const uint64_t bd0 = make_smem_desc(smem_u32(smem) + b_base, (uint32_t)N * 16, 128);
+    long long t0 = 0, t1 = 0;
+    if (warp == 1) {
+        t0 = clock64();
+        for (int i = 0; i < nmma; i += 3) {
+            const uint32_t g = (uint32_t)(i / 3);
+            const uint64_t ad = ad0 + (((g % 7u) * 4096u) >> 4), bd = bd0 + (((g % 8u) * b_stage) >> 4);
+            if (elect_one()) {
+                umma<0>(tmem, ad, bd, idesc, 1u);
+                umma<0>(tmem, ad, bd + (b_lo >> 4), idesc, 1u);
+                umma<0>(tmem, ad + (a_lo >> 4), bd, idesc, 1u);
+            }
+            __syncwarp();
+        }
+        t1 = clock64();
+        if (elect_one()) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+    }
+    const bool ok = mbar_wait_bounded(smem_u32(&bar), 0);
+    if (tid == 32 && blockIdx.x == 0) { cycles[0] = t1 - t0; cycles[1] = clock64() - t0; *status = ok ? 1 : 2; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_smem), "r"(512) : "memory");
+}
+static int g_geom_grid = 1;
+static void run_geom_probe(int nmma, int variant) {
+    long long* dc; int* ds;
+    CK(cudaMalloc(&dc, 16)); CK(cudaMalloc(&ds, 4)); CK(cudaMemset(ds, 0, 4));
+    size_t smem = 229376 + 1024;
+    CK(cudaFuncSetAttribute(umma_geom_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_geom_probe<<<g_geom_grid, 128, smem>>>(nmma, variant, dc, ds);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("geom probe error %s\n", cudaGetErrorString(e)); exit(2); }
+    long long c[2]; int st;
+    CK(cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&st, ds, 4, cudaMemcpyDeviceToHost));
+    printf("grid=%3d ", g_geom_grid);
+    printf("geom probe variant=%d (tmem col %s, %s geometry, %s data) status=%d: %.1f cyc/MMA\n", variant, (variant & 1) ? "112" : "0",
+           (variant & 2) ? "engine" : "aligned", (variant & 4) ? "random" : "const", st, (double)c[1] / nmma);
+    cudaFree(dc); cudaFree(ds);
+}
+
 // ---------------------------------------------------------------------------------- legacy mma.sync / FFMA throughput
 __global__ void __launch_bounds__(256) mma_sync_bf16_tput(float* out, int iters) {
     float c[8][4];
@@ -480,7 +552,7 @@ int main() {
     run_umma<0>(256, 128, 64);
     run_umma<1>(112, 104, 64);
     run_umma<1>(256, 64, 64);
-    for (int N : {16, 112}) for (int mode : {0, 1}) for (int ws : {0, 1}) run_elect_probe(N, 768, mode, ws);
+    for (int grid : {1, 2, 39, 74, 148}) { g_geom_grid = grid; run_geom_probe(768, 3); run_geom_probe(21, 3); }
     return 0;
     run_issue_probe(112, 21, 14); run_issue_probe(112, 63, 14);
     float* d; CK(cudaMalloc(&d, 4));

@@ -1,0 +1,54 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, and exports every symbol include/ggnn_b200.h declares
+(no compute calls without a GPU); host-side error behaviour that does not need a device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ggnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ggnn_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gated_graph_neural_network_samples_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert name in _lib.SYMBOLS, "header symbol %s has no ctypes binding" % name
+        assert getattr(lib, name) is not None
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_create_fails_loudly_without_a_gpu_or_with_bad_config():
+    """No silent CPU fallback: without a CUDA device the engine refuses to exist."""
+    import torch
+    from gated_graph_neural_network_samples_b200.engine import GgnnError, PropagationEngine
+    params = {"hidden_size": 8, "layer_timesteps": [1], "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh"}
+    with pytest.raises(Exception, match="Unknown activation"):
+        PropagationEngine(dict(params, graph_rnn_activation="swish"), 2)
+    with pytest.raises(GgnnError, match="multiple of 4"):
+        PropagationEngine(dict(params, hidden_size=6), 2)
+    with pytest.raises(GgnnError, match="residual connection"):
+        PropagationEngine(dict(params, residual_connections={"0": [1]}), 2)
+    if not torch.cuda.is_available():
+        with pytest.raises(GgnnError, match="CUDA device unavailable"):
+            PropagationEngine(params, 2)
+
+
+def test_workload_definitions_and_algorithmic_bytes():
+    from gated_graph_neural_network_samples_b200 import workloads
+    w = workloads.build("cfg2")
+    assert w["V"] > 4000 and w["timesteps"] == 4 and w["num_edge_types"] == 4
+    D, V, M, T = 100, w["V"], w["M"], 4
+    step = 4 * D * (2 * V + M) + 8 * M + 4 * V * T + 4 * (T * D * D + 2 * D * 3 * D + 3 * D)
+    assert workloads.algorithmic_bytes(w) == 4 * step
+    assert workloads.algorithmic_flops(w) == 4 * (2 * M * D * D + 2 * V * 2 * D * 3 * D)
+    w5 = workloads.build("cfg5_rgcn")
+    assert w5["V"] == 10000 and w5["M"] == 80000 and "gate_kernel" not in w5["weights"][0]
