@@ -191,23 +191,39 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
         e->local = max_span <= tc::TILE_M;
         const char* fg = getenv("GGNN_FORCE_GLOBAL");
         if (fg && fg[0] == '1') e->local = false;
-        tile_start.clear();
-        tile_start.push_back(0);
-        if (e->local) {
+        // Rows per tile: 128 fills the UMMA M dimension, but a small batch then occupies only V/128 SMs and every tile
+        // sees every edge type.  When the batch cannot fill the chip, shrink the row budget to the smallest multiple of 8
+        // that still fits all tiles in one wave: more SMs, and fewer edge-type blocks per tile (absent types are skipped).
+        auto pack = [&](int budget, std::vector<int>& ts) {
+            ts.clear(); ts.push_back(0);
             int cur = 0;
             for (size_t i = 1; i < cuts.size(); ++i)
-                if (cuts[i] - cur > tc::TILE_M) { tile_start.push_back(cuts[i - 1]); cur = cuts[i - 1]; }
-            if (V > cur) tile_start.push_back(V);
+                if (cuts[i] - cur > budget) { ts.push_back(cuts[i - 1]); cur = cuts[i - 1]; }
+            if (V > cur) ts.push_back(V);
+        };
+        int budget = tc::TILE_M;
+        if (e->local) {
+            pack(tc::TILE_M, tile_start);
+            const char* tr = getenv("GGNN_TC_TILE_ROWS");
+            if (tr && atoi(tr) >= max_span && atoi(tr) <= tc::TILE_M) { budget = atoi(tr); pack(budget, tile_start); }
+            else if ((int)tile_start.size() - 1 < e->num_sms) {
+                std::vector<int> trial;
+                for (int b = std::max(32, (max_span + 7) / 8 * 8); b < tc::TILE_M; b += 8) {
+                    pack(b, trial);
+                    if ((int)trial.size() - 1 <= e->num_sms) { budget = b; tile_start = trial; break; }
+                }
+            }
         } else {
+            tile_start.clear(); tile_start.push_back(0);
             for (int r = tc::TILE_M; r < V; r += tc::TILE_M) tile_start.push_back(r);
             if (V > 0) tile_start.push_back(V);
         }
         if (V == 0) tile_start.assign(1, 0);
         e->ntiles = (int)tile_start.size() - 1;
         char buf[256];
-        snprintf(buf, sizeof buf, "tcgen05-%s %s tiles=%d rows/tile<=128 DP=%d max_component=%d",
+        snprintf(buf, sizeof buf, "tcgen05-%s %s tiles=%d rows/tile<=%d DP=%d max_component=%d",
                  e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)",
-                 e->ntiles, e->DP, max_span);
+                 e->ntiles, budget, e->DP, max_span);
         e->plan_text = buf;
         return GGNN_OK;
     }

@@ -29,9 +29,11 @@ def engine_sparse(params, T, weights, adj, indeg, h0, precision="fp32", return_e
     eng = PropagationEngine(params, T, precision=precision)
     eng.set_weights(to_cuda_weights(weights))
     eng.set_graph_sparse(adj, indeg)
-    out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0, dtype=np.float32)).cuda())
+    h0_dev = torch.from_numpy(np.ascontiguousarray(h0, dtype=np.float32)).cuda()
+    out = eng.forward(h0_dev)
     eng.sync_check()
     res = out.cpu().numpy()
+    eng._keepalive = (h0_dev, out)   # node_states_per_layer[0] / [L] are caller-owned buffers the engine only points to
     return (res, eng) if return_engine else res
 
 
