@@ -59,11 +59,11 @@ def oracle_weights(w):
 
 def time_cpu_reference(w, budget_s=12.0, max_iters=200, threads=None):
     """node-updates/s of the fp32 torch-CPU restatement (oracle.ggnn_oracle.sparse_propagation_torch /
-    dense_propagation_torch), all host threads, bounded by ``budget_s`` seconds of work."""
+    dense_propagation_torch) on the host cores, bounded by ``budget_s`` seconds of work.  The TF graph's matmuls are
+    small, so more threads are not always faster: 1 thread, 16 threads and all cores are each timed on a slice of the
+    budget and the FASTEST setting is reported (``cores`` = the thread count that won)."""
     import torch
     from oracle import ggnn_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
     ow = oracle_weights(w)
     if w["kind"] == "dense":
         b, v = w["dense_shape"]
@@ -78,17 +78,24 @@ def time_cpu_reference(w, budget_s=12.0, max_iters=200, threads=None):
         indeg = torch.from_numpy(w["num_incoming_edges_per_type"])
         tw = [{k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in lw.items()} for lw in ow]
         fn = lambda: O.sparse_propagation_torch(h0, adj, indeg, tw, w["engine_params"])
+    ncpu = os.cpu_count() or 1
+    candidates = [threads] if threads else sorted({1, min(16, ncpu), ncpu})
+    best, tried = None, []
     with torch.no_grad():
-        fn(); fn()
-        times = []
-        t_start = time.perf_counter()
-        while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s:
-            t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
-    med = statistics.median(times)
-    return {"value": w["node_updates"] / med, "unit": "node-updates/s", "cores": int(torch.get_num_threads()),
-            "kind": "port", "ms_per_step": med * 1e3,
-            "sample": "%d full forwards of %s (V=%d, M=%d) in %.1f s, median; fp32 PyTorch-CPU restatement of the TF1 graph (TF 1.3 not installable)"
-                      % (len(times), w["name"], w["V"], w["M"], sum(times))}
+        for nt in candidates:
+            torch.set_num_threads(nt)
+            fn(); fn()
+            times, t_start = [], time.perf_counter()
+            while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s / len(candidates):
+                t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)
+            med = statistics.median(times)
+            tried.append("%d thr: %.2f ms" % (nt, med * 1e3))
+            if best is None or med < best[0]:
+                best = (med, nt, len(times), sum(times))
+    med, nt, cnt, tot = best
+    return {"value": w["node_updates"] / med, "unit": "node-updates/s", "cores": int(nt), "kind": "port", "ms_per_step": med * 1e3,
+            "sample": "%d full forwards of %s (V=%d, M=%d) in %.1f s, median, best thread count of [%s] on a %d-core host; fp32 PyTorch-CPU "
+                      "restatement of the TF1 graph (TF 1.3 not installable)" % (cnt, w["name"], w["V"], w["M"], tot, "; ".join(tried), ncpu)}
 
 
 class ClockSampler:
@@ -141,8 +148,6 @@ def run_reference(args, rank, world):
         return
     from gated_graph_neural_network_samples_b200 import workloads
     w = workloads.build(args.config, seed=0)
-    import torch
-    torch.set_num_threads(os.cpu_count() or 1)
     # K steps + W warm-ups of full forwards, bounded to a few minutes
     res = time_cpu_reference(w, budget_s=min(120.0, 2.0 * max(args.steps, 1)), max_iters=max(args.steps, 3))
     line = {"impl": "reference", "metric": "GGNN node-state-updates/sec (propagation step)", "value": res["value"],
@@ -254,7 +259,8 @@ def main():
     e1.record()
     sync_all()
     e2e_ms_total = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)  # host work + copies + kernel, every step
-    np.testing.assert_array_equal(out_np, out.cpu().numpy())  # same result either way
+    # same result either way (the tensor-core path's MMA issue order across issuer warps is not fixed -> fp32 rounding noise)
+    np.testing.assert_allclose(out_np, out.cpu().numpy(), rtol=1e-4, atol=1e-5)
     if dense:
         h2d = int(w["adjacency_matrix"].nbytes + w["V"] * w["num_edge_types"] * 4 + w["V"] * 4 + w["h0"].nbytes)
     else:

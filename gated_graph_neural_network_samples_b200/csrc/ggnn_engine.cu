@@ -814,7 +814,6 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - 3 * opb - bias_b) / stage);
     if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(2, std::min(p.nstages, atoi(ns)));
     if (p.nstages < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the weight ring (DP=%d)", DP);
-    p.fake_weights = getenv("GGNN_TC_FAKE_WEIGHTS") ? 1 : 0;
     const size_t smem = 3 * opb + bias_b + (size_t)p.nstages * stage;
     char* g = (char*)e->graph_buf.ptr;
     p.tile_start = (const int*)(g + e->off_tiles);

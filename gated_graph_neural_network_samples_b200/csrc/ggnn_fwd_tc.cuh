@@ -13,9 +13,13 @@
 //
 // Shared memory: three A-operand tiles (h, agg, A_t / r*h), each hi+lo in the canonical K-major no-swizzle UMMA
 // layout  byte(row, k) = part*(DP*256) + (k/8)*2048 + row*16 + (k%8)*2 ,  plus a ring of weight stages that a
-// producer thread fills with cp.async.bulk (1-D TMA) from a pre-split, pre-tiled bf16 copy of the weights.
+// producer thread fills with cp.async.bulk (1-D TMA) from a pre-split, pre-tiled bf16 copy of the weights.  The stream is
+// latency bound (bytes in flight / slot round trip), so the ring is extended into A-operand tiles while they hold no live
+// operand: the A_t / r*h tile during the gate GEMM, the h tile during the candidate GEMM.
 // Warp roles: warps 0-15 = workers (gather, epilogues; TMEM lane quarter = warp%4, column-chunk group = warp/4),
-// warp 16 = MMA issuer (one thread), warp 17 = weight producer (one thread) + TMEM allocator.
+// warps 16-17 = MMA issuers (K-steps round-robin; every MMA accumulates into accumulators the workers zero after reading,
+// so cross-warp issue order is irrelevant), warps 18-19 = weight producers (one thread each, pushes round-robin; warp 18 also
+// allocates TMEM).  20 warps x 96 registers fill the register file; issuer/producer counts are compile-time knobs.
 // Every mbarrier wait is bounded; on timeout an error code is written and all roles drain.
 #pragma once
 #include <cuda_bf16.h>
@@ -27,10 +31,21 @@ namespace tc {
 
 constexpr int TILE_M = 128;
 constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane quarter
-constexpr int WARP_MMA = 16;
-constexpr int WARP_PROD = 17;
-constexpr int NTHREADS = 576;
-constexpr int MAX_STAGES = 8;
+#ifndef GGNN_TC_ISSUERS
+#define GGNN_TC_ISSUERS 2
+#endif
+constexpr int NUM_ISSUERS = GGNN_TC_ISSUERS;            // MMA-issuing warps (one per SM sub-partition); issuer i takes K-steps i, i+4, ...
+#ifndef GGNN_TC_PRODUCERS
+#define GGNN_TC_PRODUCERS 2
+#endif
+constexpr int NUM_PRODUCERS = GGNN_TC_PRODUCERS;   // weight-producer warps (one thread each); slot pushes are dealt round-robin
+constexpr int WARP_MMA = 16;              // first issuer warp
+constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // first producer warp (also the TMEM allocator)
+constexpr int NTHREADS = (WARP_PROD + NUM_PRODUCERS) * 32;
+constexpr int MAX_STAGES = 8;             // ring slots proper
+constexpr int EXT_SLOTS = 8;              // an idle A-operand tile holds exactly 8 more slots (DP*512 / DP*64)
+constexpr int MAX_SLOTS = MAX_STAGES + 2 * EXT_SLOTS;
+enum { SET_BASE = 0, SET_XA = 1, SET_XH = 2 };   // ring only | ring + opA tile (gate phase) | ring + opH tile (candidate phase)
 
 struct TcLayer {
     // pre-split (bf16 hi/lo), pre-tiled weights: one 64*DP-byte stage per K-step (16 rows) of a [K x DP] block
@@ -70,7 +85,6 @@ struct TcParams {
     const float* g_in;
     float* g_out;
     int* error_flag;
-    int fake_weights;  // timing experiment only (GGNN_TC_FAKE_WEIGHTS=1): weight stages are loaded once and never refreshed -> WRONG results
     long long* dbg;  // optional [64] clock64 stamps written by tile 0 / thread 0 (profiling aid), or nullptr
 };
 
@@ -227,8 +241,10 @@ __device__ __forceinline__ void lds8(const float* s, float (&v)[8]) {
 template <bool LOCAL>
 __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_w_full[MAX_STAGES];
-    __shared__ __align__(8) uint64_t bar_w_empty[MAX_STAGES];
+    __shared__ __align__(8) uint64_t bar_w_full[MAX_SLOTS];
+    __shared__ __align__(8) uint64_t bar_w_empty[MAX_SLOTS];
+    __shared__ __align__(8) uint64_t bar_xa_free;   // opA tile holds no live operand: the producer may use it as ring slots (gate phase)
+    __shared__ __align__(8) uint64_t bar_xh_free;   // opH tile dead until the state update rewrites it (candidate phase)
     __shared__ __align__(8) uint64_t bar_a_ready;
     __shared__ __align__(8) uint64_t bar_mma_done;
     __shared__ __align__(8) uint64_t bar_g1_done[2];   // one per gather buffer (opA, opX): its MMAs are complete
@@ -260,11 +276,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
 
     if (tid == 0) {
         s_abort = 0;
-        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+        for (int i = 0; i < MAX_SLOTS; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+        mbar_init(&bar_xa_free, NUM_ISSUERS);
+        mbar_init(&bar_xh_free, NUM_ISSUERS);
         mbar_init(&bar_a_ready, NUM_WORKERS / 32);   // one arrival per worker warp
-        mbar_init(&bar_mma_done, 1);
-        mbar_init(&bar_g1_done[0], 1);
-        mbar_init(&bar_g1_done[1], 1);
+        mbar_init(&bar_mma_done, NUM_ISSUERS);      // one tcgen05.commit per issuer warp
+        mbar_init(&bar_g1_done[0], NUM_ISSUERS);
+        mbar_init(&bar_g1_done[1], NUM_ISSUERS);
         mbar_init(&bar_g_ready[0], NUM_WORKERS / 32);
         mbar_init(&bar_g_ready[1], NUM_WORKERS / 32);
         mbar_init(&bar_workers, 1);   // (unused: workers rendezvous on named barrier 1)
@@ -311,8 +329,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         auto wait_mma = [&]() { wait_on(&bar_mma_done, ph_done & 1); ++ph_done; };
         auto wait_g1 = [&](int b) { wait_on(&bar_g1_done[b], (ph_g1 >> b) & 1u); ph_g1 ^= 1u << b; };
         // every lane orders its own smem/TMEM writes, then one lane per warp signals the MMA thread
-        auto publish = [&]() { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_a_ready); };
+        auto publish = [&]() { tmem_st_wait(); tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_a_ready); };
         auto publish_g = [&](int b) { tc_fence_before(); fence_async_smem(); __syncwarp(); if (lane == 0) mbar_arrive(&bar_g_ready[b]); };
+        const float zeros8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float* res_pre = p.res_pre + (size_t)tile * TILE_M * 3 * DP + (size_t)row * 3 * DP;
         int dbg_i = 0;
         auto stamp = [&]() { if (p.dbg && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); };
@@ -327,6 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 tmem_st8(TM_H + lane_addr + kc * 8, v);
                 store_operand_chunk(opH, DP, kc, row, v);
             }
+            for (int c = cg; c < 3 * NKC; c += NCG) tmem_st8(TM_ACC + lane_addr + c * 8, zeros8);   // acc + gate accumulators start at zero
             tmem_st_wait();
         }
         const bool csr_smem = LOCAL && p.csr_cache && p.gather_mode == GATHER_SPARSE;
@@ -371,11 +391,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     const int ngate = gru ? 2 * NKC : 0;
                     for (int c = cg; c < ngate + NKC; c += NCG) {   // gate chunks [0,2NKC) then cand chunks
                         float v[8];
-                        tmem_ld8((c < ngate ? TM_GATE + c * 8 : TM_ACC + (c - ngate) * 8) + lane_addr, v);
+                        const uint32_t ta = (c < ngate ? TM_GATE + c * 8 : TM_ACC + (c - ngate) * 8) + lane_addr;
+                        tmem_ld8(ta, v);
+                        tmem_st8(ta, zeros8);
                         float* dst = res_pre + (c < ngate ? c * 8 : 2 * DP + (c - ngate) * 8);
                         *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
                     }
+                    tmem_st_wait();
                     tc_fence_before();
                     workers_sync();
                 }
@@ -475,7 +498,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     const float inv_den = (p.use_avg && row_ok) ? __fdividef(1.0f, p.denom[grow]) : 1.0f;
                     for (int kc = cg; kc < NKC; kc += NCG) {
                         float v[8];
-                        if (have_msgs) tmem_ld8(TM_ACC + lane_addr + kc * 8, v);
+                        if (have_msgs) { tmem_ld8(TM_ACC + lane_addr + kc * 8, v); tmem_st8(TM_ACC + lane_addr + kc * 8, zeros8); }
                         else {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] = 0.0f;
@@ -513,6 +536,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                             for (int j = 0; j < 8; ++j) b[j] += rp[j];
                         }
                         tmem_ld_wait();
+                        tmem_st8(TM_GATE + lane_addr + kc * 8, zeros8);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) { g[j] = sigmoid_fast(g[j] + b[j]); rh[j] = g[j] * h[j]; }
                         if (p.save && row_ok) {
@@ -549,6 +573,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                 for (int j = 0; j < 8; ++j) bc[j] += rp[j];
                             }
                             tmem_ld_wait();
+                            tmem_st8(TM_ACC + lane_addr + kc * 8, zeros8);
+                            tmem_st8(TM_GATE + lane_addr + DP + kc * 8, zeros8);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 u[j] = sigmoid_fast(u[j] + bu[j]);
@@ -568,6 +594,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                 for (int j = 0; j < 8; ++j) bc[j] += rp[j];
                             }
                             tmem_ld_wait();
+                            tmem_st8(TM_ACC + lane_addr + kc * 8, zeros8);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) hn[j] = act_fast(c[j] + bc[j], p.act);
                             if (p.save && row_ok) store8_guarded(p.save_buf.h_in + save_off, kc * 8, D, h);
@@ -592,103 +619,97 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             if (LOCAL && l + 1 < l_end) { __threadfence(); workers_sync(); }   // layer output visible before it is read as a residual
         }  // layers
         if (!ok && lane == 0) atomicExch(p.error_flag, 1);
-    } else if (warp == WARP_MMA) {
-        // =============================================================================== MMA ISSUER
-        // The whole warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.
-        // (A single-lane `if (lane == 0)` loop makes nvcc wrap every MMA in a lane-serialising ELECT loop and costs
-        // ~640 cycles per K-step; this form issues at the tensor pipe's ~68-cycle-per-instruction floor.)
+    } else if (warp < WARP_PROD) {   // issuers
+        // =============================================================================== MMA ISSUERS
+        // Each issuer warp runs the (warp-uniform) control flow; one elected lane issues the tcgen05 instructions.  K-steps are
+        // dealt round-robin to the issuer warps; all of them (and the producer) walk the same sequence of weight slots.
         {
             const bool x3 = p.nparts == 3;
-            const bool fake = p.fake_weights != 0;
             const uint32_t nstg = (uint32_t)nst;
+            const uint32_t iw = (uint32_t)(warp - WARP_MMA);
             const uint32_t a_lo16 = ((uint32_t)DP * 256u) >> 4;   // hi -> lo part of an A operand (16-byte units)
-            const uint32_t b_lo16 = ((uint32_t)DP * 32u) >> 4;    // hi -> lo part of a weight stage
+            const uint32_t b_lo16 = ((uint32_t)DP * 32u) >> 4;    // hi -> lo part of a narrow weight slot
             const uint32_t stage16 = STAGE_B >> 4;
             const uint64_t descA = make_desc(0, 2048, 128);
-            const uint32_t opH16 = smem_u32(opH) >> 4, opX16 = smem_u32(opX) >> 4, opA16 = smem_u32(opA) >> 4;
-            const uint32_t full0 = smem_u32(&bar_w_full[0]), empty0 = smem_u32(&bar_w_empty[0]);
-            const uint32_t idesc = make_idesc_bf16(DP);
-            const bool dbg_on = p.dbg && tile == 0 && lane == 0;
-            long long dbg_wfull = 0, dbg_ready = 0;
-            const long long dbg_t0 = clock64();
-            uint32_t ph_ready = 0, ph_g = 0, stage = 0, full_par = 0;
-            bool ok = true;
-            // acc(tm_d) (+)= A(op) . B(next weight stages): NKS K-steps of 1 or 3 MMAs each.
-            //   narrow (N = DP):   one ring slot per K-step holds [hi | lo] halves of the DP-wide weight block
-            //   wide   (N = 2*DP): two ring slots per K-step: slot s = hi part, slot s+1 = lo part of the [r | u] gate block
-            // Two K-steps are issued per loop iteration (one elect / fence / reconvergence for both): the issue path is a
-            // single warp's serial code and its fixed per-iteration cost is what bounds the small (N = DP) MMAs.
-            int dbg_g = 0;
-            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-            const uint32_t ring16 = __shfl_sync(0xffffffffu, smem_u32(ring) >> 4, 0);
             const uint64_t descB1 = make_desc(0, 16u * (uint32_t)DP, 128);   // N = DP   operand: K-chunk stride 16*DP
             const uint64_t descB2 = make_desc(0, 32u * (uint32_t)DP, 128);   // N = 2*DP operand: K-chunk stride 32*DP
-            const uint32_t idesc2 = make_idesc_bf16(2 * DP);
-            auto wait_full = [&](uint32_t st_, uint32_t par_) {
-                if (fake && par_) return;
-                const uint32_t fb = full0 + st_ * 8u;
-                if (!mbar_try(fb, par_)) {
-                    const long long w0 = dbg_on ? clock64() : 0;
-                    if (!mbar_wait_slow(fb, par_, abortp)) ok = false;
-                    if (dbg_on) dbg_wfull += clock64() - w0;
+            const uint32_t opH16 = smem_u32(opH) >> 4, opX16 = smem_u32(opX) >> 4, opA16 = smem_u32(opA) >> 4, ring16 = smem_u32(ring) >> 4;
+            const uint32_t full0 = smem_u32(&bar_w_full[0]), empty0 = smem_u32(&bar_w_empty[0]);
+            const uint32_t idesc = make_idesc_bf16(DP), idesc2 = make_idesc_bf16(2 * DP);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const bool dbg_on = p.dbg && tile == 0 && lane == 0 && iw == 0;
+            long long dbg_ready = 0;
+            const long long dbg_t0 = clock64();
+            int dbg_g = 0;
+            uint32_t ph_ready = 0, ph_g = 0;
+            uint32_t cur[3] = {0, 0, 0};   // round-robin cursor of each slot set
+            uint32_t fpar = 0;             // bit s = parity to wait for on bar_w_full[s]
+            bool ok = true;
+            auto next_slot = [&](int set) -> uint32_t {
+                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT_SLOTS;
+                const uint32_t i = cur[set];
+                cur[set] = (i + 1 == n) ? 0u : i + 1;
+                return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
+            };
+            auto slot16 = [&](uint32_t sl) -> uint32_t {
+                return sl < nstg ? ring16 + sl * stage16
+                     : sl < nstg + EXT_SLOTS ? opA16 + (sl - nstg) * stage16 : opH16 + (sl - nstg - EXT_SLOTS) * stage16;
+            };
+            auto wait_full = [&](uint32_t sl) {
+                const uint32_t par = (fpar >> sl) & 1u;
+                fpar ^= 1u << sl;
+                const uint32_t fb = full0 + sl * 8u;
+                if (!mbar_try(fb, par)) {
+                    if (!mbar_wait_slow(fb, par, abortp)) ok = false;
                     ok = __all_sync(0xffffffffu, ok);
                 }
             };
-            auto commit_empty = [&](uint32_t st_) {
-                if (!fake) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + st_ * 8u) : "memory");
+            auto commit_empty = [&](uint32_t sl) {
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + sl * 8u) : "memory");
             };
-            auto gemm = [&](uint32_t op16, uint32_t tm_col, uint32_t& accum, bool wide) {
+            // acc(tm_col) += A(op) . B(next weight slots of `set`): NKS K-steps of 1 or 3 MMAs each; accumulators are zeroed by the workers
+            //   narrow (N = DP):   one slot per K-step holds [hi | lo] halves of the DP-wide weight block
+            //   wide   (N = 2*DP): two slots per K-step: hi part, lo part of the [r | u] gate block
+            auto gemm = [&](uint32_t op16, uint32_t tm_col, bool wide, int set) {
                 if (!ok) return;
                 if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
-                uint32_t a16 = op16;
                 const uint32_t tm_d = tmem_u + tm_col;
-                const uint32_t slots = wide ? 2u : 1u;
 #pragma unroll 1
-                for (int ks = 0; ks < NKS; ks += ((2u * slots <= nstg) ? 2 : 1)) {
-                    const bool two = (ks + 1 < NKS) && (2u * slots <= nstg);
-                    // ring slots of this pair of K-steps (and their parities)
-                    uint32_t s[4], par[4];
-                    uint32_t st_ = stage, pr_ = full_par;
-                    const int nslots = (int)slots * (two ? 2 : 1);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        s[i] = st_; par[i] = pr_;
-                        if (i < nslots) { if (++st_ == nstg) { st_ = 0; pr_ ^= 1u; } }
+                for (int ks = 0; ks < NKS; ++ks) {
+                    const uint32_t s0 = next_slot(set);
+                    const uint32_t s1 = wide ? next_slot(set) : 0u;
+                    if ((uint32_t)ks % NUM_ISSUERS != iw) {   // someone else's K-step: only keep the slot parities in step
+                        fpar ^= 1u << s0;
+                        if (wide) fpar ^= 1u << s1;
+                        continue;
                     }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) if (i < nslots) wait_full(s[i], par[i]);
+                    wait_full(s0);
+                    if (wide) wait_full(s1);
                     if (!ok) return;
                     tc_fence_after();
                     if (elect_one()) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            if (h == 1 && !two) break;
-                            const uint64_t ad = descA | (uint64_t)(a16 + (uint32_t)h * 256u);
-                            if (!wide) {
-                                const uint64_t bd = descB1 | (uint64_t)(ring16 + s[h] * stage16);
-                                umma_bf16(tm_d, ad, bd, idesc, (h == 0) ? accum : 1u);
-                                if (x3) {
-                                    umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
-                                    umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
-                                }
-                                commit_empty(s[h]);
-                            } else {
-                                const uint64_t bh = descB2 | (uint64_t)(ring16 + s[2 * h] * stage16);
-                                const uint64_t bl = descB2 | (uint64_t)(ring16 + s[2 * h + 1] * stage16);
-                                umma_bf16(tm_d, ad, bh, idesc2, (h == 0) ? accum : 1u);
-                                if (x3) {
-                                    umma_bf16(tm_d, ad, bl, idesc2, 1u);
-                                    umma_bf16(tm_d, ad + a_lo16, bh, idesc2, 1u);
-                                }
-                                commit_empty(s[2 * h]);
-                                commit_empty(s[2 * h + 1]);
+                        const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)ks * 256u);
+                        if (!wide) {
+                            const uint64_t bd = descB1 | (uint64_t)slot16(s0);
+                            umma_bf16(tm_d, ad, bd, idesc, 1u);
+                            if (x3) {
+                                umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
+                                umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
                             }
+                            commit_empty(s0);
+                        } else {
+                            const uint64_t bh = descB2 | (uint64_t)slot16(s0);
+                            const uint64_t bl = descB2 | (uint64_t)slot16(s1);
+                            umma_bf16(tm_d, ad, bh, idesc2, 1u);
+                            if (x3) {
+                                umma_bf16(tm_d, ad, bl, idesc2, 1u);
+                                umma_bf16(tm_d, ad + a_lo16, bh, idesc2, 1u);
+                            }
+                            commit_empty(s0);
+                            commit_empty(s1);
                         }
                     }
                     __syncwarp();
-                    accum = 1u;
-                    a16 += two ? 512u : 256u;   // one or two K-steps of the A operand (4096 bytes each)
-                    stage = st_; full_par = pr_;
                 }
             };
             auto commit_to = [&](uint64_t* bar) { if (ok) { if (elect_one()) umma_commit(bar); __syncwarp(); } };
@@ -711,66 +732,75 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 const int nres = ly.nres;
                 const bool gru = p.cell == CELL_GRU;
                 if (nres > 0 && s_end > s_begin) {
-                    uint32_t f_r = 0, f_c = 0;
                     for (int i = 0; i < nres && ok; ++i) {
                         wait_ready();
-                        if (gru) gemm(opA16, 2u * DP, f_r, true);
-                        gemm(opA16, (uint32_t)DP, f_c, false);
+                        if (gru) gemm(opA16, 2u * DP, true, SET_BASE);
+                        gemm(opA16, (uint32_t)DP, false, SET_BASE);
                         commit_to(&bar_mma_done);
                     }
                 }
                 for (int s = s_begin; s < s_end && ok; ++s) {
-                    uint32_t f_agg = 0;
                     int nty = 0;
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
                         wait_g_ready(nty & 1);
-                        gemm((nty & 1) ? opX16 : opA16, (uint32_t)DP, f_agg, false);
+                        gemm((nty & 1) ? opX16 : opA16, (uint32_t)DP, false, SET_BASE);
                         commit_to(&bar_g1_done[nty & 1]);
                         ++nty;
                     }
+                    commit_to(&bar_xa_free);                        // every MMA that reads the opA tile (this step's G1, last step's G3) is tracked
                     wait_ready();                                   // agg operand (opX) ready
-                    uint32_t f_c = 0;
                     if (gru) {
-                        uint32_t f_g = 0;
-                        gemm(opX16, 2u * DP, f_g, true); gemm(opH16, 2u * DP, f_g, true);   // [r | u] in one N = 2*DP MMA stream
+                        gemm(opX16, 2u * DP, true, SET_XA); gemm(opH16, 2u * DP, true, SET_XA);   // [r | u] in one N = 2*DP MMA stream
                         commit_to(&bar_mma_done);                   // gates ready
-                        gemm(opX16, (uint32_t)DP, f_c, false);      // candidate, agg part: overlaps the r*h epilogue
+                        commit_to(&bar_xh_free);                    // ... and the opH tile is dead until the state update
+                        gemm(opX16, (uint32_t)DP, false, SET_XH);   // candidate, agg part: overlaps the r*h epilogue
                         wait_ready();                               // r*h operand (opA) ready
-                        gemm(opA16, (uint32_t)DP, f_c, false);
+                        gemm(opA16, (uint32_t)DP, false, SET_XH);
                     } else {
-                        gemm(opX16, (uint32_t)DP, f_c, false); gemm(opH16, (uint32_t)DP, f_c, false);
+                        gemm(opX16, (uint32_t)DP, false, SET_XA); gemm(opH16, (uint32_t)DP, false, SET_XA);
                     }
                     commit_to(&bar_mma_done);                       // candidate ready
                 }
             }
             if (!ok && lane == 0) atomicExch(p.error_flag, 2);
-            if (dbg_on) { p.dbg[60] = dbg_wfull; p.dbg[61] = dbg_ready; p.dbg[62] = clock64() - dbg_t0; }
+            if (dbg_on) { p.dbg[60] = 0; p.dbg[61] = dbg_ready; p.dbg[62] = clock64() - dbg_t0; }
         }
     } else {
         // =============================================================================== WEIGHT PRODUCER
+        // The stream is bound by the per-push issue cost of a single thread (wait, expect_tx, bulk copy: ~430 cycles per 7 KB slot),
+        // so several producer warps share it: all walk the same slot sequence, producer i issues pushes i, i + NUM_PRODUCERS, ...
         if (lane == 0) {
-            uint32_t stage = 0, lap = 0;
+            const uint32_t nstg = (uint32_t)nst;
+            const uint32_t ipw = (uint32_t)(warp - WARP_PROD);
+            uint32_t npush = 0;
+            uint32_t cur[3] = {0, 0, 0};
+            uint32_t used = 0, epar = 0;   // bit s: slot s has been filled before / parity to wait for on bar_w_empty[s]
+            uint32_t ph_xa = 0, ph_xh = 0;
             bool ok = true;
-            // stream one DP x DP weight block (NKS stages) starting at K-step index ks0 of a pre-tiled matrix
-            auto push_block = [&](const uint8_t* mat, int ks0) {
-                for (int ks = 0; ks < NKS && ok; ++ks) {
-                    if (p.fake_weights && lap > 0) { if (++stage == (uint32_t)nst) { stage = 0; ++lap; } continue; }   // timing experiment only
-                    // a stage is free once the MMAs that read its previous contents have completed (first lap: free)
-                    if (lap > 0 && !mbar_wait(&bar_w_empty[stage], (lap - 1) & 1, abortp)) { ok = false; break; }
-                    mbar_arrive_expect_tx(&bar_w_full[stage], STAGE_B);
-                    bulk_copy_g2s(ring + stage * STAGE_B, mat + (size_t)(ks0 + ks) * STAGE_B, STAGE_B, &bar_w_full[stage]);
-                    if (++stage == (uint32_t)nst) { stage = 0; ++lap; }
-                }
+            auto next_slot = [&](int set) -> uint32_t {
+                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT_SLOTS;
+                const uint32_t i = cur[set];
+                cur[set] = (i + 1 == n) ? 0u : i + 1;
+                return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
             };
-            // a gate block: 2 slots (hi part, lo part of the N = 2*DP operand) per K-step
-            auto push_wide = [&](const uint8_t* mat, int ks0) {
-                for (int i = 0; i < 2 * NKS && ok; ++i) {
-                    if (p.fake_weights && lap > 0) { if (++stage == (uint32_t)nst) { stage = 0; ++lap; } continue; }
-                    if (lap > 0 && !mbar_wait(&bar_w_empty[stage], (lap - 1) & 1, abortp)) { ok = false; break; }
-                    mbar_arrive_expect_tx(&bar_w_full[stage], STAGE_B);
-                    bulk_copy_g2s(ring + stage * STAGE_B, mat + (size_t)(2 * ks0 + i) * STAGE_B, STAGE_B, &bar_w_full[stage]);
-                    if (++stage == (uint32_t)nst) { stage = 0; ++lap; }
+            auto slot_ptr = [&](uint32_t sl) -> uint8_t* {
+                return sl < nstg ? ring + sl * STAGE_B
+                     : sl < nstg + EXT_SLOTS ? opA + (sl - nstg) * STAGE_B : opH + (sl - nstg - EXT_SLOTS) * STAGE_B;
+            };
+            // stream `count` consecutive 64*DP-byte stages of a pre-tiled matrix into the next slots of `set`
+            auto push = [&](const uint8_t* src, int count, int set) {
+                for (int i = 0; i < count && ok; ++i) {
+                    const uint32_t sl = next_slot(set);
+                    // a slot is free once the MMAs that read its previous contents have completed (first use: free)
+                    const bool was_used = (used >> sl) & 1u;
+                    const uint32_t par = (epar >> sl) & 1u;
+                    if (was_used) epar ^= 1u << sl;
+                    used |= 1u << sl;
+                    if (npush++ % NUM_PRODUCERS != ipw) continue;   // another producer's push: only the bookkeeping
+                    if (was_used && !mbar_wait(&bar_w_empty[sl], par, abortp)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&bar_w_full[sl], STAGE_B);
+                    bulk_copy_g2s(slot_ptr(sl), src + (size_t)i * STAGE_B, STAGE_B, &bar_w_full[sl]);
                 }
             };
             for (int l = l_begin; l < l_end && ok; ++l) {
@@ -778,20 +808,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 const int s_begin = LOCAL ? 0 : p.g_step;
                 const int s_end = LOCAL ? ly.steps : p.g_step + 1;
                 const bool gru = p.cell == CELL_GRU;
-                const int kx = ly.nres * NKS, kh = (ly.nres + 1) * NKS;
+                const size_t blk = (size_t)NKS * STAGE_B;   // one DP x DP block; a gate block is two of these per K segment
                 if (ly.nres > 0 && s_end > s_begin) {
                     for (int i = 0; i < ly.nres && ok; ++i) {
-                        if (gru) push_wide(ly.w_gate, i * NKS);
-                        push_block(ly.w_cand, i * NKS);
+                        if (gru) push(ly.w_gate + (size_t)i * 2 * blk, 2 * NKS, SET_BASE);
+                        push(ly.w_cand + (size_t)i * blk, NKS, SET_BASE);
                     }
                 }
+                const size_t kx = (size_t)ly.nres, kh = (size_t)ly.nres + 1;
                 for (int s = s_begin; s < s_end && ok; ++s) {
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
-                        push_block(ly.w_edge, t * NKS);
+                        push(ly.w_edge + (size_t)t * blk, NKS, SET_BASE);
                     }
-                    if (gru) { push_wide(ly.w_gate, kx); push_wide(ly.w_gate, kh); }
-                    push_block(ly.w_cand, kx); push_block(ly.w_cand, kh);
+                    // the opA tile joins the ring once no MMA reads it any more (this step's G1 / last step's candidate are complete)
+                    if (ok) { ok = mbar_wait(&bar_xa_free, ph_xa & 1, abortp); ++ph_xa; }
+                    if (gru) {
+                        push(ly.w_gate + kx * 2 * blk, 2 * NKS, SET_XA); push(ly.w_gate + kh * 2 * blk, 2 * NKS, SET_XA);
+                        // the opH tile joins the ring once the gate GEMM (its last reader) is complete
+                        if (ok) { ok = mbar_wait(&bar_xh_free, ph_xh & 1, abortp); ++ph_xh; }
+                        push(ly.w_cand + kx * blk, NKS, SET_XH); push(ly.w_cand + kh * blk, NKS, SET_XH);
+                    } else {
+                        push(ly.w_cand + kx * blk, NKS, SET_XA); push(ly.w_cand + kh * blk, NKS, SET_XA);
+                    }
                 }
             }
             if (!ok) atomicExch(p.error_flag, 3);

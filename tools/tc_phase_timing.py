@@ -31,7 +31,7 @@ ks = ts[40:60].copy()
 print("MMA warp: start-to-start cycles of the first 20 GEMM blocks (7 K-steps each):", (ks[1:] - ks[:-1]).tolist())
 ts = ts[:40]
 ts = ts[ts > 0]
-print(cfg, prec, eng.plan, "stages env", os.environ.get("GGNN_TC_STAGES"), "fake", os.environ.get("GGNN_TC_FAKE_WEIGHTS"))
-print("MMA thread: cycles waiting for weight stages %d, waiting for operands %d, total %d" % tuple(extra))
+print(cfg, prec, eng.plan, "stages env", os.environ.get("GGNN_TC_STAGES"))
+print("MMA issuer 0: cycles in slow waits for operands %d, total %d" % (extra[1], extra[2]))
 print("stamps:", len(ts), "total cycles:", int(ts[-1] - ts[0]))
 print("deltas:", (ts[1:] - ts[:-1]).tolist())
