@@ -650,6 +650,34 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     const int T = e->T;
     if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
     const int V = b * v;
+    {   // The reference only ever feeds 0/1 adjacency (dense:30-36).  A binary adjacency IS an edge list: A_t.(h W_t + b_t) =
+        // (sum of h over the row's sources) W_t + rowsum(A_t) b_t, which is exactly the sparse path with in-degree = row sums.
+        // Convert once on the host and use the CSR gather (deterministic source order j ascending) instead of the matrix walk.
+        const size_t n = (size_t)b * T * v * v;
+        bool binary = !getenv("GGNN_DENSE_KEEP_MATRIX");
+        for (size_t i = 0; i < n && binary; ++i) binary = (adjm[i] == 0.0f || adjm[i] == 1.0f);
+        if (binary) {
+            std::vector<std::vector<int32_t>> lists(T);
+            std::vector<float> indeg((size_t)std::max(V, 1) * T, 0.0f);
+            for (int g = 0; g < b; ++g)
+                for (int t = 0; t < T; ++t) {
+                    const float* m = adjm + ((size_t)g * T + t) * v * v;
+                    for (int i = 0; i < v; ++i)
+                        for (int j = 0; j < v; ++j)
+                            if (m[(size_t)i * v + j] != 0.0f) {
+                                lists[t].push_back(g * v + j);   // source
+                                lists[t].push_back(g * v + i);   // target
+                                indeg[((size_t)g * v + i) * T + t] += 1.0f;
+                            }
+                }
+            std::vector<const int32_t*> ptrs(T);
+            std::vector<int32_t> counts(T);
+            for (int t = 0; t < T; ++t) { ptrs[t] = lists[t].data(); counts[t] = (int32_t)(lists[t].size() / 2); }
+            int rc = ggnn_set_graph_sparse(e, V, ptrs.data(), counts.data(), indeg.data(), stream);
+            if (rc == GGNN_OK) { e->dense_v = v; e->plan_text += " [binary dense adjacency -> CSR]"; }
+            return rc;
+        }
+    }
     e->V = V; e->M = 0; e->gather_mode = GATHER_DENSE; e->dense_v = v;
     e->has_transpose = true;   // the dense adjacency is its own transpose source
     for (int t = 0; t < T; ++t) e->edges_of_type[t] = 1;
@@ -799,7 +827,7 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
     p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
     p.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
-    const size_t opb = (size_t)DP * 512, stage = (size_t)DP * 64;
+    const size_t opb = (size_t)DP * 512, stage = (size_t)DP * 128;   // a ring slot = two 64*DP-byte K-step stages
     // tile-local sparse graphs: stage the tile's CSR slice in shared memory when it is small enough
     p.csr_cache = 0; p.csr_cap_msgs = 0;
     size_t csr_b = 0;
@@ -810,10 +838,10 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     }
     const size_t bias_b = (size_t)3 * DP * sizeof(float) + csr_b + 64;
     const size_t avail = e->max_smem > 1024 ? e->max_smem - 1024 : 0;
-    if (avail < 3 * opb + bias_b + 2 * stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
+    if (avail < 3 * opb + bias_b + stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
     p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - 3 * opb - bias_b) / stage);
-    if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(2, std::min(p.nstages, atoi(ns)));
-    if (p.nstages < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the weight ring (DP=%d)", DP);
+    if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(1, std::min(p.nstages, atoi(ns)));
+    if (p.nstages < 1) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the weight ring (DP=%d)", DP);
     const size_t smem = 3 * opb + bias_b + (size_t)p.nstages * stage;
     char* g = (char*)e->graph_buf.ptr;
     p.tile_start = (const int*)(g + e->off_tiles);

@@ -17,9 +17,9 @@
 // latency bound (bytes in flight / slot round trip), so the ring is extended into A-operand tiles while they hold no live
 // operand: the A_t / r*h tile during the gate GEMM, the h tile during the candidate GEMM.
 // Warp roles: warps 0-15 = workers (gather, epilogues; TMEM lane quarter = warp%4, column-chunk group = warp/4),
-// warps 16-17 = MMA issuers (K-steps round-robin; every MMA accumulates into accumulators the workers zero after reading,
-// so cross-warp issue order is irrelevant), warps 18-19 = weight producers (one thread each, pushes round-robin; warp 18 also
-// allocates TMEM).  20 warps x 96 registers fill the register file; issuer/producer counts are compile-time knobs.
+// warps 16-17 = MMA issuers (each owns a fixed subset of the weight slots; every MMA accumulates into accumulators the workers zero after
+// reading, so cross-warp issue order is irrelevant), warp 18 = weight producer (ONE thread, strictly in order: parity-based
+// mbarrier waits are only sound when no agent can lap another by a whole ring) + TMEM allocator.
 // Every mbarrier wait is bounded; on timeout an error code is written and all roles drain.
 #pragma once
 #include <cuda_bf16.h>
@@ -35,15 +35,11 @@ constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane qu
 #define GGNN_TC_ISSUERS 2
 #endif
 constexpr int NUM_ISSUERS = GGNN_TC_ISSUERS;            // MMA-issuing warps (one per SM sub-partition); issuer i takes K-steps i, i+4, ...
-#ifndef GGNN_TC_PRODUCERS
-#define GGNN_TC_PRODUCERS 2
-#endif
-constexpr int NUM_PRODUCERS = GGNN_TC_PRODUCERS;   // weight-producer warps (one thread each); slot pushes are dealt round-robin
 constexpr int WARP_MMA = 16;              // first issuer warp
-constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // first producer warp (also the TMEM allocator)
-constexpr int NTHREADS = (WARP_PROD + NUM_PRODUCERS) * 32;
-constexpr int MAX_STAGES = 8;             // ring slots proper
-constexpr int EXT_SLOTS = 8;              // an idle A-operand tile holds exactly 8 more slots (DP*512 / DP*64)
+constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // weight producer (one thread, strictly in order) + TMEM allocator
+constexpr int NTHREADS = (WARP_PROD + 1) * 32;
+constexpr int MAX_STAGES = 4;             // ring slots proper; a slot holds TWO K-step stages (2 x 64*DP bytes, one bulk copy)
+constexpr int EXT_SLOTS = 4;              // an idle A-operand tile holds exactly 4 more slots (DP*512 / DP*128)
 constexpr int MAX_SLOTS = MAX_STAGES + 2 * EXT_SLOTS;
 enum { SET_BASE = 0, SET_XA = 1, SET_XH = 2 };   // ring only | ring + opA tile (gate phase) | ring + opH tile (candidate phase)
 
@@ -261,8 +257,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     uint8_t* opH = smem;
     uint8_t* opX = opH + OPB;
     uint8_t* opA = opX + OPB;
-    uint8_t* ring = opA + OPB;                             // nstages x STAGE_B, 1024-byte aligned (DP*512 and DP*64 are multiples of 1024)
-    float* sBias = reinterpret_cast<float*>(ring + (size_t)p.nstages * STAGE_B);   // [3*DP]: gate r | gate u | cand, zero padded
+    uint8_t* ring = opA + OPB;                             // nstages slots of 2*STAGE_B, 1024-byte aligned (DP*512 and DP*128 are multiples of 1024)
+    float* sBias = reinterpret_cast<float*>(ring + (size_t)p.nstages * 2 * STAGE_B);   // [3*DP]: gate r | gate u | cand, zero padded
     uint16_t* sRowPtr = reinterpret_cast<uint16_t*>(sBias + 3 * DP);              // [128*T + 1] (csr_cache)
     uint8_t* sSrc = reinterpret_cast<uint8_t*>(sRowPtr + ((TILE_M * T + 1 + 7) & ~7)); // [csr_cap_msgs]
 
@@ -455,10 +451,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                     unpack8_add(*reinterpret_cast<const uint4*>(sp), acc, 1.0f);
                                     if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + (size_t)DP * 256), acc, 1.0f);
                                 } else {
-                                    float hv[8];
-                                    load8_guarded_cg(p.g_in + (size_t)p.csr_src[m] * D, kc * 8, D, hv);
+                                    // GLOBAL mode: source rows come from the previous step's fp32 state in L2; keep 4 rows in flight
+                                    float hv[4][8];
+                                    const int nb = min(4, end - m);
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) acc[j] += hv[j];
+                                    for (int q = 0; q < 4; ++q)
+                                        if (q < nb) load8_guarded_cg(p.g_in + (size_t)p.csr_src[m + q] * D, kc * 8, D, hv[q]);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        if (q < nb) {
+#pragma unroll
+                                            for (int j = 0; j < 8; ++j) acc[j] += hv[q][j];
+                                        }
+                                    m += nb - 1;
                                 }
                             }
                         } else if (row_ok) {
@@ -652,8 +657,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
             };
             auto slot16 = [&](uint32_t sl) -> uint32_t {
-                return sl < nstg ? ring16 + sl * stage16
-                     : sl < nstg + EXT_SLOTS ? opA16 + (sl - nstg) * stage16 : opH16 + (sl - nstg - EXT_SLOTS) * stage16;
+                return sl < nstg ? ring16 + sl * 2u * stage16
+                     : sl < nstg + EXT_SLOTS ? opA16 + (sl - nstg) * 2u * stage16 : opH16 + (sl - nstg - EXT_SLOTS) * 2u * stage16;
             };
             auto wait_full = [&](uint32_t sl) {
                 const uint32_t par = (fpar >> sl) & 1u;
@@ -667,47 +672,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             auto commit_empty = [&](uint32_t sl) {
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + sl * 8u) : "memory");
             };
-            // acc(tm_col) += A(op) . B(next weight slots of `set`): NKS K-steps of 1 or 3 MMAs each; accumulators are zeroed by the workers
-            //   narrow (N = DP):   one slot per K-step holds [hi | lo] halves of the DP-wide weight block
-            //   wide   (N = 2*DP): two slots per K-step: hi part, lo part of the [r | u] gate block
+            // acc(tm_col) += A(op) . B(next weight slots of `set`); accumulators are zeroed by the workers.  A slot = two stages:
+            //   narrow (N = DP):   K-steps 2i and 2i+1 of a DP-wide block, each stage = [hi | lo] halves        (odd tail: one stage)
+            //   wide   (N = 2*DP): one K-step of the [r | u] gate block, stage 0 = hi part, stage 1 = lo part
+            // Each slot belongs to one issuer warp (slot index modulo the number of issuers).
             auto gemm = [&](uint32_t op16, uint32_t tm_col, bool wide, int set) {
                 if (!ok) return;
                 if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
                 const uint32_t tm_d = tmem_u + tm_col;
+                const int nslots = wide ? NKS : (NKS + 1) / 2;
 #pragma unroll 1
-                for (int ks = 0; ks < NKS; ++ks) {
-                    const uint32_t s0 = next_slot(set);
-                    const uint32_t s1 = wide ? next_slot(set) : 0u;
-                    if ((uint32_t)ks % NUM_ISSUERS != iw) {   // someone else's K-step: only keep the slot parities in step
-                        fpar ^= 1u << s0;
-                        if (wide) fpar ^= 1u << s1;
-                        continue;
-                    }
-                    wait_full(s0);
-                    if (wide) wait_full(s1);
+                for (int i = 0; i < nslots; ++i) {
+                    const uint32_t sl = next_slot(set);
+                    // STATIC slot ownership: every use of a slot is consumed by the same issuer, so that issuer observes each
+                    // phase of the slot's barrier in order.  (Parity waits alias if a waiter can be two phases ahead, which
+                    // round-robin ownership allows when bulk copies complete out of order or the ring is a single slot.)
+                    if (sl % NUM_ISSUERS != iw) continue;
+                    wait_full(sl);
                     if (!ok) return;
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)ks * 256u);
-                        if (!wide) {
-                            const uint64_t bd = descB1 | (uint64_t)slot16(s0);
-                            umma_bf16(tm_d, ad, bd, idesc, 1u);
-                            if (x3) {
-                                umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
-                                umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
-                            }
-                            commit_empty(s0);
-                        } else {
-                            const uint64_t bh = descB2 | (uint64_t)slot16(s0);
-                            const uint64_t bl = descB2 | (uint64_t)slot16(s1);
+                        const uint32_t b16 = slot16(sl);
+                        if (wide) {
+                            const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)i * 256u);
+                            const uint64_t bh = descB2 | (uint64_t)b16, bl = descB2 | (uint64_t)(b16 + stage16);
                             umma_bf16(tm_d, ad, bh, idesc2, 1u);
                             if (x3) {
                                 umma_bf16(tm_d, ad, bl, idesc2, 1u);
                                 umma_bf16(tm_d, ad + a_lo16, bh, idesc2, 1u);
                             }
-                            commit_empty(s0);
-                            commit_empty(s1);
+                        } else {
+                            const int nk = (2 * i + 1 < NKS) ? 2 : 1;
+                            for (int h = 0; h < nk; ++h) {
+                                const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)(2 * i + h) * 256u);
+                                const uint64_t bd = descB1 | (uint64_t)(b16 + (uint32_t)h * stage16);
+                                umma_bf16(tm_d, ad, bd, idesc, 1u);
+                                if (x3) {
+                                    umma_bf16(tm_d, ad, bd + b_lo16, idesc, 1u);
+                                    umma_bf16(tm_d, ad + a_lo16, bd, idesc, 1u);
+                                }
+                            }
                         }
+                        commit_empty(sl);   // slot reusable once these MMAs have read it
                     }
                     __syncwarp();
                 }
@@ -768,12 +774,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         }
     } else {
         // =============================================================================== WEIGHT PRODUCER
-        // The stream is bound by the per-push issue cost of a single thread (wait, expect_tx, bulk copy: ~430 cycles per 7 KB slot),
-        // so several producer warps share it: all walk the same slot sequence, producer i issues pushes i, i + NUM_PRODUCERS, ...
+        // One thread, strictly in order.  The stream is bound by the per-push issue cost (wait, expect_tx, bulk copy: ~430 cycles),
+        // so a push moves a whole slot = two stages (2 x 64*DP bytes, contiguous in the pre-tiled weights) with one bulk copy.
         if (lane == 0) {
             const uint32_t nstg = (uint32_t)nst;
-            const uint32_t ipw = (uint32_t)(warp - WARP_PROD);
-            uint32_t npush = 0;
             uint32_t cur[3] = {0, 0, 0};
             uint32_t used = 0, epar = 0;   // bit s: slot s has been filled before / parity to wait for on bar_w_empty[s]
             uint32_t ph_xa = 0, ph_xh = 0;
@@ -785,22 +789,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
             };
             auto slot_ptr = [&](uint32_t sl) -> uint8_t* {
-                return sl < nstg ? ring + sl * STAGE_B
-                     : sl < nstg + EXT_SLOTS ? opA + (sl - nstg) * STAGE_B : opH + (sl - nstg - EXT_SLOTS) * STAGE_B;
+                return sl < nstg ? ring + sl * 2u * STAGE_B
+                     : sl < nstg + EXT_SLOTS ? opA + (sl - nstg) * 2u * STAGE_B : opH + (sl - nstg - EXT_SLOTS) * 2u * STAGE_B;
             };
-            // stream `count` consecutive 64*DP-byte stages of a pre-tiled matrix into the next slots of `set`
-            auto push = [&](const uint8_t* src, int count, int set) {
-                for (int i = 0; i < count && ok; ++i) {
+            // stream `nstages` consecutive 64*DP-byte stages of a pre-tiled matrix, two per slot, into the next slots of `set`
+            auto push = [&](const uint8_t* src, int nstages, int set) {
+                for (int i = 0; i < nstages && ok; i += 2) {
+                    const uint32_t bytes = (i + 1 < nstages) ? 2u * STAGE_B : STAGE_B;
                     const uint32_t sl = next_slot(set);
                     // a slot is free once the MMAs that read its previous contents have completed (first use: free)
-                    const bool was_used = (used >> sl) & 1u;
-                    const uint32_t par = (epar >> sl) & 1u;
-                    if (was_used) epar ^= 1u << sl;
+                    if ((used >> sl) & 1u) {
+                        if (!mbar_wait(&bar_w_empty[sl], (epar >> sl) & 1u, abortp)) { ok = false; break; }
+                        epar ^= 1u << sl;
+                    }
                     used |= 1u << sl;
-                    if (npush++ % NUM_PRODUCERS != ipw) continue;   // another producer's push: only the bookkeeping
-                    if (was_used && !mbar_wait(&bar_w_empty[sl], par, abortp)) { ok = false; break; }
-                    mbar_arrive_expect_tx(&bar_w_full[sl], STAGE_B);
-                    bulk_copy_g2s(slot_ptr(sl), src + (size_t)i * STAGE_B, STAGE_B, &bar_w_full[sl]);
+                    mbar_arrive_expect_tx(&bar_w_full[sl], bytes);
+                    bulk_copy_g2s(slot_ptr(sl), src + (size_t)i * STAGE_B, bytes, &bar_w_full[sl]);
                 }
             };
             for (int l = l_begin; l < l_end && ok; ++l) {

@@ -200,3 +200,23 @@ def test_full_size_cfg4_properties():
     idx = np.concatenate([np.arange(starts[i], starts[i + 1]) for i in range(len(mols) - 1, -1, -1)])
     got2 = U.engine_sparse(CFG4, 8, w, b2["adjacency_lists"], b2["num_incoming_edges_per_type"], h0[idx])
     np.testing.assert_allclose(got2, got[idx], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_dense_weighted_adjacency_uses_the_matrix_path(precision, monkeypatch):
+    """A non-binary adjacency cannot be an edge list: the engine keeps the [b,T,v,v] matrix and multiplies by its entries
+    (the reference's matmul semantics, dense:110-112); a binary one is converted to CSR -- both must agree with the oracle."""
+    D, T, steps, b, v = 24, 3, 2, 5, 16
+    rng = np.random.default_rng(11)
+    A = (rng.random((b, T, v, v)) < 0.15).astype(np.float32)
+    Aw = A * rng.uniform(0.25, 1.5, size=A.shape).astype(np.float32)
+    h0 = rng.normal(0, 0.3, (b, v, D)).astype(np.float32)
+    dw = O.init_dense_weights({"hidden_size": D}, T, np.random.default_rng(5))
+    dp = {"num_timesteps": steps, "use_edge_bias": True}
+    for adj in (Aw, A):
+        ref = O.dense_propagation_loops(h0, adj, dw, dp)
+        got = U.engine_dense(dp, T, dw, adj, h0, precision=precision)
+        assert U.max_rel_err(got, ref) < 1e-4
+    monkeypatch.setenv("GGNN_DENSE_KEEP_MATRIX", "1")   # binary adjacency through the matrix path as well
+    got = U.engine_dense(dp, T, dw, A, h0, precision=precision)
+    assert U.max_rel_err(got, O.dense_propagation_loops(h0, A, dw, dp)) < 1e-4
