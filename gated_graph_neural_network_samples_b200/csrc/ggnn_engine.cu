@@ -92,6 +92,7 @@ struct ggnn_engine {
     // device memory
     DevBuf graph_buf;   // packed: row_ptr | csr_src | csr_msg | indeg | denom | tile_start | tile_mask | (dense adj)
     HostPinned graph_stage;
+    cudaEvent_t stage_done = nullptr;   // recorded after the staged H2D copy: the next set_graph waits for it before refilling
     size_t off_row_ptr = 0, off_src = 0, off_msg = 0, off_indeg = 0, off_denom = 0, off_tiles = 0, off_mask = 0, off_adj = 0;
     size_t off_trow = 0, off_ttgt = 0;   // source-keyed CSR (rows source*T+type -> targets), built when save_for_backward is on
     bool has_transpose = false;
@@ -485,6 +486,7 @@ int ggnn_destroy(ggnn_engine* e) {
     e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
     e->tc_weights.release(); e->tc_respre.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
+    if (e->stage_done) cudaEventDestroy(e->stage_done);
     delete e;
     return GGNN_OK;
 }
@@ -510,6 +512,8 @@ int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t n
 static int upload_graph(ggnn_engine* e, size_t bytes, cudaStream_t st) {
     CU_TRY(e, e->graph_buf.reserve(bytes));
     CU_TRY(e, cudaMemcpyAsync(e->graph_buf.ptr, e->graph_stage.ptr, bytes, cudaMemcpyHostToDevice, st));
+    if (!e->stage_done) CU_TRY(e, cudaEventCreateWithFlags(&e->stage_done, cudaEventDisableTiming));
+    CU_TRY(e, cudaEventRecord(e->stage_done, st));
     return GGNN_OK;
 }
 
@@ -580,6 +584,7 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
         e->off_ttgt = off; off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
     }
     for (int t = 0; t < T; ++t) e->edges_of_type[t] = num_edges[t];
+    if (e->stage_done) CU_TRY(e, cudaEventSynchronize(e->stage_done));   // previous upload may still be reading the stage
     CU_TRY(e, e->graph_stage.reserve(off));
     char* base = (char*)e->graph_stage.ptr;
     int* row_ptr = (int*)(base + e->off_row_ptr);
@@ -653,23 +658,33 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     {   // The reference only ever feeds 0/1 adjacency (dense:30-36).  A binary adjacency IS an edge list: A_t.(h W_t + b_t) =
         // (sum of h over the row's sources) W_t + rowsum(A_t) b_t, which is exactly the sparse path with in-degree = row sums.
         // Convert once on the host and use the CSR gather (deterministic source order j ascending) instead of the matrix walk.
-        const size_t n = (size_t)b * T * v * v;
         bool binary = !getenv("GGNN_DENSE_KEEP_MATRIX");
-        for (size_t i = 0; i < n && binary; ++i) binary = (adjm[i] == 0.0f || adjm[i] == 1.0f);
+        std::vector<std::vector<int32_t>> lists(T);
+        std::vector<float> indeg;
         if (binary) {
-            std::vector<std::vector<int32_t>> lists(T);
-            std::vector<float> indeg((size_t)std::max(V, 1) * T, 0.0f);
-            for (int g = 0; g < b; ++g)
-                for (int t = 0; t < T; ++t) {
+            indeg.assign((size_t)std::max(V, 1) * T, 0.0f);
+            for (int t = 0; t < T; ++t) lists[t].reserve((size_t)V * 6);
+            for (int g = 0; g < b && binary; ++g)
+                for (int t = 0; t < T && binary; ++t) {
                     const float* m = adjm + ((size_t)g * T + t) * v * v;
-                    for (int i = 0; i < v; ++i)
-                        for (int j = 0; j < v; ++j)
-                            if (m[(size_t)i * v + j] != 0.0f) {
-                                lists[t].push_back(g * v + j);   // source
-                                lists[t].push_back(g * v + i);   // target
-                                indeg[((size_t)g * v + i) * T + t] += 1.0f;
+                    std::vector<int32_t>& lst = lists[t];
+                    for (int i = 0; i < v && binary; ++i) {
+                        const float* row = m + (size_t)i * v;
+                        int cnt = 0;
+                        for (int j = 0; j < v; ++j) {
+                            const float a = row[j];
+                            if (a != 0.0f) {
+                                if (a != 1.0f) { binary = false; break; }
+                                lst.push_back(g * v + j);   // source
+                                lst.push_back(g * v + i);   // target
+                                ++cnt;
                             }
+                        }
+                        indeg[((size_t)g * v + i) * T + t] = (float)cnt;
+                    }
                 }
+        }
+        if (binary) {
             std::vector<const int32_t*> ptrs(T);
             std::vector<int32_t> counts(T);
             for (int t = 0; t < T; ++t) { ptrs[t] = lists[t].data(); counts[t] = (int32_t)(lists[t].size() / 2); }
@@ -697,6 +712,7 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     e->off_tiles = off;   off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
     e->off_mask = off;    off = align_up(off + sizeof(unsigned) * (size_t)std::max(ntiles, 1), 16);
     e->off_adj = off;     off = align_up(off + sizeof(float) * std::max<size_t>(adj_elems, 1), 16);
+    if (e->stage_done) CU_TRY(e, cudaEventSynchronize(e->stage_done));   // previous upload may still be reading the stage
     CU_TRY(e, e->graph_stage.reserve(off));
     char* base = (char*)e->graph_stage.ptr;
     float* h_indeg = (float*)(base + e->off_indeg);
@@ -962,7 +978,7 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
     return GGNN_OK;
 }
 
-int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream) {
+int ggnn_forward_host_async(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
     if (!e->graph_set) return e->fail(GGNN_ESTATE, "no graph set (ggnn_set_graph_sparse/dense)");
     if ((!h0_host || !h_out_host) && e->V > 0) return e->fail(GGNN_EINVAL, "null host pointer");
@@ -977,7 +993,13 @@ int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, g
     int rc = ggnn_forward(e, d_in, d_out, stream);
     if (rc) return rc;
     if (bytes) CU_TRY(e, cudaMemcpyAsync(h_out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
-    CU_TRY(e, cudaStreamSynchronize(st));
+    return GGNN_OK;
+}
+
+int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream) {
+    int rc = ggnn_forward_host_async(e, h0_host, h_out_host, stream);
+    if (rc) return rc;
+    CU_TRY(e, cudaStreamSynchronize((cudaStream_t)stream));
     return GGNN_OK;
 }
 

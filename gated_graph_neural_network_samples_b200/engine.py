@@ -165,14 +165,16 @@ class PropagationEngine:
         self._check(self.lib.ggnn_forward(self._h, h0.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def forward_host(self, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Same through HOST buffers (H2D + propagation + D2H inside the call, synchronous)."""
+    def forward_host(self, h0: np.ndarray, out: Optional[np.ndarray] = None, sync: bool = True) -> np.ndarray:
+        """Same through HOST buffers (H2D + propagation + D2H inside the call).  ``sync=False`` returns right after
+        enqueueing (pinned buffers required); the result is valid after ``sync_check()``."""
         h0 = np.ascontiguousarray(h0, dtype=np.float32)
         if h0.size != self.V * self.D:
             raise GgnnError("h0 has %d elements, the graph has %d nodes x %d" % (h0.size, self.V, self.D))
         if out is None:
             out = np.empty_like(h0)
-        self._check(self.lib.ggnn_forward_host(self._h, h0.ctypes.data, out.ctypes.data, self._stream()))
+        fn = self.lib.ggnn_forward_host if sync else self.lib.ggnn_forward_host_async
+        self._check(fn(self._h, h0.ctypes.data, out.ctypes.data, self._stream()))
         return out
 
     def sync_check(self):

@@ -110,6 +110,9 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
 
 /* Same with HOST buffers: H2D copy of h0, propagation, D2H copy of the result, stream-synchronised. */
 int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
+/* ... without the final synchronisation (pinned host buffers; pair with ggnn_sync_check): lets a caller keep two batches in
+ * flight on two engines/streams, the way ChemModel's ThreadedIterator overlaps packing with sess.run (chem_tensorflow.py:225). */
+int ggnn_forward_host_async(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
 
 /* Synchronises `stream` and reports asynchronous kernel-side failures (a bounded barrier wait that expired). */
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream);

@@ -166,6 +166,33 @@ def test_host_buffer_call_matches_device_call():
     assert eng.last_launch_count == 1 and "LOCAL" in eng.plan
 
 
+def test_two_batches_in_flight_on_two_engines():
+    """forward_host(sync=False) on two engines / two streams: both results equal the synchronous call."""
+    import torch
+    from gated_graph_neural_network_samples_b200.engine import PropagationEngine
+    w = U.to_cuda_weights(O.init_sparse_weights(CFG2, 4, np.random.default_rng(1)))
+    batches = [U.molecule_batch(24 + 8 * k, 100, seed=5 + k)[1] for k in range(2)]
+    engs, streams, outs, ins = [], [], [], []
+    for b in batches:
+        e = PropagationEngine(CFG2, 4)
+        e.set_weights(w)
+        engs.append(e)
+        streams.append(torch.cuda.Stream())
+        ins.append(torch.from_numpy(b["initial_node_representation"]).pin_memory())
+        outs.append(torch.empty_like(ins[-1]).pin_memory())
+    for rep in range(3):
+        for k, b in enumerate(batches):
+            with torch.cuda.stream(streams[k]):
+                engs[k].set_graph_sparse(b["adjacency_lists"], b["num_incoming_edges_per_type"])
+                engs[k].forward_host(ins[k].numpy(), outs[k].numpy(), sync=False)
+        for k in range(2):
+            with torch.cuda.stream(streams[k]):
+                engs[k].sync_check()
+    for k, b in enumerate(batches):
+        ref = engs[k].forward_host(b["initial_node_representation"])
+        np.testing.assert_allclose(outs[k].numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
 def test_error_behaviour_matches_reference():
     from gated_graph_neural_network_samples_b200.engine import GgnnError, PropagationEngine
     with pytest.raises(Exception, match="Unknown activation"):
