@@ -59,9 +59,11 @@ class DenseGGNNChemModel(ChemModel):
         self.engine.set_save_for_backward(torch.is_grad_enabled())
         self.engine.set_graph_dense(adj)
         keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
-        if keep < 1.0 or float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0)) < 1.0:
+        if keep < 1.0:
             # the dense reference draws a fresh weight-dropout mask per timestep and type (dense:104); not supported
-            raise Exception("dropout inside the dense propagation is not supported by the B200 engine")
+            raise Exception("edge-weight dropout inside the dense propagation is not supported by the B200 engine")
+        state_keep = float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0))          # DropoutWrapper, dense:89
+        self.engine.set_state_dropout(state_keep, int(torch.randint(0, 2 ** 62, (1,)).item()) if state_keep < 1.0 else 0)
         flat, lay = [self.weights['edge_weights']], {'edge_weights': 0}
         if 'edge_biases' in self.weights:
             lay['edge_biases'] = len(flat); flat.append(self.weights['edge_biases'].view(T, D))

@@ -124,8 +124,10 @@ class SparseGGNNChemModel(ChemModel):
         adjacency_lists = [feed[k] for k in self.placeholders['adjacency_lists']]
         self.engine.set_save_for_backward(torch.is_grad_enabled())   # before set_graph: the source-keyed CSR is built there
         self.engine.set_graph_sparse(adjacency_lists, feed[self.placeholders['num_incoming_edges_per_type']])
-        if float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0)) < 1.0:
-            raise Exception("graph_state_dropout_keep_prob < 1 is not supported by the B200 engine")   # DropoutWrapper, sparse:113-114
+        state_keep = float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0))
+        # DropoutWrapper(state_keep_prob), sparse:113-114: done inside the kernels; a fresh mask seed per run, drawn from
+        # torch's generator (seeded by params['random_seed'] like tf.set_random_seed, chem_tensorflow.py:85)
+        self.engine.set_state_dropout(state_keep, int(torch.randint(0, 2 ** 62, (1,)).item()) if state_keep < 1.0 else 0)
         keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
         flat, layout = [], []
         for l in range(len(self.params['layer_timesteps'])):

@@ -143,10 +143,17 @@ __global__ void gru_bwd2_kernel(const float* __restrict__ dXc, int ldx, int rh_o
         dpg[row * 2 * D + col] = drh * h[i] * rr * (1.0f - rr);
     }
 }
-// RNN: dpc = dh' act'(h')
-__global__ void rnn_bwd1_kernel(const float* __restrict__ dhn, const float* __restrict__ hnew, float* __restrict__ dpc, long long n, int act) {
+// RNN: dpc = dh' act'(h')   (yscale = keep_prob undoes the state dropout's 1/keep on the saved output; dropped entries have dh' = 0)
+__global__ void rnn_bwd1_kernel(const float* __restrict__ dhn, const float* __restrict__ hnew, float* __restrict__ dpc, long long n, int act, float yscale) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dpc[i] = dhn[i] * act_grad_from_output(hnew[i], act);
+        dpc[i] = dhn[i] * act_grad_from_output(hnew[i] * yscale, act);
+}
+// state dropout backward, in place: d(pre-dropout state) = d(state) * mask / keep   (mask regenerated, ggnn_common.cuh)
+__global__ void dropout_grad_kernel(float* __restrict__ dhn, unsigned long long seed, int gstep, int V, int D, float keep, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(i / D), col = (int)(i - (long long)row * D);
+        dhn[i] = dropout_apply(dhn[i], seed, gstep, V, D, row, col, keep);
+    }
 }
 // Split the gradient of the cell input row [res_0 .. res_{R-1} | x | h-or-rh]:
 //   dres_i[v] += dX[v, i*D..]   dxp[v] = dX[v, x segment] (/ denom)   (GRU second pass / RNN: dh (+)= dX[v, last segment])

@@ -56,7 +56,25 @@ struct FwdParams {
     int g_layer, g_step;
     const float* g_in;
     float* g_out;
+    // DropoutWrapper(state_keep_prob) (sparse:113-114,216 / dense:89): off when drop_keep >= 1
+    float drop_keep;
+    unsigned long long drop_seed;
 };
+
+// State-dropout mask: a counter-based hash (splitmix64 finaliser) of (seed, global step, node, column), so the forward
+// kernels, the backward pass and the test oracle regenerate the same mask without storing it.  TF's own generator cannot
+// be reproduced; what is kept is DropoutWrapper's arithmetic: kept values are DIVIDED by keep_prob, dropped ones are 0.
+__host__ __device__ __forceinline__ bool dropout_keeps(unsigned long long seed, int gstep, int V, int D, int row, int col, float keep) {
+    unsigned long long x = ((unsigned long long)gstep * (unsigned long long)V + (unsigned long long)row) * (unsigned long long)D + (unsigned long long)col;
+    x += (seed + 1ull) * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (float)(x >> 40) * (1.0f / 16777216.0f) < keep;
+}
+__host__ __device__ __forceinline__ float dropout_apply(float v, unsigned long long seed, int gstep, int V, int D, int row, int col, float keep) {
+    return dropout_keeps(seed, gstep, V, D, row, col, keep) ? v / keep : 0.0f;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

@@ -112,6 +112,8 @@ struct ggnn_engine {
     float* last_out = nullptr;
     bool save = false;
     bool saved_valid = false;
+    float drop_keep = 1.0f; unsigned long long drop_seed = 0;          // state dropout for the next forward
+    float saved_drop_keep = 1.0f; unsigned long long saved_drop_seed = 0; // ... and what the saved forward used
     int last_launches = 0;
     std::string err;
 
@@ -363,6 +365,10 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
         for (int s = e->steps[l] - 1; s >= 0; --s) {
             const size_t so = (size_t)(e->step_base[l] + s) * vd;
             const float *h = sv_h + so, *x = sv_x + so;
+            if (e->saved_drop_keep < 1.0f) {
+                dropout_grad_kernel<<<eb, 256, 0, st>>>(dhn, e->saved_drop_seed, e->step_base[l] + s, V, D, e->saved_drop_keep, n);
+                ++e->last_launches;
+            }
             auto seg_src = [&](int i) -> const float* { return i < R ? fstate[e->res[l][i]] : (i == R ? x : nullptr); };
             if (e->cell == CELL_GRU) {
                 const float *r = sv_r + so, *u = sv_u + so, *c = sv_c + so;
@@ -380,7 +386,7 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
                 ++e->last_launches;
             } else {
                 const float* hnew = (s == e->steps[l] - 1) ? fstate[l + 1] : sv_h + so + vd;
-                rnn_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, hnew, dpc, n, e->act); ++e->last_launches;
+                rnn_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, hnew, dpc, n, e->act, e->saved_drop_keep < 1.0f ? e->saved_drop_keep : 1.0f); ++e->last_launches;
                 gemm_nt(false, dpc, D, w.cand_kernel, D, dxc, ldx, V, ldx, D);
                 for (int i = 0; i <= R + 1; ++i)
                     gemm_tn(i <= R ? seg_src(i) : h, D, dpc, D, gw.cand_kernel ? gw.cand_kernel + (size_t)i * D * D : nullptr, D, V, D, D);
@@ -767,6 +773,7 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
     p.V = e->V; p.D = e->D; p.T = e->T; p.L = e->L;
     p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
     p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
+    p.drop_keep = e->drop_keep; p.drop_seed = e->drop_seed;
     char* g = (char*)e->graph_buf.ptr;
     p.tile_start = (const int*)(g + e->off_tiles);
     p.tile_mask = (const unsigned*)(g + e->off_mask);
@@ -843,6 +850,7 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
     p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
     p.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
+    p.drop_keep = e->drop_keep; p.drop_seed = e->drop_seed;
     const size_t opb = (size_t)DP * 512, stage = (size_t)DP * 128;   // a ring slot = two 64*DP-byte K-step stages
     // tile-local sparse graphs: stage the tile's CSR slice in shared memory when it is small enough
     p.csr_cache = 0; p.csr_cap_msgs = 0;
@@ -921,7 +929,7 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
         }
     }
     CU_TRY(e, cudaGetLastError());
-    if (e->save) e->saved_valid = true;
+    if (e->save) { e->saved_valid = true; e->saved_drop_keep = e->drop_keep; e->saved_drop_seed = e->drop_seed; }
     return GGNN_OK;
 }
 
@@ -974,7 +982,7 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
         }
     }
     CU_TRY(e, cudaGetLastError());
-    if (e->save) e->saved_valid = true;
+    if (e->save) { e->saved_valid = true; e->saved_drop_keep = e->drop_keep; e->saved_drop_seed = e->drop_seed; }
     return GGNN_OK;
 }
 
@@ -1029,6 +1037,22 @@ int ggnn_set_save_for_backward(ggnn_engine* e, int32_t enable) {
     if (!e) return GGNN_EINVAL;
     e->save = enable != 0;
     e->saved_valid = false;
+    return GGNN_OK;
+}
+
+int ggnn_set_state_dropout(ggnn_engine* e, float keep_prob, uint64_t seed) {
+    if (!e) return GGNN_EINVAL;
+    if (!(keep_prob > 0.0f) || keep_prob > 1.0f) return e->fail(GGNN_EINVAL, "state keep probability must be in (0, 1], got %g", (double)keep_prob);
+    e->drop_keep = keep_prob;
+    e->drop_seed = (unsigned long long)seed;
+    return GGNN_OK;
+}
+
+int ggnn_state_dropout_mask(int32_t V, int32_t D, int32_t global_step, float keep_prob, uint64_t seed, uint8_t* mask_out) {
+    if (V < 0 || D <= 0 || (!mask_out && V > 0)) return GGNN_EINVAL;
+    for (int r = 0; r < V; ++r)
+        for (int c = 0; c < D; ++c)
+            mask_out[(size_t)r * D + c] = dropout_keeps((unsigned long long)seed, global_step, V, D, r, c, keep_prob) ? 1 : 0;
     return GGNN_OK;
 }
 

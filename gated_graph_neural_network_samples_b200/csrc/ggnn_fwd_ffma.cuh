@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
                                 const float c = activate(acc1[j][r] + bc, p.act);
                                 const float u = sU[row * D + col];
                                 const float h = sH[row * D + col];
-                                sH[row * D + col] = u * h + (1.0f - u) * c;
+                                float hn = u * h + (1.0f - u) * c;
+                                if (p.drop_keep < 1.0f) hn = dropout_apply(hn, p.drop_seed, p.step_base[l] + s, p.V, D, row0 + row, col, p.drop_keep);
+                                sH[row * D + col] = hn;
                                 if (p.save) p.save_buf.c[save_off + (size_t)(row0 + row) * D + col] = c;
                             }
                         }
@@ -322,7 +324,11 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
 #pragma unroll
                         for (int r = 0; r < 8; ++r) {
                             const int row = rg * 8 + r;
-                            if (row < rows) sA[row * D + col] = activate(acc1[j][r] + bc, p.act);
+                            if (row < rows) {
+                                float hn = activate(acc1[j][r] + bc, p.act);
+                                if (p.drop_keep < 1.0f) hn = dropout_apply(hn, p.drop_seed, p.step_base[l] + s, p.V, D, row0 + row, col, p.drop_keep);
+                                sA[row * D + col] = hn;
+                            }
                         }
                     }
                 }

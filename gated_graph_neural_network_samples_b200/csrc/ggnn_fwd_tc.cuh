@@ -80,6 +80,8 @@ struct TcParams {
     int g_layer, g_step;
     const float* g_in;
     float* g_out;
+    float drop_keep;                // state dropout (ggnn_common.cuh dropout_apply); off when >= 1
+    unsigned long long drop_seed;
     int* error_flag;
     long long* dbg;  // optional [64] clock64 stamps written by tile 0 / thread 0 (profiling aid), or nullptr
 };
@@ -603,6 +605,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
 #pragma unroll
                             for (int j = 0; j < 8; ++j) hn[j] = act_fast(c[j] + bc[j], p.act);
                             if (p.save && row_ok) store8_guarded(p.save_buf.h_in + save_off, kc * 8, D, h);
+                        }
+                        if (p.drop_keep < 1.0f) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                hn[j] = dropout_apply(hn[j], p.drop_seed, p.step_base[l] + s, p.V, D, grow, kc * 8 + j, p.drop_keep);
                         }
                         tmem_st8(TM_H + lane_addr + kc * 8, hn);
                         store_operand_chunk(opH, DP, kc, row, hn);

@@ -181,6 +181,16 @@ class PropagationEngine:
         """Synchronise the stream and raise if a kernel reported an (always bounded) barrier timeout."""
         self._check(self.lib.ggnn_sync_check(self._h, self._stream()))
 
+    def set_state_dropout(self, keep_prob: float, seed: int = 0):
+        """DropoutWrapper(state_keep_prob) (sparse:113-114): applies to the following forwards; 1.0 = off."""
+        self._check(self.lib.ggnn_set_state_dropout(self._h, float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def state_dropout_mask(self, global_step: int, keep_prob: float, seed: int, V: Optional[int] = None) -> np.ndarray:
+        V = self.V if V is None else V
+        m = np.empty((V, self.D), np.uint8)
+        self._check(self.lib.ggnn_state_dropout_mask(V, self.D, int(global_step), float(keep_prob), int(seed) & 0xFFFFFFFFFFFFFFFF, m.ctypes.data))
+        return m
+
     def set_save_for_backward(self, enable: bool):
         self._check(self.lib.ggnn_set_save_for_backward(self._h, int(bool(enable))))
 

@@ -117,6 +117,16 @@ int ggnn_forward_host_async(ggnn_engine* e, const float* h0_host, float* h_out_h
 /* Synchronises `stream` and reports asynchronous kernel-side failures (a bounded barrier wait that expired). */
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream);
 
+/* DropoutWrapper(cell, state_keep_prob) of sparse:113-114 / dense:89 (the reference keeps element [1], the dropped STATE,
+ * sparse:216): every timestep's new state is multiplied by a keep mask and DIVIDED by keep_prob before it is stored and
+ * carried on.  keep_prob = 1 (the default, and what the reference feeds in evaluation, sparse:284) turns it off.  The mask is
+ * a counter-based hash of (seed, global timestep, node, column) -- TensorFlow's own random stream cannot be reproduced -- so
+ * ggnn_backward regenerates it; use a fresh seed per training step.  Applies to the following ggnn_forward calls. */
+int ggnn_set_state_dropout(ggnn_engine* e, float keep_prob, uint64_t seed);
+/* The same mask on the host ([V, D] bytes, 1 = kept) for timestep `global_step` (layers' timesteps numbered consecutively):
+ * lets a caller or a test restate the dropped forward. */
+int ggnn_state_dropout_mask(int32_t V, int32_t D, int32_t global_step, float keep_prob, uint64_t seed, uint8_t* mask_out);
+
 /* Gradient of the propagation (what optimizer.compute_gradients builds, chem_tensorflow.py:184).
  * Must follow a ggnn_forward on the same graph with save_for_backward enabled.
  * d_h_out: DEVICE [V, D]; grads: per layer, accumulated into; d_h0: DEVICE [V, D] or NULL. */

@@ -291,8 +291,23 @@ def stable_target_csr(adjacency_lists, V):
 # ----------------------------------------------------------------------------------------------
 # fp32 PyTorch-CPU restatement at the TF graph's op granularity -- the timed "reference CPU path"
 # ----------------------------------------------------------------------------------------------
+def state_dropout_mask(seed, global_step, V, D, keep):
+    """The engine's state-dropout keep mask ([V, D] bool), restated: splitmix64 finaliser of
+    ((global_step*V + node)*D + column) + (seed+1)*golden-ratio, top 24 bits as a uniform in [0,1), kept iff < fp32(keep).
+    (DropoutWrapper's own random stream is TensorFlow's and cannot be reproduced -- sparse:113-114.)"""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        idx = (np.uint64(global_step) * np.uint64(V) + np.arange(V, dtype=np.uint64)[:, None]) * np.uint64(D) + np.arange(D, dtype=np.uint64)[None, :]
+        x = idx + np.uint64((int(seed) + 1) * 0x9E3779B97F4A7C15 & 0xFFFFFFFFFFFFFFFF)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9)
+        x ^= x >> np.uint64(27); x *= np.uint64(0x94D049BB133111EB)
+        x ^= x >> np.uint64(31)
+    u = (x >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return u < np.float32(keep)
+
+
 def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, weights, params,
-                             return_all_layers=False, dtype=None):
+                             return_all_layers=False, dtype=None, state_dropout=None):
     """Same ops and materialisations as sparse:159-216 with torch CPU fp32 kernels:
     index_select (embedding_lookup) -> matmul -> cat -> index_add_ (unsorted_segment_sum) -> matmul bias
     -> divide -> cat -> explicit GRUCell/BasicRNNCell arithmetic.  Inputs may be NumPy or torch."""
@@ -308,6 +323,7 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
     cell_type = params.get("graph_rnn_cell", "GRU").lower()
     message_targets = torch.cat([a[:, 1] for a in adjs])
     states = [h0]
+    global_step = 0   # state_dropout = (keep, seed): DropoutWrapper on the state after every timestep (sparse:113-114,216)
     for layer_idx, num_timesteps in enumerate(params["layer_timesteps"]):
         w = {k: t(v).to(dtype) for k, v in weights[layer_idx].items()}
         residual_states = [states[i] for i in residual_inputs_of_layer(params, layer_idx)]
@@ -332,6 +348,11 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
                 states[-1] = u * h + (1 - u) * c
             else:
                 states[-1] = act(torch.matmul(torch.cat([x, h], -1), w["rnn_kernel"]) + w["rnn_bias"])
+            if state_dropout is not None and state_dropout[0] < 1.0:
+                keep, seed = state_dropout
+                mask = torch.from_numpy(state_dropout_mask(seed, global_step, V, D, keep))
+                states[-1] = torch.where(mask, states[-1] / float(np.float32(keep)), torch.zeros((), dtype=dtype))
+            global_step += 1
     return states if return_all_layers else states[-1]
 
 

@@ -52,3 +52,17 @@ def test_workload_definitions_and_algorithmic_bytes():
     assert workloads.algorithmic_flops(w) == 4 * (2 * M * D * D + 2 * V * 2 * D * 3 * D)
     w5 = workloads.build("cfg5_rgcn")
     assert w5["V"] == 10000 and w5["M"] == 80000 and "gate_kernel" not in w5["weights"][0]
+
+
+def test_state_dropout_mask_host_restatement_matches_oracle():
+    """ggnn_state_dropout_mask (host arithmetic only, no GPU) == the oracle's NumPy restatement of the counter hash."""
+    import ctypes as C
+    from gated_graph_neural_network_samples_b200 import _lib
+    from oracle import ggnn_oracle as O
+    lib = _lib.load()
+    for V, D, step, keep, seed in [(37, 100, 0, 0.8, 0), (5, 8, 3, 0.5, 12345678901234), (64, 128, 11, 0.9, 2 ** 62 - 1), (0, 4, 0, 0.5, 1)]:
+        m = np.empty((V, D), np.uint8)
+        assert lib.ggnn_state_dropout_mask(V, D, step, C.c_float(keep), C.c_uint64(seed), m.ctypes.data) == 0
+        np.testing.assert_array_equal(m.astype(bool), O.state_dropout_mask(seed, step, V, D, keep))
+        if V * D > 1000:
+            assert abs(m.mean() - keep) < 0.03

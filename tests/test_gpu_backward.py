@@ -20,16 +20,16 @@ CASES = {
 }
 
 
-def _autograd_reference(params, T, w_np, adj, indeg, h0, G):
+def _autograd_reference(params, T, w_np, adj, indeg, h0, G, state_dropout=None):
     import torch
     tw = [{k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in lw.items()} for lw in w_np]
     th0 = torch.tensor(h0, dtype=torch.float64, requires_grad=True)
-    out = O.sparse_propagation_torch(th0, adj, indeg, tw, params, dtype=torch.float64)
+    out = O.sparse_propagation_torch(th0, adj, indeg, tw, params, dtype=torch.float64, state_dropout=state_dropout)
     (out * torch.tensor(G, dtype=torch.float64)).sum().backward()
     return out.detach().numpy(), th0.grad.numpy(), [{k: v.grad.numpy() for k, v in lw.items()} for lw in tw]
 
 
-def _engine_grads(params, T, w_np, set_graph, h0, G, precision):
+def _engine_grads(params, T, w_np, set_graph, h0, G, precision, state_dropout=None):
     import torch
     from gated_graph_neural_network_samples_b200.engine import PropagationEngine
     eng = PropagationEngine(params, T, precision=precision)
@@ -37,6 +37,8 @@ def _engine_grads(params, T, w_np, set_graph, h0, G, precision):
     dev_w = [{ren.get(k, k): torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).cuda() for k, v in lw.items()} for lw in w_np]
     eng.set_weights(dev_w)
     eng.set_save_for_backward(True)
+    if state_dropout is not None:
+        eng.set_state_dropout(*state_dropout)
     set_graph(eng)
     th0 = torch.from_numpy(np.ascontiguousarray(h0, dtype=np.float32)).cuda()
     out = eng.forward(th0)
