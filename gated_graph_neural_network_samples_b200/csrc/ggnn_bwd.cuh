@@ -11,97 +11,196 @@
 //          dW_t += A_t^T . dx'   (A_t = per-type gathered source states, recomputed from the target CSR)
 //          dh   += G_t . W_t^T   (G_t[s] = sum of dx'[target] over the type-t messages LEAVING s: source CSR)
 //
-// Kernels: elementwise cell gradients, CSR gathers, a 64x64-tile FFMA GEMM  C (+)= A . B^T  for the data gradients and a
-// split-row  C += A^T . B  with fp32 atomics for the weight gradients.  Clarity first; the forward is the hot path.
+// Kernels: elementwise cell gradients, one CSR gather for all edge types, a 64x64-tile FFMA GEMM  C (+)= sum_s A_s . B_s^T
+// for the data gradients and a split-row  C_s += A_s^T . B  with fp32 atomics for the weight (+ bias) gradients; the
+// segment lists keep it at ~12 launches per timestep whatever the number of edge types and residual inputs.
 #pragma once
 #include "ggnn_common.cuh"
 
 namespace ggnn {
 namespace bwd {
 
-// ---------------------------------------------------------------- C[M,N] (+)= A[M,K] . B[N,K]^T
+// ---------------------------------------------------------------- C[M,N] (+)= sum_s A_s[M,K] . B_s[N,K]^T
+// A_s = A + s*a_stride (row stride lda), B_s = B + s*b_stride (row stride ldb): one launch covers the per-edge-type sum
+// dh += sum_t G_t . W_t^T  (A = [G_0 | .. | G_{T-1}] side by side, B = the stacked [T][D][D] weights).
+// 128x64 tile, 128 threads x (8x8) outputs, K in slabs of 16 through double-buffered shared memory (register-staged
+// float4 global loads).  Requires K, lda, ldb, ldc, a_stride, b_stride multiples of 4 and 16-byte aligned bases
+// (hidden sizes are multiples of 4 and every buffer is 16-byte aligned -- checked by the caller).
+constexpr int NT_BM = 128, NT_BN = 64, GEMM_BK = 16;
 template <bool ACC>
-__global__ void __launch_bounds__(256) gemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                      float* __restrict__ C, int ldc, int M, int N, int K) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4];
+__global__ void __launch_bounds__(128) gemm_nt_kernel(const float* __restrict__ A, int lda, int a_stride, const float* __restrict__ B, int ldb,
+                                                      int b_stride, int nseg, float* __restrict__ C, int ldc, int M, int N, int K) {
+    __shared__ __align__(16) float As[2][GEMM_BK][NT_BM + 4];
+    __shared__ __align__(16) float Bs[2][GEMM_BK][NT_BN + 4];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int m0 = blockIdx.y * NT_BM, n0 = blockIdx.x * NT_BN;
+    const int kslabs = (K + GEMM_BK - 1) / GEMM_BK, nit = nseg * kslabs;
+    float acc[8][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
-            const int r = idx >> 4, kk = idx & 15;
-            As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(size_t)(m0 + r) * lda + k0 + kk] : 0.f;
-            Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? B[(size_t)(n0 + r) * ldb + k0 + kk] : 0.f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 ra[4], rb[2];
+    auto load_global = [&](int it) {
+        const int sg = it / kslabs, k0 = (it - sg * kslabs) * GEMM_BK;
+        const float* Ag = A + (size_t)sg * a_stride;
+        const float* Bg = B + (size_t)sg * b_stride;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + j * 128, row = f >> 2, kq = (f & 3) * 4;
+            ra[j] = (m0 + row < M && k0 + kq < K) ? *reinterpret_cast<const float4*>(Ag + (size_t)(m0 + row) * lda + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) {
+            const int f = tid + j * 128, row = f >> 2, kq = (f & 3) * 4;
+            rb[j] = (n0 + row < N && k0 + kq < K) ? *reinterpret_cast<const float4*>(Bg + (size_t)(n0 + row) * ldb + k0 + kq) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    auto store_shared = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + j * 128, row = f >> 2, kq = (f & 3) * 4;
+            As[buf][kq + 0][row] = ra[j].x; As[buf][kq + 1][row] = ra[j].y; As[buf][kq + 2][row] = ra[j].z; As[buf][kq + 3][row] = ra[j].w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int f = tid + j * 128, row = f >> 2, kq = (f & 3) * 4;
+            Bs[buf][kq + 0][row] = rb[j].x; Bs[buf][kq + 1][row] = rb[j].y; Bs[buf][kq + 2][row] = rb[j].z; Bs[buf][kq + 3][row] = rb[j].w;
+        }
+    };
+    load_global(0);
+    store_shared(0);
+    __syncthreads();
+    for (int it = 0; it < nit; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < nit) load_global(it + 1);
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (it + 1 < nit) store_shared(buf ^ 1);
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
+        if (m >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
-            if (m < M && n < N) {
-                float* c = C + (size_t)m * ldc + n;
-                *c = ACC ? (*c + acc[i][j]) : acc[i][j];
-            }
+        for (int jq = 0; jq < 2; ++jq) {
+            const int n = n0 + tx * 8 + jq * 4;
+            if (n >= N) continue;
+            float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
+            float4 v = make_float4(acc[i][jq * 4], acc[i][jq * 4 + 1], acc[i][jq * 4 + 2], acc[i][jq * 4 + 3]);
+            if (ACC) { const float4 o = *c; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *c = v;
         }
+    }
 }
 
-// ---------------------------------------------------------------- C[K,N] += A[M,K]^T . B[M,N]   (rows split over blockIdx.z, fp32 atomics)
-__global__ void __launch_bounds__(256) gemm_tn_atomic_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
-                                                             float* __restrict__ C, int ldc, int M, int N, int K, int rows_per_split) {
-    __shared__ float As[16][64 + 4];
-    __shared__ float Bs[16][64 + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int k0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+// ---------------------------------------------------------------- weight gradients: for every segment s
+//   C[s*c_stride + k*ldc + n] += sum_m A_s[m,k] . B[m,n]      (k < K; rows m split over blockIdx.z, fp32 vector atomics)
+// The segments are the pieces of the cell input row ([res.. | x | h-or-rh], each its own [V,D] array) or the per-type
+// gathered source states (columns t*D.. of one [V,T*D] array): one launch per weight tensor instead of one per piece.
+// bias_out (optional): bias_out[n] += sum_m B[m,n] -- the bias gradient rides along with the first segment's blocks.
+// 64x64 output tile, 64 threads x (8x8), rows in slabs of 16.  a_vec = 0 selects scalar loads of A (the [V,T] in-degree table
+// of the edge-bias gradient, whose row length need not be a multiple of 4); B, C, ldb, ldc, N as for gemm_nt.
+constexpr int MAX_SEGS = 16;
+struct SegList {
+    const float* p[MAX_SEGS];
+    int ld[MAX_SEGS];
+};
+__global__ void __launch_bounds__(64) gemm_tn_atomic_kernel(SegList segs, int kblocks, int a_vec, const float* __restrict__ B, int ldb,
+                                                            float* __restrict__ C, int ldc, size_t c_stride, float* __restrict__ bias_out, int M,
+                                                            int N, int K, int rows_per_split) {
+    __shared__ __align__(16) float As[2][GEMM_BK][64 + 4];
+    __shared__ __align__(16) float Bs[2][GEMM_BK][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    const int sg = blockIdx.y / kblocks;
+    const int k0 = (blockIdx.y - sg * kblocks) * 64, n0 = blockIdx.x * 64;
+    const float* __restrict__ A = segs.p[sg];
+    const int lda = segs.ld[sg];
     const int mb = blockIdx.z * rows_per_split, me = min(M, mb + rows_per_split);
-    float acc[4][4];
+    const bool do_bias = bias_out != nullptr && blockIdx.y == 0;
+    float acc[8][8];
+    float bsum = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int m0 = mb; m0 < me; m0 += 16) {
-        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
-            const int mm = idx >> 6, c = idx & 63;
-            As[mm][c] = (m0 + mm < me && k0 + c < K) ? A[(size_t)(m0 + mm) * lda + k0 + c] : 0.f;
-            Bs[mm][c] = (m0 + mm < me && n0 + c < N) ? B[(size_t)(m0 + mm) * ldb + n0 + c] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int mm = 0; mm < 16; ++mm) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[mm][ty * 4 + i]; b[i] = Bs[mm][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 ra[4], rb[4];
+    auto load_global = [&](int m0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = k0 + ty * 4 + i, n = n0 + tx * 4 + j;
-            if (k < K && n < N) atomicAdd(C + (size_t)k * ldc + n, acc[i][j]);
+            const int f = tid + j * 64, mm = f >> 4, c4 = (f & 15) * 4;
+            const bool row_ok = m0 + mm < me;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok) {
+                const float* ap = A + (size_t)(m0 + mm) * lda + k0 + c4;
+                if (a_vec) { if (k0 + c4 < K) a = *reinterpret_cast<const float4*>(ap); }
+                else {
+                    if (k0 + c4 + 0 < K) a.x = ap[0];
+                    if (k0 + c4 + 1 < K) a.y = ap[1];
+                    if (k0 + c4 + 2 < K) a.z = ap[2];
+                    if (k0 + c4 + 3 < K) a.w = ap[3];
+                }
+            }
+            ra[j] = a;
+            rb[j] = (row_ok && n0 + c4 < N) ? *reinterpret_cast<const float4*>(B + (size_t)(m0 + mm) * ldb + n0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    auto store_shared = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + j * 64, mm = f >> 4, c4 = (f & 15) * 4;
+            *reinterpret_cast<float4*>(&As[buf][mm][c4]) = ra[j];
+            *reinterpret_cast<float4*>(&Bs[buf][mm][c4]) = rb[j];
+        }
+    };
+    const int nit = (me - mb + GEMM_BK - 1) / GEMM_BK;
+    if (nit > 0) {
+        load_global(mb);
+        store_shared(0);
+    }
+    __syncthreads();
+    for (int it = 0; it < nit; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < nit) load_global(mb + (it + 1) * GEMM_BK);
+#pragma unroll
+        for (int mm = 0; mm < GEMM_BK; ++mm) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 8 + 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int mm = 0; mm < GEMM_BK; ++mm) bsum += Bs[buf][mm][tid];
+        }
+        if (it + 1 < nit) store_shared(buf ^ 1);
+        __syncthreads();
+    }
+    float* Cs = C + (size_t)sg * c_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = k0 + ty * 8 + i;
+        if (k >= K) continue;
+#pragma unroll
+        for (int jq = 0; jq < 2; ++jq) {
+            const int n = n0 + tx * 8 + jq * 4;
+            if (n >= N) continue;
+            atomicAdd(reinterpret_cast<float4*>(Cs + (size_t)k * ldc + n), make_float4(acc[i][jq * 4], acc[i][jq * 4 + 1], acc[i][jq * 4 + 2], acc[i][jq * 4 + 3]));
+        }
+    }
+    if (do_bias && n0 + tid < N) atomicAdd(bias_out + n0 + tid, bsum);
 }
 
 // ---------------------------------------------------------------- column sums: dst[n] += sum_m src[m, n]  (optionally weighted by w[m*wstride])
@@ -179,24 +278,30 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] += src[i];
 }
 
-// ---------------------------------------------------------------- gathers: out[v] = sum_{slots of row (v*T+t)} in[idx[slot]]   (one warp per node)
-__global__ void __launch_bounds__(256) csr_gather_sum_kernel(const int* __restrict__ row_ptr, const int* __restrict__ idx, const float* __restrict__ in,
-                                                             float* __restrict__ out, int V, int D, int T, int t) {
+// ---------------------------------------------------------------- gathers, all edge types in one launch (one warp per node):
+//   out[v, t*D + :] = sum_{slots of row (v*T+t)} in[idx[slot], :]        out is [V, T*D]
+// blockIdx.y = 0: A_t from the target-keyed CSR over the states; 1: G_t from the source-keyed CSR over dx'.
+struct GatherJob { const int* row_ptr; const int* idx; const float* in; float* out; };
+__global__ void __launch_bounds__(256) csr_gather_all_kernel(GatherJob j0, GatherJob j1, int V, int D, int T) {
+    const GatherJob jb = blockIdx.y == 0 ? j0 : j1;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= V) return;
-    const int beg = row_ptr[(size_t)v * T + t], end = row_ptr[(size_t)v * T + t + 1];
-    for (int c4 = lane; c4 < (D >> 2); c4 += 32) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int m = beg; m < end; ++m) {
-            const float4 x = *reinterpret_cast<const float4*>(in + (size_t)idx[m] * D + (c4 << 2));
-            s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    for (int t = 0; t < T; ++t) {
+        const int beg = jb.row_ptr[(size_t)v * T + t], end = jb.row_ptr[(size_t)v * T + t + 1];
+        float* o = jb.out + ((size_t)v * T + t) * D;
+        for (int c4 = lane; c4 < (D >> 2); c4 += 32) {
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = beg; m < end; ++m) {
+                const float4 x = *reinterpret_cast<const float4*>(jb.in + (size_t)jb.idx[m] * D + (c4 << 2));
+                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            }
+            *reinterpret_cast<float4*>(o + (c4 << 2)) = s;
         }
-        *reinterpret_cast<float4*>(out + (size_t)v * D + (c4 << 2)) = s;
     }
 }
 // dense adjacency [b][T][v][v]: out[g*nv+i] = sum_j A[g,t,i,j] in[g*nv+j]   (transpose: sum_j A[g,t,j,i] in[g*nv+j])
 __global__ void __launch_bounds__(256) dense_gather_sum_kernel(const float* __restrict__ adj, const float* __restrict__ in, float* __restrict__ out,
-                                                               int V, int D, int T, int t, int nv, int transpose) {
+                                                               int ldo, int V, int D, int T, int t, int nv, int transpose) {
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= V) return;
     const int g = v / nv, i = v - g * nv;
@@ -210,7 +315,7 @@ __global__ void __launch_bounds__(256) dense_gather_sum_kernel(const float* __re
                 s.x = fmaf(a, x.x, s.x); s.y = fmaf(a, x.y, s.y); s.z = fmaf(a, x.z, s.z); s.w = fmaf(a, x.w, s.w);
             }
         }
-        *reinterpret_cast<float4*>(out + (size_t)v * D + (c4 << 2)) = s;
+        *reinterpret_cast<float4*>(out + (size_t)v * ldo + (c4 << 2)) = s;
     }
 }
 

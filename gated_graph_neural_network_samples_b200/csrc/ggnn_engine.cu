@@ -288,6 +288,12 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     if (!e->saved_valid) return e->fail(GGNN_ESTATE, "ggnn_backward needs a preceding ggnn_forward with save_for_backward enabled");
     if (!e->has_transpose) return e->fail(GGNN_ESTATE, "enable save_for_backward BEFORE ggnn_set_graph_sparse (the source-keyed CSR is built there)");
     if (!grads || num_layers != e->L || (!d_h_out && e->V > 0)) return e->fail(GGNN_EINVAL, "bad backward arguments");
+    for (int l = 0; l < e->L; ++l) {   // the weight-gradient kernels use 16-byte vector atomics
+        const void* ps[6] = {grads[l].edge_weights, grads[l].edge_biases, grads[l].gate_kernel, grads[l].gate_bias, grads[l].cand_kernel, grads[l].cand_bias};
+        for (const void* q : ps)
+            if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: gradient pointers must be 16-byte aligned", l);
+    }
+    if (((uintptr_t)d_h_out & 15) || ((uintptr_t)d_h0 & 15)) return e->fail(GGNN_EINVAL, "d_h_out / d_h0 must be 16-byte aligned");
     CU_TRY(e, cudaSetDevice(e->device));
     cudaStream_t st = (cudaStream_t)stream;
     e->last_launches = 0;
@@ -301,7 +307,7 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     size_t off = 0;
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
     const size_t o_dstate = take(vd * (L + 1)), o_dha = take(vd), o_dhb = take(vd), o_dpc = take(vd), o_dpg = take(2 * vd);
-    const size_t o_dxc = take((size_t)V * ldx_max), o_dxg = take((size_t)V * ldx_max), o_rh = take(vd), o_dxp = take(vd), o_at = take(vd), o_gt = take(vd);
+    const size_t o_dxc = take((size_t)V * ldx_max), o_dxg = take((size_t)V * ldx_max), o_rh = take(vd), o_dxp = take(vd), o_at = take(vd * T), o_gt = take(vd * T);
     const size_t o_ptrs = off; off += 256;
     CU_TRY(e, e->bwd_buf.reserve(off));
     char* bb = (char*)e->bwd_buf.ptr;
@@ -329,28 +335,35 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     const float* denom = (const float*)(g + e->off_denom);
     const long long n = (long long)vd;
     const int eb = (int)std::min<long long>((n + 255) / 256, 4096);
-    auto gemm_nt = [&](bool acc, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
-        dim3 grid((N + 63) / 64, (M + 63) / 64);
-        if (acc) gemm_nt_kernel<true><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
-        else gemm_nt_kernel<false><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K);
+    auto gemm_nt = [&](bool acc, const float* A, int lda, int a_stride, const float* B, int ldb, int b_stride, int nseg, float* C, int ldc,
+                       int M, int N, int K) {
+        dim3 grid((N + NT_BN - 1) / NT_BN, (M + NT_BM - 1) / NT_BM);
+        if (acc) gemm_nt_kernel<true><<<grid, 128, 0, st>>>(A, lda, a_stride, B, ldb, b_stride, nseg, C, ldc, M, N, K);
+        else gemm_nt_kernel<false><<<grid, 128, 0, st>>>(A, lda, a_stride, B, ldb, b_stride, nseg, C, ldc, M, N, K);
         ++e->last_launches;
     };
-    auto gemm_tn = [&](const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
-        if (!C) return;
-        const int splits = std::max(1, std::min(128, (M + 255) / 256));
-        const int rps = ((M + splits - 1) / splits + 15) / 16 * 16;
-        dim3 grid((N + 63) / 64, (K + 63) / 64, (M + rps - 1) / rps);
-        gemm_tn_atomic_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, rps);
-        ++e->last_launches;
-    };
-    auto colsum = [&](const float* src, int ld, const float* w, int wstride, float* dst, int M, int N) {
-        if (!dst) return;
-        const int rpb = 512;
-        dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
-        colsum_atomic_kernel<<<grid, 256, 0, st>>>(src, ld, w, wstride, dst, M, N, rpb);
+    // C_s[K,N] += A_s^T . B for every segment (C_s = C + s*c_stride), bias[n] += sum_m B[m,n]
+    auto gemm_tn = [&](const SegList& segs, int nseg, bool a_vec, const float* B, int ldb, float* C, int ldc, size_t c_stride, float* bias, int M,
+                       int N, int K) {
+        if (!C && !bias) return;
+        if (C) {
+            const int kblocks = (K + 63) / 64;
+            const int tiles = ((N + 63) / 64) * nseg * kblocks;
+            // ~4 CTAs of 64 threads per SM; every split costs K*N atomics per segment, so keep >= 64 rows per split
+            const int want = std::max(1, (4 * e->num_sms + tiles - 1) / tiles);
+            const int splits = std::max(1, std::min(want, (M + 63) / 64));
+            const int rps = ((M + splits - 1) / splits + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
+            dim3 grid((N + 63) / 64, nseg * kblocks, (M + rps - 1) / rps);
+            gemm_tn_atomic_kernel<<<grid, 64, 0, st>>>(segs, kblocks, a_vec ? 1 : 0, B, ldb, C, ldc, c_stride, bias, M, N, K, rps);
+        } else {   // bias gradient only
+            const int rpb = 512;
+            dim3 grid((N + 255) / 256, (M + rpb - 1) / rpb);
+            colsum_atomic_kernel<<<grid, 256, 0, st>>>(B, ldb, nullptr, 0, bias, M, N, rpb);
+        }
         ++e->last_launches;
     };
     const int nodes_blocks = (V + 7) / 8;
+    const int TD = T * D;
     for (int l = L - 1; l >= 0; --l) {
         const int R = e->nres[l], din = D * (1 + R), ldx = din + D;
         const ggnn_layer_weights& w = e->w[l];
@@ -369,46 +382,62 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
                 dropout_grad_kernel<<<eb, 256, 0, st>>>(dhn, e->saved_drop_seed, e->step_base[l] + s, V, D, e->saved_drop_keep, n);
                 ++e->last_launches;
             }
-            auto seg_src = [&](int i) -> const float* { return i < R ? fstate[e->res[l][i]] : (i == R ? x : nullptr); };
+            // the cell input row [res_0 .. res_{R-1} | x | last], one [V,D] array per piece
+            auto cell_segs = [&](const float* last) {
+                SegList sl;
+                memset(&sl, 0, sizeof sl);
+                for (int i = 0; i < R; ++i) { sl.p[i] = fstate[e->res[l][i]]; sl.ld[i] = D; }
+                sl.p[R] = x; sl.ld[R] = D;
+                sl.p[R + 1] = last; sl.ld[R + 1] = D;
+                return sl;
+            };
             if (e->cell == CELL_GRU) {
                 const float *r = sv_r + so, *u = sv_u + so, *c = sv_c + so;
                 gru_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, h, r, u, c, dpc, dpg, dh_new, rh, n, D, e->act); ++e->last_launches;
-                gemm_nt(false, dpc, D, w.cand_kernel, D, dxc, ldx, V, ldx, D);
-                for (int i = 0; i <= R + 1; ++i)
-                    gemm_tn(i <= R ? seg_src(i) : rh, D, dpc, D, gw.cand_kernel ? gw.cand_kernel + (size_t)i * D * D : nullptr, D, V, D, D);
-                colsum(dpc, D, nullptr, 0, gw.cand_bias, V, D);
+                gemm_nt(false, dpc, D, 0, w.cand_kernel, D, 0, 1, dxc, ldx, V, ldx, D);
+                gemm_tn(cell_segs(rh), R + 2, true, dpc, D, gw.cand_kernel, D, (size_t)D * D, gw.cand_bias, V, D, D);
                 gru_bwd2_kernel<<<eb, 256, 0, st>>>(dxc, ldx, (R + 1) * D, h, r, dpg, dh_new, n, D); ++e->last_launches;
-                gemm_nt(false, dpg, 2 * D, w.gate_kernel, 2 * D, dxg, ldx, V, ldx, 2 * D);
-                for (int i = 0; i <= R + 1; ++i)
-                    gemm_tn(i <= R ? seg_src(i) : h, D, dpg, 2 * D, gw.gate_kernel ? gw.gate_kernel + (size_t)i * D * 2 * D : nullptr, 2 * D, V, 2 * D, D);
-                colsum(dpg, 2 * D, nullptr, 0, gw.gate_bias, V, 2 * D);
+                gemm_nt(false, dpg, 2 * D, 0, w.gate_kernel, 2 * D, 0, 1, dxg, ldx, V, ldx, 2 * D);
+                gemm_tn(cell_segs(h), R + 2, true, dpg, 2 * D, gw.gate_kernel, 2 * D, (size_t)D * 2 * D, gw.gate_bias, V, 2 * D, D);
                 split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, dxg, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 0, 1, 1, n, D);
                 ++e->last_launches;
             } else {
                 const float* hnew = (s == e->steps[l] - 1) ? fstate[l + 1] : sv_h + so + vd;
                 rnn_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, hnew, dpc, n, e->act, e->saved_drop_keep < 1.0f ? e->saved_drop_keep : 1.0f); ++e->last_launches;
-                gemm_nt(false, dpc, D, w.cand_kernel, D, dxc, ldx, V, ldx, D);
-                for (int i = 0; i <= R + 1; ++i)
-                    gemm_tn(i <= R ? seg_src(i) : h, D, dpc, D, gw.cand_kernel ? gw.cand_kernel + (size_t)i * D * D : nullptr, D, V, D, D);
-                colsum(dpc, D, nullptr, 0, gw.cand_bias, V, D);
+                gemm_nt(false, dpc, D, 0, w.cand_kernel, D, 0, 1, dxc, ldx, V, ldx, D);
+                gemm_tn(cell_segs(h), R + 2, true, dpc, D, gw.cand_kernel, D, (size_t)D * D, gw.cand_bias, V, D, D);
                 split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, nullptr, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 1, 0, 0, n, D);
                 ++e->last_launches;
             }
-            // ---- messages
-            for (int t = 0; t < T; ++t) {
-                if (e->use_bias) colsum(dxp, D, indeg + t, T, gw.edge_biases ? gw.edge_biases + (size_t)t * D : nullptr, V, D);
-                if (e->edges_of_type[t] == 0) continue;
-                if (e->gather_mode == GATHER_SPARSE) {
-                    csr_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(row_ptr, csr_src, h, At, V, D, T, t);
-                    csr_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(trow, ttgt, dxp, Gt, V, D, T, t);
-                } else {
-                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, h, At, V, D, T, t, e->dense_v, 0);
-                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, dxp, Gt, V, D, T, t, e->dense_v, 1);
+            // ---- messages: all edge types at once.  At[v, t*D..] = sum of h over the type-t sources of v, Gt[s, t*D..] = sum of dx' over
+            // the type-t targets of s
+            if (e->gather_mode == GATHER_SPARSE) {
+                GatherJob j0{row_ptr, csr_src, h, At}, j1{trow, ttgt, dxp, Gt};
+                csr_gather_all_kernel<<<dim3(nodes_blocks, 2), 256, 0, st>>>(j0, j1, V, D, T);
+                ++e->last_launches;
+            } else {
+                for (int t = 0; t < T; ++t) {
+                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, h, At + (size_t)t * D, TD, V, D, T, t, e->dense_v, 0);
+                    dense_gather_sum_kernel<<<nodes_blocks, 256, 0, st>>>(dadj, dxp, Gt + (size_t)t * D, TD, V, D, T, t, e->dense_v, 1);
+                    e->last_launches += 2;
                 }
-                e->last_launches += 2;
-                gemm_tn(At, D, dxp, D, gw.edge_weights ? gw.edge_weights + (size_t)t * D * D : nullptr, D, V, D, D);
-                gemm_nt(true, Gt, D, w.edge_weights + (size_t)t * D * D, D, dh_new, D, V, D, D);
             }
+            if (e->use_bias && gw.edge_biases) {   // dB[t,:] += sum_v indeg[v,t] dx'[v,:]  =  indeg^T . dx'
+                SegList sl;
+                memset(&sl, 0, sizeof sl);
+                sl.p[0] = indeg; sl.ld[0] = T;
+                gemm_tn(sl, 1, false, dxp, D, gw.edge_biases, D, 0, nullptr, V, D, T);
+            }
+            if (gw.edge_weights) {
+                for (int t0 = 0; t0 < T; t0 += MAX_SEGS) {
+                    SegList sl;
+                    memset(&sl, 0, sizeof sl);
+                    const int nt = std::min(MAX_SEGS, T - t0);
+                    for (int t = 0; t < nt; ++t) { sl.p[t] = At + (size_t)(t0 + t) * D; sl.ld[t] = TD; }
+                    gemm_tn(sl, nt, true, dxp, D, gw.edge_weights + (size_t)t0 * D * D, D, (size_t)D * D, nullptr, V, D, D);
+                }
+            }
+            gemm_nt(true, Gt, TD, D, w.edge_weights, D, D * D, T, dh_new, D, V, D, D);
             dhn = dh_new;
             dh_new = (dh_new == dha) ? dhb : dha;
         }
@@ -677,15 +706,23 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
                     for (int i = 0; i < v && binary; ++i) {
                         const float* row = m + (size_t)i * v;
                         int cnt = 0;
-                        for (int j = 0; j < v; ++j) {
+                        auto visit = [&](int j) {
                             const float a = row[j];
                             if (a != 0.0f) {
-                                if (a != 1.0f) { binary = false; break; }
+                                if (a != 1.0f) { binary = false; return; }
                                 lst.push_back(g * v + j);   // source
                                 lst.push_back(g * v + i);   // target
                                 ++cnt;
                             }
+                        };
+                        int j = 0;
+                        for (; j + 4 <= v && binary; j += 4) {   // the matrix is ~99% zeros: test 16 bytes at a time
+                            uint64_t w0, w1;
+                            memcpy(&w0, row + j, 8); memcpy(&w1, row + j + 2, 8);
+                            if ((w0 | w1) == 0) continue;
+                            visit(j); visit(j + 1); visit(j + 2); visit(j + 3);
                         }
+                        for (; j < v && binary; ++j) visit(j);
                         indeg[((size_t)g * v + i) * T + t] = (float)cnt;
                     }
                 }

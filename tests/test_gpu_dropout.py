@@ -78,7 +78,7 @@ def test_chem_model_trains_with_state_and_weight_dropout(tmp_path):
                          "learning_rate": 0.01, "num_epochs": 1}}
     model = SparseGGNNChemModel(args)
     l0 = model.run_epoch("valid0", model.valid_data, False)[0]
-    assert l0 == model.run_epoch("valid0b", model.valid_data, False)[0]
+    assert abs(l0 - model.run_epoch("valid0b", model.valid_data, False)[0]) < 1e-4 * max(1.0, abs(l0))   # no mask in evaluation
     for ep in range(8):
         model.run_epoch("train%d" % ep, model.train_data, True)
     l1 = model.run_epoch("valid1", model.valid_data, False)[0]
