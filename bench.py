@@ -241,12 +241,11 @@ def main():
     out_host = torch.empty_like(h0_host).pin_memory()
     h0_np, out_np = h0_host.numpy(), out_host.numpy()
 
-    def e2e_step():
+    def e2e_step():   # one public call per batch, host buffers in and out (the shape of sess.run(fetch, feed_dict))
         if dense:
-            eng.set_graph_dense(w["adjacency_matrix"])
+            eng.run_dense_host(w["adjacency_matrix"], h0_np, out_np)
         else:
-            eng.set_graph_sparse(w["adjacency_lists"], w["num_incoming_edges_per_type"])
-        eng.forward_host(h0_np, out_np)
+            eng.run_sparse_host(w["adjacency_lists"], w["num_incoming_edges_per_type"], h0_np, out_np)
 
     for _ in range(max(args.warmup, 3)):
         e2e_step()
@@ -368,7 +367,7 @@ def main():
             "gpu_launches": launches,
             "e2e": {"value": total_units_per_step / (e2e_ms_total / args.steps * 1e-3), "unit": "node-updates/s",
                     "ms_per_step": e2e_ms_total / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "set_graph (host CSR build + H2D) + forward_host (H2D h0, kernel, D2H result) per step, serial"},
+                    "what": "run_{sparse,dense}_host per step: H2D h0 (pinned) | host CSR build + H2D graph, kernel, D2H result, sync; serial"},
             "e2e_pipelined": {"value": total_units_per_step / (pipe_ms_total / args.steps * 1e-3), "unit": "node-updates/s",
                               "ms_per_step": pipe_ms_total / args.steps,
                               "what": "same calls and bytes, two batches in flight (2 engines x 2 streams, forward_host_async); wall clock"},

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(const float* __restrict__ 
 #pragma unroll
         for (int kk = 0; kk < GEMM_BK; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][32 + tx * 4]);   // columns tx*4.. and 32+tx*4..: conflict-free
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128) gemm_nt_kernel(const float* __restrict__ 
         if (m >= M) continue;
 #pragma unroll
         for (int jq = 0; jq < 2; ++jq) {
-            const int n = n0 + tx * 8 + jq * 4;
+            const int n = n0 + tx * 4 + jq * 32;
             if (n >= N) continue;
             float4* c = reinterpret_cast<float4*>(C + (size_t)m * ldc + n);
             float4 v = make_float4(acc[i][jq * 4], acc[i][jq * 4 + 1], acc[i][jq * 4 + 2], acc[i][jq * 4 + 3]);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(64) gemm_tn_atomic_kernel(SegList segs, int kb
 #pragma unroll
         for (int mm = 0; mm < GEMM_BK; ++mm) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 8 + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][mm][32 + tx * 4]);
             const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(64) gemm_tn_atomic_kernel(SegList segs, int kb
         if (k >= K) continue;
 #pragma unroll
         for (int jq = 0; jq < 2; ++jq) {
-            const int n = n0 + tx * 8 + jq * 4;
+            const int n = n0 + tx * 4 + jq * 32;
             if (n >= N) continue;
             atomicAdd(reinterpret_cast<float4*>(Cs + (size_t)k * ldc + n), make_float4(acc[i][jq * 4], acc[i][jq * 4 + 1], acc[i][jq * 4 + 2], acc[i][jq * 4 + 3]));
         }

@@ -1048,6 +1048,45 @@ int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, g
     return GGNN_OK;
 }
 
+}  // extern "C"
+
+// One call per batch, the shape of the reference's sess.run(fetch, feed_dict) (chem_tensorflow.py:235): the h0 upload is
+// enqueued FIRST so the host-side CSR build of set_graph overlaps it.
+template <class SetGraph>
+static int run_host(ggnn_engine* e, int64_t V, const float* h0_host, float* h_out_host, cudaStream_t st, SetGraph set_graph) {
+    if (!e) return GGNN_EINVAL;
+    if (V < 0 || ((!h0_host || !h_out_host) && V > 0)) return e->fail(GGNN_EINVAL, "null host pointer / negative size");
+    CU_TRY(e, cudaSetDevice(e->device));
+    const size_t bytes = (size_t)V * e->D * sizeof(float);
+    const size_t slot = align_up(std::max<size_t>(bytes, 16), 256);
+    CU_TRY(e, e->io_buf.reserve(2 * slot));
+    float* d_in = (float*)e->io_buf.ptr;
+    float* d_out = (float*)((char*)e->io_buf.ptr + slot);
+    if (bytes) CU_TRY(e, cudaMemcpyAsync(d_in, h0_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = set_graph();
+    if (rc) return rc;
+    if ((int64_t)e->V != V) return e->fail(GGNN_EINVAL, "graph has %d nodes, h0 has %lld rows", e->V, (long long)V);
+    rc = ggnn_forward(e, d_in, d_out, (ggnn_stream_t)st);
+    if (rc) return rc;
+    if (bytes) CU_TRY(e, cudaMemcpyAsync(h_out_host, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    CU_TRY(e, cudaStreamSynchronize(st));
+    return GGNN_OK;
+}
+
+extern "C" {
+
+int ggnn_run_sparse_host(ggnn_engine* e, int32_t V, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                         const float* num_incoming_edges_per_type, const float* h0_host, float* h_out_host, ggnn_stream_t stream) {
+    return run_host(e, V, h0_host, h_out_host, (cudaStream_t)stream,
+                    [&]() { return ggnn_set_graph_sparse(e, V, adjacency_lists, num_edges, num_incoming_edges_per_type, stream); });
+}
+
+int ggnn_run_dense_host(ggnn_engine* e, int32_t b, int32_t v, const float* adjacency_matrix, const float* h0_host, float* h_out_host,
+                        ggnn_stream_t stream) {
+    return run_host(e, (int64_t)b * v, h0_host, h_out_host, (cudaStream_t)stream,
+                    [&]() { return ggnn_set_graph_dense(e, b, v, adjacency_matrix, stream); });
+}
+
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
     CU_TRY(e, cudaSetDevice(e->device));

@@ -127,21 +127,55 @@ class PropagationEngine:
         self._weights_keepalive = keep
 
     # ------------------------------------------------------------------ batch
-    def set_graph_sparse(self, adjacency_lists: Sequence[np.ndarray], num_incoming_edges_per_type: np.ndarray):
-        """Reference wire format (sparse:331-348): per type an ``[E_t, 2]`` int32 (source, target) list and the
-        ``[V, T]`` in-degree table.  HOST arrays; index validation, CSR build and upload happen in the library."""
+    def _sparse_args(self, adjacency_lists, num_incoming_edges_per_type):
         if len(adjacency_lists) != self.T:
             raise GgnnError("expected %d adjacency lists, got %d" % (self.T, len(adjacency_lists)))
         adjs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, 2)) for a in adjacency_lists]
         indeg = np.ascontiguousarray(np.asarray(num_incoming_edges_per_type, dtype=np.float32))
         if indeg.ndim != 2 or indeg.shape[1] != self.T:
             raise GgnnError("num_incoming_edges_per_type must be [V, %d]" % self.T)
-        V = indeg.shape[0]
         ptrs = (C.c_void_p * self.T)(*[a.ctypes.data for a in adjs])
         counts = (C.c_int32 * self.T)(*[a.shape[0] for a in adjs])
+        return adjs, indeg, ptrs, counts
+
+    def set_graph_sparse(self, adjacency_lists: Sequence[np.ndarray], num_incoming_edges_per_type: np.ndarray):
+        """Reference wire format (sparse:331-348): per type an ``[E_t, 2]`` int32 (source, target) list and the
+        ``[V, T]`` in-degree table.  HOST arrays; index validation, CSR build and upload happen in the library."""
+        adjs, indeg, ptrs, counts = self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+        V = indeg.shape[0]
         self._check(self.lib.ggnn_set_graph_sparse(self._h, V, ptrs, counts, indeg.ctypes.data, self._stream()))
         self.V = V
         self._graph_keepalive = (adjs, indeg)
+
+    def run_sparse_host(self, adjacency_lists, num_incoming_edges_per_type, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """One call per batch (the shape of ``sess.run(fetch, feed_dict)``, chem_tensorflow.py:235): graph + initial
+        states in, final node states out, HOST arrays, synchronous; the h0 upload overlaps the host-side CSR build."""
+        adjs, indeg, ptrs, counts = self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+        V = indeg.shape[0]
+        h0 = np.ascontiguousarray(h0, dtype=np.float32)
+        if h0.size != V * self.D:
+            raise GgnnError("h0 has %d elements, the graph has %d nodes x %d" % (h0.size, V, self.D))
+        if out is None:
+            out = np.empty_like(h0)
+        self._check(self.lib.ggnn_run_sparse_host(self._h, V, ptrs, counts, indeg.ctypes.data, h0.ctypes.data, out.ctypes.data, self._stream()))
+        self.V = V
+        self._graph_keepalive = (adjs, indeg)
+        return out
+
+    def run_dense_host(self, adjacency_matrix: np.ndarray, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        a = np.ascontiguousarray(np.asarray(adjacency_matrix, dtype=np.float32))
+        if a.ndim != 4 or a.shape[1] != self.T or a.shape[2] != a.shape[3]:
+            raise GgnnError("adjacency_matrix must be [b, %d, v, v]" % self.T)
+        h0 = np.ascontiguousarray(h0, dtype=np.float32)
+        V = a.shape[0] * a.shape[2]
+        if h0.size != V * self.D:
+            raise GgnnError("h0 has %d elements, the graph has %d nodes x %d" % (h0.size, V, self.D))
+        if out is None:
+            out = np.empty_like(h0)
+        self._check(self.lib.ggnn_run_dense_host(self._h, a.shape[0], a.shape[2], a.ctypes.data, h0.ctypes.data, out.ctypes.data, self._stream()))
+        self.V = V
+        self._graph_keepalive = (a,)
+        return out
 
     def set_graph_dense(self, adjacency_matrix: np.ndarray):
         """Dense wire format (dense:214-224): ``[b, T, v, v]`` float32 with ``A[g, t, dest, src]``."""

@@ -110,6 +110,13 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
 
 /* Same with HOST buffers: H2D copy of h0, propagation, D2H copy of the result, stream-synchronised. */
 int ggnn_forward_host(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
+/* One call per batch -- the shape of the reference's sess.run(fetch_list, feed_dict=batch) (chem_tensorflow.py:235): graph
+ * structure + initial states in, final node states out, all HOST buffers, synchronous.  Equivalent to ggnn_set_graph_* followed
+ * by ggnn_forward_host, except that the h0 upload is enqueued first so the host-side CSR build overlaps it. */
+int ggnn_run_sparse_host(ggnn_engine* e, int32_t num_nodes, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                         const float* num_incoming_edges_per_type, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
+int ggnn_run_dense_host(ggnn_engine* e, int32_t num_graphs, int32_t num_vertices, const float* adjacency_matrix,
+                        const float* h0_host, float* h_out_host, ggnn_stream_t stream);
 /* ... without the final synchronisation (pinned host buffers; pair with ggnn_sync_check): lets a caller keep two batches in
  * flight on two engines/streams, the way ChemModel's ThreadedIterator overlaps packing with sess.run (chem_tensorflow.py:225). */
 int ggnn_forward_host_async(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);

@@ -56,6 +56,9 @@ def engine_dense(dparams, T, w, adjm, h0, precision="fp32"):
     eng.set_graph_dense(adjm)
     out = eng.forward(torch.from_numpy(np.ascontiguousarray(h0.reshape(b * v, D), dtype=np.float32)).cuda())
     eng.sync_check()
+    # the one-call host-buffer entry point (ggnn_run_dense_host) must give the same result
+    one_call = eng.run_dense_host(adjm, np.ascontiguousarray(h0.reshape(b * v, D), dtype=np.float32))
+    np.testing.assert_allclose(one_call, out.cpu().numpy(), rtol=1e-5, atol=1e-6)
     return out.cpu().numpy().reshape(b, v, D)
 
 

@@ -163,6 +163,8 @@ def test_host_buffer_call_matches_device_call():
     dev = eng.forward(torch.from_numpy(b["initial_node_representation"]).cuda()).cpu().numpy()
     host = eng.forward_host(b["initial_node_representation"])
     np.testing.assert_array_equal(dev, host)
+    one_call = eng.run_sparse_host(b["adjacency_lists"], b["num_incoming_edges_per_type"], b["initial_node_representation"])
+    np.testing.assert_allclose(one_call, host, rtol=1e-5, atol=1e-6)
     assert eng.last_launch_count == 1 and "LOCAL" in eng.plan
 
 
