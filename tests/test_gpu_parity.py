@@ -164,7 +164,7 @@ def test_host_buffer_call_matches_device_call():
     host = eng.forward_host(b["initial_node_representation"])
     np.testing.assert_array_equal(dev, host)
     one_call = eng.run_sparse_host(b["adjacency_lists"], b["num_incoming_edges_per_type"], b["initial_node_representation"])
-    np.testing.assert_allclose(one_call, host, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(one_call, host, rtol=1e-4, atol=1e-5)
     assert eng.last_launch_count == 1 and "LOCAL" in eng.plan
 
 
@@ -192,7 +192,7 @@ def test_two_batches_in_flight_on_two_engines():
                 engs[k].sync_check()
     for k, b in enumerate(batches):
         ref = engs[k].forward_host(b["initial_node_representation"])
-        np.testing.assert_allclose(outs[k].numpy(), ref, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(outs[k].numpy(), ref, rtol=1e-4, atol=1e-5)
 
 
 def test_error_behaviour_matches_reference():
