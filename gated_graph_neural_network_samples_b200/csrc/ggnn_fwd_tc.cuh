@@ -34,7 +34,7 @@ constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane qu
 #ifndef GGNN_TC_ISSUERS
 #define GGNN_TC_ISSUERS 2
 #endif
-constexpr int NUM_ISSUERS = GGNN_TC_ISSUERS;            // MMA-issuing warps (one per SM sub-partition); issuer i takes K-steps i, i+4, ...
+constexpr int NUM_ISSUERS = GGNN_TC_ISSUERS;            // MMA-issuing warps; issuer i owns the weight slots s with s % NUM_ISSUERS == i (2 and 3 verified, 4 deadlocks)
 constexpr int WARP_MMA = 16;              // first issuer warp
 constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // weight producer (one thread, strictly in order) + TMEM allocator
 constexpr int NTHREADS = (WARP_PROD + 1) * 32;
@@ -247,7 +247,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     __shared__ __align__(8) uint64_t bar_mma_done;
     __shared__ __align__(8) uint64_t bar_g1_done[2];   // one per gather buffer (opA, opX): its MMAs are complete
     __shared__ __align__(8) uint64_t bar_g_ready[2];   // one per gather buffer: A_t written (never more than one phase pending each)
-    __shared__ __align__(8) uint64_t bar_workers;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
 
@@ -283,7 +282,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         mbar_init(&bar_g1_done[1], NUM_ISSUERS);
         mbar_init(&bar_g_ready[0], NUM_WORKERS / 32);
         mbar_init(&bar_g_ready[1], NUM_WORKERS / 32);
-        mbar_init(&bar_workers, 1);   // (unused: workers rendezvous on named barrier 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_PROD) {
