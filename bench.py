@@ -321,6 +321,46 @@ def main():
     train_ms_total = float(sum(a.elapsed_time(b) for a, b in tr))
     eng.set_save_for_backward(False)
 
+    # ---- the fused gated-regression readout that follows the propagation (one task), against the same op written
+    # as the reference's TF op sequence in torch on the GPU (cat, 2 matmuls, sigmoid, mul, index_add / masked sum)
+    readout = None
+    if w["kind"] in ("sparse", "dense"):
+        D = int(P["hidden_size"])
+        rr = np.random.default_rng(3)
+        wg = torch.from_numpy(rr.normal(0, 0.2, (2 * D, 1)).astype(np.float32)).cuda(); bg = torch.zeros(1, device="cuda")
+        wt = torch.from_numpy(rr.normal(0, 0.2, (D, 1)).astype(np.float32)).cuda(); bt = torch.zeros(1, device="cuda")
+        if dense:
+            nb, nv = w["dense_shape"]
+            eng.readout_set_graphs(nb, nodes_per_graph=nv, node_mask=w["node_mask"])
+            mask_t = torch.from_numpy(np.ascontiguousarray(w["node_mask"], dtype=np.float32)).cuda()
+        else:
+            eng.readout_set_graphs(w["num_graphs"], graph_nodes_list=w["graph_nodes_list"])
+            gnl_t = torch.from_numpy(np.asarray(w["graph_nodes_list"])).long().cuda()
+
+        def torch_readout():
+            gated = torch.sigmoid(torch.cat([out, h0], dim=-1) @ wg + bg) * (out @ wt + bt)
+            if dense:
+                return (gated.reshape(nb, nv) * mask_t).sum(dim=1)
+            return torch.zeros(w["num_graphs"], 1, device="cuda").index_add_(0, gnl_t, gated).squeeze(-1)
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            sync_all()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in evs:
+                flush(); a.record(); fn(); b.record()
+            sync_all()
+            return statistics.median([a.elapsed_time(b) for a, b in evs])
+
+        fused_ms = timed(lambda: eng.readout_forward(out, h0, wg, bg, wt, bt))
+        torch_ms = timed(torch_readout)
+        np.testing.assert_allclose(eng.readout_forward(out, h0, wg, bg, wt, bt).cpu().numpy(), torch_readout().cpu().numpy(), rtol=1e-4, atol=1e-5)
+        ro_bytes = 2 * w["V"] * D * 4 + w["V"] * 4 + w["num_graphs"] * 4 + 3 * D * 4   # read h_T and h_0 once, node->graph map, write [G]
+        readout = {"fused_ms": fused_ms, "torch_ops_ms": torch_ms, "algorithmic_bytes": ro_bytes,
+                   "achieved_gbs": ro_bytes / (fused_ms * 1e-3) / 1e9,
+                   "what": "gated_regression (sparse:220-231 / dense:119-129) forward, one task, L2 flushed; fused kernel vs the TF op sequence in torch"}
+
     # ---- max over ranks
     t = torch.tensor([dev_ms_total, e2e_ms_total, hot_ms, pipe_ms_total, train_ms_total], dtype=torch.float64, device="cuda")
     units = torch.tensor([float(w["node_updates"])], dtype=torch.float64, device="cuda")
@@ -374,6 +414,7 @@ def main():
             "train_propagation": {"value": total_units_per_step / (train_ms_total / args.steps * 1e-3), "unit": "node-updates/s",
                                   "ms_per_step": train_ms_total / args.steps,
                                   "what": "forward (states saved) + backward of the propagation (d weights, d h0), device-resident, fp32 backward"},
+            "readout": readout,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(launches / args.steps, 1),
                          "algorithmic_bytes_per_step": alg_bytes, "kernel": "ggnn_fwd_*_kernel", "peak_source": peak_src,

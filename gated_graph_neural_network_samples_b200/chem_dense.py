@@ -11,6 +11,7 @@ import numpy as np
 from . import packing
 from .chem_model import ChemModel
 from .chem_sparse import _propagation_function
+from .readout import gated_readout_function
 from .engine import PropagationEngine
 from .utils import glorot_init
 from .workloads import dense_engine_params
@@ -42,6 +43,7 @@ class DenseGGNNChemModel(ChemModel):
                                     'cand_kernel': var(glorot_init([2 * h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
         self.engine = PropagationEngine(dense_engine_params(self.params), T, device=self.device.index or 0, precision=self.precision)
         self._propagation = _propagation_function()
+        self._readout = gated_readout_function()
 
     def graph_model_variables(self):
         out = [("graph_model/edge_weights", self.weights['edge_weights'])]
@@ -77,6 +79,13 @@ class DenseGGNNChemModel(ChemModel):
         import torch
         D = self.params['hidden_size']
         h0 = self.initial_node_representation_tensor()
+        ag = regression_gate.affine() if hasattr(regression_gate, 'affine') else None
+        at = regression_transform.affine() if hasattr(regression_transform, 'affine') else None
+        if ag is not None and at is not None and last_h.is_cuda:   # fused kernel: masked per-graph sum included
+            b, v = last_h.shape[0], last_h.shape[1]
+            self.engine.readout_set_graphs(b, nodes_per_graph=v, node_mask=self.feed[self.placeholders['node_mask']])
+            self.output = self._readout.apply(self.engine, last_h.reshape(b * v, D), h0.reshape(b * v, D), ag[0], ag[1], at[0], at[1])
+            return self.output
         gate_input = torch.cat([last_h, h0], dim=2).reshape(-1, 2 * D)
         gated = torch.sigmoid(regression_gate(gate_input)) * regression_transform(last_h.reshape(-1, D))
         gated = gated.reshape(last_h.shape[0], last_h.shape[1])

@@ -143,7 +143,7 @@ class ChemModel(object):
         losses, accs = [], []
         for internal_id, task_id in enumerate(self.params['task_ids']):
             gate, trans = self.weights['regression_gate_task%i' % task_id], self.weights['regression_transform_task%i' % task_id]
-            computed = self.gated_regression(final, lambda x: gate(x, keep), lambda x: trans(x, keep))
+            computed = self.gated_regression(final, gate.bind(keep), trans.bind(keep))
             diff = (computed - tv[internal_id, :]) * tm[internal_id, :]                         # :161-164
             num = tm[internal_id, :].sum() + SMALL_NUMBER
             accs.append(diff.abs().sum() / num)                                                 # :165

@@ -13,6 +13,7 @@ import numpy as np
 
 from . import packing
 from .chem_model import ChemModel
+from .readout import gated_readout_function
 from .engine import PropagationEngine, residual_inputs_of_layer
 from .utils import glorot_init
 
@@ -104,6 +105,7 @@ class SparseGGNNChemModel(ChemModel):
             self.gnn_weights.rnn_cells.append(cell)
         self.engine = PropagationEngine(self.params, T, device=self.device.index or 0, precision=self.precision)
         self._propagation = _propagation_function()
+        self._readout = gated_readout_function()
 
     def graph_model_variables(self):
         out = []
@@ -144,10 +146,18 @@ class SparseGGNNChemModel(ChemModel):
         h0 = self.initial_node_representation_tensor()
         return self._propagation.apply(self.engine, layout, h0, *flat)                           # [V, D]
 
-    # ------------------------------------------------------------------ readout (sparse:220-231) -- torch plumbing, SURVEY 8f-1
+    # ------------------------------------------------------------------ readout (sparse:220-231), SURVEY 8f-1
     def gated_regression(self, last_h, regression_gate, regression_transform):
         import torch
         h0 = self.initial_node_representation_tensor()
+        ag = regression_gate.affine() if hasattr(regression_gate, 'affine') else None
+        at = regression_transform.affine() if hasattr(regression_transform, 'affine') else None
+        if ag is not None and at is not None and last_h.is_cuda:
+            # the fused kernel: both dot products, sigmoid, product and the per-graph segment sum in one launch
+            self.engine.readout_set_graphs(int(self.feed[self.placeholders['num_graphs']]),
+                                           graph_nodes_list=self.feed[self.placeholders['graph_nodes_list']])
+            self.output = self._readout.apply(self.engine, last_h, h0, ag[0], ag[1], at[0], at[1])
+            return self.output
         gate_input = torch.cat([last_h, h0], dim=-1)
         gated_outputs = torch.sigmoid(regression_gate(gate_input)) * regression_transform(last_h)   # [v, 1]
         gnl = torch.as_tensor(np.asarray(self.feed[self.placeholders['graph_nodes_list']]), device=self.device, dtype=torch.long)

@@ -18,6 +18,7 @@
 #include "../../include/ggnn_b200.h"
 #include "ggnn_common.cuh"
 #include "ggnn_bwd.cuh"
+#include "ggnn_readout.cuh"
 #include "ggnn_fwd_ffma.cuh"
 #include "ggnn_fwd_tc.cuh"
 
@@ -92,6 +93,10 @@ struct ggnn_engine {
     // device memory
     DevBuf graph_buf;   // packed: row_ptr | csr_src | csr_msg | indeg | denom | tile_start | tile_mask | (dense adj)
     HostPinned graph_stage;
+    // readout (gated_regression): node -> graph map of the current batch
+    DevBuf ro_buf; HostPinned ro_stage; cudaEvent_t ro_stage_done = nullptr;
+    int ro_V = -1, ro_G = 0; bool ro_grouped = false, ro_has_mask = false;
+    size_t ro_off_graph_of = 0, ro_off_start = 0, ro_off_mask = 0;
     cudaEvent_t stage_done = nullptr;   // recorded after the staged H2D copy: the next set_graph waits for it before refilling
     size_t off_row_ptr = 0, off_src = 0, off_msg = 0, off_indeg = 0, off_denom = 0, off_tiles = 0, off_mask = 0, off_adj = 0;
     size_t off_trow = 0, off_ttgt = 0;   // source-keyed CSR (rows source*T+type -> targets), built when save_for_backward is on
@@ -522,6 +527,8 @@ int ggnn_destroy(ggnn_engine* e) {
     e->tc_weights.release(); e->tc_respre.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
     if (e->stage_done) cudaEventDestroy(e->stage_done);
+    if (e->ro_stage_done) cudaEventDestroy(e->ro_stage_done);
+    e->ro_buf.release(); e->ro_stage.release();
     delete e;
     return GGNN_OK;
 }
@@ -1085,6 +1092,99 @@ int ggnn_run_dense_host(ggnn_engine* e, int32_t b, int32_t v, const float* adjac
                         ggnn_stream_t stream) {
     return run_host(e, (int64_t)b * v, h0_host, h_out_host, (cudaStream_t)stream,
                     [&]() { return ggnn_set_graph_dense(e, b, v, adjacency_matrix, stream); });
+}
+
+// ------------------------------------------------------------------------------------------ readout
+int ggnn_readout_set_graphs(ggnn_engine* e, int32_t num_nodes, const int32_t* graph_nodes_list, int32_t num_graphs,
+                            int32_t nodes_per_graph, const float* node_mask, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    e->ro_V = -1;
+    if (num_nodes < 0 || num_graphs < 0) return e->fail(GGNN_EINVAL, "negative size");
+    if (!graph_nodes_list && (nodes_per_graph <= 0 || (int64_t)nodes_per_graph * num_graphs != num_nodes))
+        return e->fail(GGNN_EINVAL, "without a graph_nodes_list the batch must be num_graphs x nodes_per_graph (%d x %d != %d)", num_graphs, nodes_per_graph, num_nodes);
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int V = num_nodes, G = num_graphs;
+    size_t off = 0;
+    e->ro_off_graph_of = off; off = align_up(off + sizeof(int) * (size_t)std::max(V, 1), 16);
+    e->ro_off_start = off;    off = align_up(off + sizeof(int) * (size_t)(G + 1), 16);
+    e->ro_off_mask = off;     off = align_up(off + sizeof(float) * (size_t)std::max(V, 1), 16);
+    if (e->ro_stage_done) CU_TRY(e, cudaEventSynchronize(e->ro_stage_done));
+    CU_TRY(e, e->ro_stage.reserve(off));
+    CU_TRY(e, e->ro_buf.reserve(off));
+    char* base = (char*)e->ro_stage.ptr;
+    int* graph_of = (int*)(base + e->ro_off_graph_of);
+    int* start = (int*)(base + e->ro_off_start);
+    bool grouped = true;
+    for (int v = 0; v < V; ++v) {
+        const int g = graph_nodes_list ? graph_nodes_list[v] : v / nodes_per_graph;
+        if ((unsigned)g >= (unsigned)G) return e->fail(GGNN_ERANGE, "graph_nodes_list[%d] = %d is out of range for %d graphs", v, g, G);
+        if (v > 0 && g < graph_of[v - 1]) grouped = false;
+        graph_of[v] = g;
+    }
+    if (grouped) {   // graph g owns the contiguous node range [start[g], start[g+1])
+        int v = 0;
+        for (int g = 0; g <= G; ++g) {
+            while (v < V && graph_of[v] < g) ++v;
+            start[g] = v;
+        }
+    }
+    if (node_mask) memcpy(base + e->ro_off_mask, node_mask, sizeof(float) * (size_t)V);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(e, cudaMemcpyAsync(e->ro_buf.ptr, base, off, cudaMemcpyHostToDevice, st));
+    if (!e->ro_stage_done) CU_TRY(e, cudaEventCreateWithFlags(&e->ro_stage_done, cudaEventDisableTiming));
+    CU_TRY(e, cudaEventRecord(e->ro_stage_done, st));
+    e->ro_V = V; e->ro_G = G; e->ro_grouped = grouped; e->ro_has_mask = node_mask != nullptr;
+    return GGNN_OK;
+}
+
+static int readout_check(ggnn_engine* e, const void* const* ptrs, int n) {
+    if (e->ro_V < 0) return e->fail(GGNN_ESTATE, "ggnn_readout_set_graphs has not been called for this batch");
+    if (e->D > 32 * readout::MAX_D_PER_LANE) return e->fail(GGNN_EUNSUPPORTED, "readout supports hidden_size <= %d", 32 * readout::MAX_D_PER_LANE);
+    for (int i = 0; i < n; ++i)
+        if (!ptrs[i]) return e->fail(GGNN_EINVAL, "null readout argument %d", i);
+    return GGNN_OK;
+}
+
+int ggnn_readout_forward(ggnn_engine* e, const float* h_last, const float* h0, const float* w_gate, const float* b_gate,
+                         const float* w_trans, const float* b_trans, float* out, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    const void* ps[7] = {h_last, h0, w_gate, b_gate, w_trans, b_trans, out};
+    if (int rc = readout_check(e, ps, e->ro_V > 0 ? 7 : 0)) return rc;
+    CU_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = e->ro_V, G = e->ro_G;
+    if (G == 0) return GGNN_OK;
+    if (!out) return e->fail(GGNN_EINVAL, "null output");
+    char* g = (char*)e->ro_buf.ptr;
+    const float* mask = e->ro_has_mask ? (const float*)(g + e->ro_off_mask) : nullptr;
+    readout::Weights w{w_gate, b_gate, w_trans, b_trans};
+    if (e->ro_grouped || V == 0) {
+        readout::readout_fwd_grouped_kernel<<<(G + 7) / 8, 256, 0, st>>>(h_last, h0, w, (const int*)(g + e->ro_off_start), mask, out, G, e->D);
+    } else {
+        CU_TRY(e, cudaMemsetAsync(out, 0, sizeof(float) * (size_t)G, st));
+        readout::readout_fwd_atomic_kernel<<<(V + 7) / 8, 256, 0, st>>>(h_last, h0, w, (const int*)(g + e->ro_off_graph_of), mask, out, V, e->D);
+    }
+    CU_TRY(e, cudaGetLastError());
+    return GGNN_OK;
+}
+
+int ggnn_readout_backward(ggnn_engine* e, const float* h_last, const float* h0, const float* w_gate, const float* b_gate,
+                          const float* w_trans, const float* b_trans, const float* d_out, float* d_h_last, float* d_w_gate,
+                          float* d_b_gate, float* d_w_trans, float* d_b_trans, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    const void* ps[8] = {h_last, h0, w_gate, b_gate, w_trans, b_trans, d_out, d_h_last};
+    if (int rc = readout_check(e, ps, e->ro_V > 0 ? 8 : 0)) return rc;
+    CU_TRY(e, cudaSetDevice(e->device));
+    const int V = e->ro_V;
+    if (V == 0) return GGNN_OK;
+    char* g = (char*)e->ro_buf.ptr;
+    const float* mask = e->ro_has_mask ? (const float*)(g + e->ro_off_mask) : nullptr;
+    readout::Weights w{w_gate, b_gate, w_trans, b_trans};
+    const int blocks = std::max(1, std::min((V + 7) / 8, 4 * e->num_sms));
+    readout::readout_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h_last, h0, w, (const int*)(g + e->ro_off_graph_of), mask, d_out, d_h_last,
+                                                                         d_w_gate, d_b_gate, d_w_trans, d_b_trans, V, e->D);
+    CU_TRY(e, cudaGetLastError());
+    return GGNN_OK;
 }
 
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream) {

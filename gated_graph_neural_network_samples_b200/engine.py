@@ -237,6 +237,55 @@ class PropagationEngine:
         self._check(self.lib.ggnn_backward(self._h, d_out.data_ptr(), arr, len(grads),
                                            None if d_h0 is None else d_h0.data_ptr(), self._stream()))
 
+    # ------------------------------------------------------------------ readout (gated_regression, sparse:220-231 / dense:119-129)
+    def readout_set_graphs(self, num_graphs: int, graph_nodes_list=None, nodes_per_graph: int = 0, node_mask=None):
+        """The batch's node -> graph map in the reference wire format: sparse ``graph_nodes_list`` [V] int32 (sparse:337), or
+        dense ``nodes_per_graph`` = num_vertices with ``node_mask`` [b, v] (dense:126).  HOST arrays."""
+        gnl = mask = None
+        if graph_nodes_list is not None:
+            gnl = np.ascontiguousarray(np.asarray(graph_nodes_list, dtype=np.int32).reshape(-1))
+            V = gnl.shape[0]
+        else:
+            V = int(num_graphs) * int(nodes_per_graph)
+        if node_mask is not None:
+            mask = np.ascontiguousarray(np.asarray(node_mask, dtype=np.float32).reshape(-1))
+            if mask.shape[0] != V:
+                raise GgnnError("node_mask has %d entries for %d nodes" % (mask.shape[0], V))
+        self._check(self.lib.ggnn_readout_set_graphs(self._h, V, None if gnl is None else gnl.ctypes.data, int(num_graphs), int(nodes_per_graph),
+                                                     None if mask is None else mask.ctypes.data, self._stream()))
+        self._readout_keepalive = (gnl, mask)
+        self._readout_shape = (V, int(num_graphs))
+
+    @staticmethod
+    def _f32(t, n, what):
+        if not (t.is_cuda and t.is_contiguous() and t.element_size() == 4 and t.dtype.is_floating_point and t.numel() == n):
+            raise GgnnError("%s must be a contiguous fp32 CUDA tensor with %d elements" % (what, n))
+        return t.data_ptr()
+
+    def readout_forward(self, h_last, h0, w_gate, b_gate, w_trans, b_trans):
+        import torch
+        V, G = self._readout_shape
+        D = self.D
+        out = torch.empty(G, dtype=torch.float32, device=h_last.device)
+        self._check(self.lib.ggnn_readout_forward(
+            self._h, self._f32(h_last, V * D, "h_last"), self._f32(h0, V * D, "h0"), self._f32(w_gate, 2 * D, "w_gate"), self._f32(b_gate, 1, "b_gate"),
+            self._f32(w_trans, D, "w_trans"), self._f32(b_trans, 1, "b_trans"), out.data_ptr(), self._stream()))
+        return out
+
+    def readout_backward(self, h_last, h0, w_gate, b_gate, w_trans, b_trans, d_out):
+        import torch
+        V, G = self._readout_shape
+        D = self.D
+        d_h = torch.empty(V, D, dtype=torch.float32, device=h_last.device)
+        d_wg = torch.zeros(2 * D, dtype=torch.float32, device=h_last.device)
+        d_wt = torch.zeros(D, dtype=torch.float32, device=h_last.device)
+        d_b = torch.zeros(2, dtype=torch.float32, device=h_last.device)
+        self._check(self.lib.ggnn_readout_backward(
+            self._h, self._f32(h_last, V * D, "h_last"), self._f32(h0, V * D, "h0"), self._f32(w_gate, 2 * D, "w_gate"), self._f32(b_gate, 1, "b_gate"),
+            self._f32(w_trans, D, "w_trans"), self._f32(b_trans, 1, "b_trans"), self._f32(d_out, G, "d_out"), d_h.data_ptr(), d_wg.data_ptr(),
+            d_b.data_ptr(), d_wt.data_ptr(), d_b.data_ptr() + 4, self._stream()))
+        return d_h, d_wg, d_b[0:1], d_wt, d_b[1:2]
+
     # ------------------------------------------------------------------ introspection
     def num_messages(self) -> int:
         m = C.c_int64()

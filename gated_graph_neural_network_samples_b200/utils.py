@@ -37,6 +37,24 @@ class ThreadedIterator:
         self._thread.join()
 
 
+class _BoundMLP:
+    def __init__(self, mlp, keep):
+        self.mlp, self.keep = mlp, keep
+
+    def __call__(self, inputs):
+        return self.mlp(inputs, self.keep)
+
+    def affine(self):
+        """(W, b) of the single affine map when the MLP has no hidden layers (weight dropout applied), else None."""
+        import torch
+        if len(self.mlp.weights) != 1:
+            return None
+        W, b = self.mlp.weights[0], self.mlp.biases[0]
+        if self.keep < 1.0:
+            W = torch.nn.functional.dropout(W, p=1.0 - self.keep, training=True)
+        return W, b
+
+
 class MLP:
     """utils.py:39-71 as torch parameters: ReLU MLP with inverted weight-dropout; the readout uses it with no
     hidden layers (chem_tensorflow.py:153-157), i.e. one affine map."""
@@ -52,6 +70,11 @@ class MLP:
 
     def parameters(self):
         return self.weights + self.biases
+
+    def bind(self, dropout_keep_prob: float = 1.0):
+        """The callable handed to ``gated_regression`` (the reference passes ``self.weights['regression_gate_task%i']`` itself,
+        whose dropout placeholder is fixed at construction, chem_tensorflow.py:153-160)."""
+        return _BoundMLP(self, dropout_keep_prob)
 
     def __call__(self, inputs, dropout_keep_prob: float = 1.0):
         import torch

@@ -121,6 +121,23 @@ int ggnn_run_dense_host(ggnn_engine* e, int32_t num_graphs, int32_t num_vertices
  * flight on two engines/streams, the way ChemModel's ThreadedIterator overlaps packing with sess.run (chem_tensorflow.py:225). */
 int ggnn_forward_host_async(ggnn_engine* e, const float* h0_host, float* h_out_host, ggnn_stream_t stream);
 
+/* ---- Readout: gated_regression (sparse:220-231, dense:119-129), the op right after the propagation, one task:
+ *   out[g] = sum over the nodes v of graph g of  sigmoid([h_T[v] | h_0[v]] . w_gate + b_gate) * (h_T[v] . w_trans + b_trans) * mask[v]
+ * The reference's two readout MLPs have no hidden layers (chem_tensorflow.py:153-157): w_gate is the [2D,1] kernel, w_trans the [D,1]
+ * kernel.  ggnn_readout_set_graphs feeds the batch's node -> graph map in the reference wire format, HOST pointers:
+ *   sparse: graph_nodes_list [V] int32 (sparse:337), node_mask NULL
+ *   dense : graph_nodes_list NULL, nodes_per_graph = num_vertices (graph = row / num_vertices), node_mask [b*v] float32 (dense:126)
+ * Nodes grouped by graph (what the packers produce) are summed in node order, deterministically, like TF's CPU
+ * unsorted_segment_sum; an ungrouped list falls back to float atomics.  All other pointers are DEVICE fp32; `out` is [num_graphs].
+ * ggnn_readout_backward writes d_h_last [V,D] and ACCUMULATES into the weight gradients (caller zeroes; any may be NULL). */
+int ggnn_readout_set_graphs(ggnn_engine* e, int32_t num_nodes, const int32_t* graph_nodes_list, int32_t num_graphs,
+                            int32_t nodes_per_graph, const float* node_mask, ggnn_stream_t stream);
+int ggnn_readout_forward(ggnn_engine* e, const float* h_last, const float* h0, const float* w_gate, const float* b_gate,
+                         const float* w_trans, const float* b_trans, float* out, ggnn_stream_t stream);
+int ggnn_readout_backward(ggnn_engine* e, const float* h_last, const float* h0, const float* w_gate, const float* b_gate,
+                          const float* w_trans, const float* b_trans, const float* d_out, float* d_h_last, float* d_w_gate,
+                          float* d_b_gate, float* d_w_trans, float* d_b_trans, ggnn_stream_t stream);
+
 /* Synchronises `stream` and reports asynchronous kernel-side failures (a bounded barrier wait that expired). */
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream);
 

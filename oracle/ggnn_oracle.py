@@ -381,3 +381,23 @@ def dense_propagation_torch(h0, adjacency_matrix, weights, params, dtype=None):
         c = torch.tanh(torch.matmul(torch.cat([acts, r * h], -1), w["cand_kernel"]) + w["cand_bias"])
         h = u * h + (1 - u) * c
     return h.reshape(b, v, D)
+
+
+def gated_regression_torch(last_h, h0, w_gate, b_gate, w_trans, b_trans, graph_nodes_list=None, num_graphs=None, node_mask=None,
+                           dtype=None):
+    """gated_regression of sparse:220-231 (``graph_nodes_list`` given: unsorted_segment_sum over graphs) or dense:119-129
+    (``last_h`` [b, v, D] with ``node_mask`` [b, v]) for readout MLPs without hidden layers (chem_tensorflow.py:153-157,
+    utils.py:65-71: one affine map each).  torch CPU; float64 + requires_grad inputs give the autograd reference."""
+    import torch
+    dtype = dtype or torch.float32
+    t = lambda a: a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    last_h, h0 = t(last_h).to(dtype), t(h0).to(dtype)
+    w_gate, b_gate, w_trans, b_trans = (t(x).to(dtype) for x in (w_gate, b_gate, w_trans, b_trans))
+    D = last_h.shape[-1]
+    gate_input = torch.cat([last_h, h0], dim=-1).reshape(-1, 2 * D)
+    gated = torch.sigmoid(gate_input @ w_gate.reshape(2 * D, 1) + b_gate) * (last_h.reshape(-1, D) @ w_trans.reshape(D, 1) + b_trans)
+    if graph_nodes_list is not None:
+        ids = t(np.asarray(graph_nodes_list)).long()
+        return torch.zeros(int(num_graphs), 1, dtype=dtype).index_add_(0, ids, gated).squeeze(-1)
+    gated = gated.reshape(last_h.shape[0], last_h.shape[1])
+    return (gated * t(node_mask).to(dtype)).sum(dim=1)
