@@ -96,7 +96,7 @@ struct ggnn_engine {
     // readout (gated_regression): node -> graph map of the current batch
     DevBuf ro_buf; HostPinned ro_stage; cudaEvent_t ro_stage_done = nullptr;
     int ro_V = -1, ro_G = 0; bool ro_grouped = false, ro_has_mask = false;
-    size_t ro_off_graph_of = 0, ro_off_start = 0, ro_off_mask = 0;
+    size_t ro_off_graph_of = 0, ro_off_start = 0, ro_off_mask = 0, ro_off_val = 0;
     cudaEvent_t stage_done = nullptr;   // recorded after the staged H2D copy: the next set_graph waits for it before refilling
     size_t off_row_ptr = 0, off_src = 0, off_msg = 0, off_indeg = 0, off_denom = 0, off_tiles = 0, off_mask = 0, off_adj = 0;
     size_t off_trow = 0, off_ttgt = 0;   // source-keyed CSR (rows source*T+type -> targets), built when save_for_backward is on
@@ -1108,9 +1108,11 @@ int ggnn_readout_set_graphs(ggnn_engine* e, int32_t num_nodes, const int32_t* gr
     e->ro_off_graph_of = off; off = align_up(off + sizeof(int) * (size_t)std::max(V, 1), 16);
     e->ro_off_start = off;    off = align_up(off + sizeof(int) * (size_t)(G + 1), 16);
     e->ro_off_mask = off;     off = align_up(off + sizeof(float) * (size_t)std::max(V, 1), 16);
+    e->ro_off_val = off;      // device-only scratch: per-node gated value
+    const size_t dev_bytes = align_up(off + sizeof(float) * (size_t)std::max(V, 1), 16);
     if (e->ro_stage_done) CU_TRY(e, cudaEventSynchronize(e->ro_stage_done));
     CU_TRY(e, e->ro_stage.reserve(off));
-    CU_TRY(e, e->ro_buf.reserve(off));
+    CU_TRY(e, e->ro_buf.reserve(dev_bytes));
     char* base = (char*)e->ro_stage.ptr;
     int* graph_of = (int*)(base + e->ro_off_graph_of);
     int* start = (int*)(base + e->ro_off_start);
@@ -1140,8 +1142,10 @@ int ggnn_readout_set_graphs(ggnn_engine* e, int32_t num_nodes, const int32_t* gr
 static int readout_check(ggnn_engine* e, const void* const* ptrs, int n) {
     if (e->ro_V < 0) return e->fail(GGNN_ESTATE, "ggnn_readout_set_graphs has not been called for this batch");
     if (e->D > 32 * readout::MAX_D_PER_LANE) return e->fail(GGNN_EUNSUPPORTED, "readout supports hidden_size <= %d", 32 * readout::MAX_D_PER_LANE);
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
         if (!ptrs[i]) return e->fail(GGNN_EINVAL, "null readout argument %d", i);
+        if (i != 3 && i != 5 && ((uintptr_t)ptrs[i] & 15)) return e->fail(GGNN_EINVAL, "readout argument %d must be 16-byte aligned", i);
+    }
     return GGNN_OK;
 }
 
@@ -1158,11 +1162,13 @@ int ggnn_readout_forward(ggnn_engine* e, const float* h_last, const float* h0, c
     char* g = (char*)e->ro_buf.ptr;
     const float* mask = e->ro_has_mask ? (const float*)(g + e->ro_off_mask) : nullptr;
     readout::Weights w{w_gate, b_gate, w_trans, b_trans};
+    float* val = (float*)(g + e->ro_off_val);
+    if (V > 0) readout::readout_node_kernel<<<(V + 7) / 8, 256, 0, st>>>(h_last, h0, w, mask, val, V, e->D);
     if (e->ro_grouped || V == 0) {
-        readout::readout_fwd_grouped_kernel<<<(G + 7) / 8, 256, 0, st>>>(h_last, h0, w, (const int*)(g + e->ro_off_start), mask, out, G, e->D);
+        readout::readout_sum_grouped_kernel<<<(G + 127) / 128, 128, 0, st>>>(val, (const int*)(g + e->ro_off_start), out, G);
     } else {
         CU_TRY(e, cudaMemsetAsync(out, 0, sizeof(float) * (size_t)G, st));
-        readout::readout_fwd_atomic_kernel<<<(V + 7) / 8, 256, 0, st>>>(h_last, h0, w, (const int*)(g + e->ro_off_graph_of), mask, out, V, e->D);
+        readout::readout_sum_atomic_kernel<<<(V + 255) / 256, 256, 0, st>>>(val, (const int*)(g + e->ro_off_graph_of), out, V);
     }
     CU_TRY(e, cudaGetLastError());
     return GGNN_OK;

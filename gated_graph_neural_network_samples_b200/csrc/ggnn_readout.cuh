@@ -2,8 +2,8 @@
 //   val[v]  = sigmoid([h_T[v] | h_0[v]] . w_gate + b_gate) * (h_T[v] . w_trans + b_trans) * mask[v]
 //   out[g]  = sum of val over the nodes of graph g          (tf.unsorted_segment_sum / masked reduce_sum)
 // The reference's readout MLPs have no hidden layers (chem_tensorflow.py:153-157), so each is one affine map to a scalar.
-// Forward: one warp per graph walks the graph's nodes in order (the serial order of TF's CPU segment sum, deterministic);
-// node lists that are not grouped by graph take the one-warp-per-node + atomicAdd variant.  Backward: one warp per node
+// Forward: one warp per node computes val[v] (every node row read once, float4), then one thread per graph adds its nodes in
+// order (the serial order of TF's CPU segment sum, deterministic); node lists not grouped by graph take an atomicAdd stage.  Backward: one warp per node
 // recomputes the two dot products, writes d h_T, accumulates the weight gradients in registers and reduces them per block.
 #pragma once
 #include "ggnn_common.cuh"
@@ -39,34 +39,43 @@ __device__ __forceinline__ void node_dots(const float* __restrict__ hT, const fl
     trans_pre = warp_sum(t) + w.b_trans[0];
 }
 
-// graphs grouped: graph g owns nodes [graph_start[g], graph_start[g+1])
-__global__ void __launch_bounds__(256) readout_fwd_grouped_kernel(const float* __restrict__ h_last, const float* __restrict__ h0, Weights w,
-                                                                  const int* __restrict__ graph_start, const float* __restrict__ mask,
-                                                                  float* __restrict__ out, int G, int D) {
-    const int g = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (g >= G) return;
-    float acc = 0.f;
-    for (int v = graph_start[g]; v < graph_start[g + 1]; ++v) {
-        float gp, tp;
-        node_dots(h_last + (size_t)v * D, h0 + (size_t)v * D, w, D, lane, gp, tp);
-        float val = sigmoidf_acc(gp) * tp;
-        if (mask) val *= mask[v];
-        acc += val;
-    }
-    if (lane == 0) out[g] = acc;
-}
-
-// arbitrary graph_of[v]: out must be zeroed by the caller
-__global__ void __launch_bounds__(256) readout_fwd_atomic_kernel(const float* __restrict__ h_last, const float* __restrict__ h0, Weights w,
-                                                                 const int* __restrict__ graph_of, const float* __restrict__ mask,
-                                                                 float* __restrict__ out, int V, int D) {
+// stage 1: one warp per node -> val[v]   (fully parallel; the node rows are read exactly once, 16 bytes per lane)
+__global__ void __launch_bounds__(256) readout_node_kernel(const float* __restrict__ h_last, const float* __restrict__ h0, Weights w,
+                                                           const float* __restrict__ mask, float* __restrict__ val, int V, int D) {
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= V) return;
-    float gp, tp;
-    node_dots(h_last + (size_t)v * D, h0 + (size_t)v * D, w, D, lane, gp, tp);
-    float val = sigmoidf_acc(gp) * tp;
-    if (mask) val *= mask[v];
-    if (lane == 0) atomicAdd(out + graph_of[v], val);
+    const float4* hT = reinterpret_cast<const float4*>(h_last + (size_t)v * D);
+    const float4* hz = reinterpret_cast<const float4*>(h0 + (size_t)v * D);
+    const float4* wa = reinterpret_cast<const float4*>(w.w_gate);
+    const float4* wb = reinterpret_cast<const float4*>(w.w_gate + D);
+    const float4* wt = reinterpret_cast<const float4*>(w.w_trans);
+    float g = 0.f, t = 0.f;
+    for (int q = lane; q < (D >> 2); q += 32) {
+        const float4 a = hT[q], z = hz[q], ga = wa[q], gb = wb[q], tt = wt[q];
+        g += a.x * ga.x + a.y * ga.y + a.z * ga.z + a.w * ga.w + z.x * gb.x + z.y * gb.y + z.z * gb.z + z.w * gb.w;
+        t += a.x * tt.x + a.y * tt.y + a.z * tt.z + a.w * tt.w;
+    }
+    g = warp_sum(g) + w.b_gate[0];
+    t = warp_sum(t) + w.b_trans[0];
+    float r = sigmoidf_acc(g) * t;
+    if (mask) r *= mask[v];
+    if (lane == 0) val[v] = r;
+}
+// stage 2, graphs grouped: graph g owns nodes [graph_start[g], graph_start[g+1]); summed in node order (deterministic, the order of
+// TF's CPU unsorted_segment_sum)
+__global__ void __launch_bounds__(128) readout_sum_grouped_kernel(const float* __restrict__ val, const int* __restrict__ graph_start,
+                                                                  float* __restrict__ out, int G) {
+    const int g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= G) return;
+    float acc = 0.f;
+    for (int v = graph_start[g]; v < graph_start[g + 1]; ++v) acc += val[v];
+    out[g] = acc;
+}
+// stage 2, arbitrary graph_of[v]: out must be zeroed by the caller
+__global__ void __launch_bounds__(256) readout_sum_atomic_kernel(const float* __restrict__ val, const int* __restrict__ graph_of,
+                                                                 float* __restrict__ out, int V) {
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    if (v < V) atomicAdd(out + graph_of[v], val[v]);
 }
 
 // d_out[G] -> d_h_last[V,D] (written), d_w_gate[2D] / d_b_gate[1] / d_w_trans[D] / d_b_trans[1] (accumulated, atomics per block)
