@@ -15,17 +15,18 @@ class GgnnConfig(C.Structure):
     _fields_ = [("hidden_size", C.c_int32), ("num_edge_types", C.c_int32), ("num_layers", C.c_int32),
                 ("layer_timesteps", c_i32p), ("residual_offsets", c_i32p), ("residual_layers", c_i32p),
                 ("use_edge_bias", C.c_int32), ("use_edge_msg_avg_aggregation", C.c_int32), ("cell", C.c_int32),
-                ("activation", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32)]
+                ("activation", C.c_int32), ("precision", C.c_int32), ("device", C.c_int32),
+                ("use_propagation_attention", C.c_int32)]
 
 
 class GgnnLayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias")]
+                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")]
 
 
 class GgnnLayerGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias")]
+                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")]
 
 
 # name -> (restype, argtypes): every symbol include/ggnn_b200.h declares

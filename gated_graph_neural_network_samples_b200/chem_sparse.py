@@ -94,6 +94,8 @@ class SparseGGNNChemModel(ChemModel):
         self.gnn_weights = GGNNWeights([], [], [], [])
         for layer_idx in range(len(self.params['layer_timesteps'])):
             self.gnn_weights.edge_weights.append(var(glorot_init([T * h_dim, h_dim])))           # sparse:88 (stacked-shape fan)
+            if self.params['use_propagation_attention']:
+                self.gnn_weights.edge_type_attention_weights.append(var(np.ones([T])))           # sparse:94-96
             if self.params['use_edge_bias']:
                 self.gnn_weights.edge_biases.append(var(np.zeros([T, h_dim])))                   # sparse:99
             din = h_dim * (1 + len(residual_inputs_of_layer(self.params, layer_idx)))
@@ -113,6 +115,8 @@ class SparseGGNNChemModel(ChemModel):
             out.append(("graph_model/gnn_layer_%i/gnn_edge_weights_%i" % (l, l), w))
         for l, b in enumerate(self.gnn_weights.edge_biases):
             out.append(("graph_model/gnn_layer_%i/gnn_edge_biases_%i" % (l, l), b))
+        for l, a in enumerate(self.gnn_weights.edge_type_attention_weights):
+            out.append(("graph_model/gnn_layer_%i/edge_type_attention_weights_%i" % (l, l), a))
         for l, cell in enumerate(self.gnn_weights.rnn_cells):
             for k, v in cell.items():
                 out.append(("graph_model/gnn_layer_%i/cell/%s" % (l, k), v))
@@ -140,6 +144,8 @@ class SparseGGNNChemModel(ChemModel):
             flat.append(w)
             if self.params['use_edge_bias']:
                 lay['edge_biases'] = len(flat); flat.append(self.gnn_weights.edge_biases[l])
+            if self.params['use_propagation_attention']:
+                lay['edge_type_attention_weights'] = len(flat); flat.append(self.gnn_weights.edge_type_attention_weights[l])
             for k, v in self.gnn_weights.rnn_cells[l].items():
                 lay[k] = len(flat); flat.append(v)
             layout.append(lay)

@@ -281,7 +281,8 @@ __global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restr
 // ---------------------------------------------------------------- gathers, all edge types in one launch (one warp per node):
 //   out[v, t*D + :] = sum_{slots of row (v*T+t)} in[idx[slot], :]        out is [V, T*D]
 // blockIdx.y = 0: A_t from the target-keyed CSR over the states; 1: G_t from the source-keyed CSR over dx'.
-struct GatherJob { const int* row_ptr; const int* idx; const float* in; float* out; };
+// w (optional): per-slot weight (the attention probability), looked up as w[widx ? widx[slot] : slot]
+struct GatherJob { const int* row_ptr; const int* idx; const float* in; float* out; const float* w; const int* widx; };
 __global__ void __launch_bounds__(256) csr_gather_all_kernel(GatherJob j0, GatherJob j1, int V, int D, int T) {
     const GatherJob jb = blockIdx.y == 0 ? j0 : j1;
     const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -291,12 +292,105 @@ __global__ void __launch_bounds__(256) csr_gather_all_kernel(GatherJob j0, Gathe
         float* o = jb.out + ((size_t)v * T + t) * D;
         for (int c4 = lane; c4 < (D >> 2); c4 += 32) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int m = beg; m < end; ++m) {
-                const float4 x = *reinterpret_cast<const float4*>(jb.in + (size_t)jb.idx[m] * D + (c4 << 2));
-                s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+            if (jb.w) {
+                for (int m = beg; m < end; ++m) {
+                    const float a = jb.w[jb.widx ? jb.widx[m] : m];
+                    const float4 x = *reinterpret_cast<const float4*>(jb.in + (size_t)jb.idx[m] * D + (c4 << 2));
+                    s.x = fmaf(a, x.x, s.x); s.y = fmaf(a, x.y, s.y); s.z = fmaf(a, x.z, s.z); s.w = fmaf(a, x.w, s.w);
+                }
+            } else {
+                for (int m = beg; m < end; ++m) {
+                    const float4 x = *reinterpret_cast<const float4*>(jb.in + (size_t)jb.idx[m] * D + (c4 << 2));
+                    s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+                }
             }
             *reinterpret_cast<float4*>(o + (c4 << 2)) = s;
         }
+    }
+}
+
+// ---------------------------------------------------------------- propagation attention backward (sparse:170-196)
+// incoming[v] = sum_m alpha_m (h[src_m] W_t),  alpha = softmax over the messages into v of  s_m = a_t <h[src_m], h[v]>  (+1e-7 in the
+// denominator).  With P = dx' . W^T ([V, T*D], one GEMM):  d alpha_m = <P[v, t*D..], h[src_m]>,
+//   d s_m = alpha_m (d alpha_m - sum_k alpha_k d alpha_k),   d a_t += d s_m <h[src], h[v]>,
+//   d h[v] += sum_m d s_m a_t h[src_m]   (this kernel, one warp per target),   d h[src] += d s_m a_t h[v]  (source kernel below).
+// dsa[slot] = d s_m a_t is left for the source kernel; scratch[slot] holds d alpha in between.
+__global__ void __launch_bounds__(256) attention_bwd_target_kernel(const int* __restrict__ row_ptr, const int* __restrict__ csr_src,
+                                                                   const float* __restrict__ h, const float* __restrict__ P,
+                                                                   const float* __restrict__ alpha, const float* __restrict__ att_w,
+                                                                   float* __restrict__ dsa, float* __restrict__ dh, float* __restrict__ d_att_w,
+                                                                   int V, int D, int T) {
+    __shared__ float s_daw[16];
+    if (threadIdx.x < 16) s_daw[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v < V) {
+        const float* hv = h + (size_t)v * D;
+        float acc = 0.f;   // sum_k alpha_k d alpha_k
+        for (int t = 0; t < T; ++t) {
+            const float* Pv = P + ((size_t)v * T + t) * D;
+            for (int m = row_ptr[(size_t)v * T + t]; m < row_ptr[(size_t)v * T + t + 1]; ++m) {
+                const float* hs = h + (size_t)csr_src[m] * D;
+                float dal = 0.f;
+                for (int c = lane; c < D; c += 32) dal = fmaf(Pv[c], hs[c], dal);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dal += __shfl_xor_sync(0xffffffffu, dal, o);
+                if (lane == 0) dsa[m] = dal;
+                acc = fmaf(alpha[m], dal, acc);
+            }
+        }
+        __syncwarp();
+        float dhv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dhv[j] = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float aw = att_w[t];
+            float daw = 0.f;
+            for (int m = row_ptr[(size_t)v * T + t]; m < row_ptr[(size_t)v * T + t + 1]; ++m) {
+                const float* hs = h + (size_t)csr_src[m] * D;
+                const float ds = alpha[m] * (dsa[m] - acc);
+                float dot = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = lane + 32 * j;
+                    if (c < D) { const float x = hs[c]; dot = fmaf(x, hv[c], dot); dhv[j] = fmaf(ds * aw, x, dhv[j]); }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                daw = fmaf(ds, dot, daw);
+                __syncwarp();
+                if (lane == 0) dsa[m] = ds * aw;
+            }
+            if (lane == 0 && d_att_w && daw != 0.f) atomicAdd(&s_daw[t], daw);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < D) dh[(size_t)v * D + c] += dhv[j];
+        }
+    }
+    __syncthreads();
+    if (d_att_w && threadIdx.x < T && s_daw[threadIdx.x] != 0.f) atomicAdd(d_att_w + threadIdx.x, s_daw[threadIdx.x]);
+}
+// d h[s] += sum over the messages LEAVING s of dsa[target-CSR slot] * h[target]     (source-keyed CSR, one warp per source)
+__global__ void __launch_bounds__(256) attention_bwd_source_kernel(const int* __restrict__ trow, const int* __restrict__ ttgt,
+                                                                   const int* __restrict__ tslot, const float* __restrict__ h,
+                                                                   const float* __restrict__ dsa, float* __restrict__ dh, int V, int D, int T) {
+    const int s = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (s >= V) return;
+    const int beg = trow[(size_t)s * T], end = trow[(size_t)(s + 1) * T];
+    if (beg == end) return;
+    for (int c4 = lane; c4 < (D >> 2); c4 += 32) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = beg; j < end; ++j) {
+            const float w = dsa[tslot[j]];
+            const float4 x = *reinterpret_cast<const float4*>(h + (size_t)ttgt[j] * D + (c4 << 2));
+            a.x = fmaf(w, x.x, a.x); a.y = fmaf(w, x.y, a.y); a.z = fmaf(w, x.z, a.z); a.w = fmaf(w, x.w, a.w);
+        }
+        float4* o = reinterpret_cast<float4*>(dh + (size_t)s * D + (c4 << 2));
+        float4 cur = *o;
+        cur.x += a.x; cur.y += a.y; cur.z += a.z; cur.w += a.w;
+        *o = cur;
     }
 }
 // dense adjacency [b][T][v][v]: out[g*nv+i] = sum_j A[g,t,i,j] in[g*nv+j]   (transpose: sum_j A[g,t,j,i] in[g*nv+j])

@@ -20,6 +20,7 @@ struct LayerDev {
     const float* gate_b;   // [2D]
     const float* cand_k;   // [(Din+D)][D]   (RNN: the only kernel)
     const float* cand_b;   // [D]
+    const float* att_w;    // [T] edge_type_attention_weights or nullptr (sparse:94-96)
     int steps;
     int nres;
     int res[MAX_RES];      // indices into node_states_per_layer
@@ -56,6 +57,10 @@ struct FwdParams {
     int g_layer, g_step;
     const float* g_in;
     float* g_out;
+    // propagation attention (sparse:170-196): per-message softmax weight, indexed by target-CSR slot; step gs lives at att + gs*att_stride
+    int use_att;
+    float* att;
+    size_t att_stride;
     // DropoutWrapper(state_keep_prob) (sparse:113-114,216 / dense:89): off when drop_keep >= 1
     float drop_keep;
     unsigned long long drop_seed;

@@ -117,6 +117,9 @@ struct ggnn_engine {
     float* last_out = nullptr;
     bool save = false;
     bool saved_valid = false;
+    int use_att = 0;                 // use_propagation_attention (sparse:170-196): fp32 path only
+    DevBuf att_buf;                  // attention probabilities per target-CSR slot ([steps][M] when saving for backward, else [M])
+    size_t off_tslot = 0;            // source-keyed CSR entry -> target-CSR slot (attention backward)
     float drop_keep = 1.0f; unsigned long long drop_seed = 0;          // state dropout for the next forward
     float saved_drop_keep = 1.0f; unsigned long long saved_drop_seed = 0; // ... and what the saved forward used
     int last_launches = 0;
@@ -276,7 +279,7 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
     if (V == 0) tile_start.assign(1, 0);
     e->ntiles = (int)tile_start.size() - 1;
     char buf[256];
-    snprintf(buf, sizeof buf, "fp32-ffma %s tiles=%d rows/tile<=%d warps=8 colsplit=%d nb1=%d max_component=%d smem=%zuB",
+    snprintf(buf, sizeof buf, "fp32-ffma%s %s tiles=%d rows/tile<=%d warps=8 colsplit=%d nb1=%d max_component=%d smem=%zuB", e->use_att ? "+attention" : "",
              local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)", e->ntiles, MT,
              variant_cs(variant), e->nb1, max_span, fwd_smem_bytes(variant, e->nb1, D, e->T));
     e->plan_text = buf;
@@ -294,7 +297,8 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     if (!e->has_transpose) return e->fail(GGNN_ESTATE, "enable save_for_backward BEFORE ggnn_set_graph_sparse (the source-keyed CSR is built there)");
     if (!grads || num_layers != e->L || (!d_h_out && e->V > 0)) return e->fail(GGNN_EINVAL, "bad backward arguments");
     for (int l = 0; l < e->L; ++l) {   // the weight-gradient kernels use 16-byte vector atomics
-        const void* ps[6] = {grads[l].edge_weights, grads[l].edge_biases, grads[l].gate_kernel, grads[l].gate_bias, grads[l].cand_kernel, grads[l].cand_bias};
+        const void* ps[7] = {grads[l].edge_weights, grads[l].edge_biases, grads[l].gate_kernel, grads[l].gate_bias, grads[l].cand_kernel, grads[l].cand_bias,
+                             grads[l].edge_type_attention_weights};
         for (const void* q : ps)
             if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: gradient pointers must be 16-byte aligned", l);
     }
@@ -313,13 +317,14 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     auto take = [&](size_t floats) { size_t o = off; off = align_up(off + floats * sizeof(float), 256); return o; };
     const size_t o_dstate = take(vd * (L + 1)), o_dha = take(vd), o_dhb = take(vd), o_dpc = take(vd), o_dpg = take(2 * vd);
     const size_t o_dxc = take((size_t)V * ldx_max), o_dxg = take((size_t)V * ldx_max), o_rh = take(vd), o_dxp = take(vd), o_at = take(vd * T), o_gt = take(vd * T);
+    const size_t o_pall = take(e->use_att ? vd * T : 0), o_dsa = take(e->use_att ? (size_t)std::max<int64_t>(e->M, 1) : 0);
     const size_t o_ptrs = off; off += 256;
     CU_TRY(e, e->bwd_buf.reserve(off));
     char* bb = (char*)e->bwd_buf.ptr;
     float* dstate = (float*)(bb + o_dstate);
     float *dha = (float*)(bb + o_dha), *dhb = (float*)(bb + o_dhb), *dpc = (float*)(bb + o_dpc), *dpg = (float*)(bb + o_dpg);
     float *dxc = (float*)(bb + o_dxc), *dxg = (float*)(bb + o_dxg), *rh = (float*)(bb + o_rh), *dxp = (float*)(bb + o_dxp);
-    float *At = (float*)(bb + o_at), *Gt = (float*)(bb + o_gt);
+    float *At = (float*)(bb + o_at), *Gt = (float*)(bb + o_gt), *Pall = (float*)(bb + o_pall), *dsa = (float*)(bb + o_dsa);
     float** d_ptrs = (float**)(bb + o_ptrs);
     CU_TRY(e, cudaMemsetAsync(dstate, 0, vd * L * sizeof(float), st));
     CU_TRY(e, cudaMemcpyAsync(dstate + vd * L, d_h_out, vd * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -335,6 +340,7 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     const int* csr_src = (const int*)(g + e->off_src);
     const int* trow = (const int*)(g + e->off_trow);
     const int* ttgt = (const int*)(g + e->off_ttgt);
+    const int* tslot = (const int*)(g + e->off_tslot);
     const float* dadj = (const float*)(g + e->off_adj);
     const float* indeg = (const float*)(g + e->off_indeg);
     const float* denom = (const float*)(g + e->off_denom);
@@ -417,7 +423,16 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
             // ---- messages: all edge types at once.  At[v, t*D..] = sum of h over the type-t sources of v, Gt[s, t*D..] = sum of dx' over
             // the type-t targets of s
             if (e->gather_mode == GATHER_SPARSE) {
-                GatherJob j0{row_ptr, csr_src, h, At}, j1{trow, ttgt, dxp, Gt};
+                const float* alpha = nullptr;
+                if (e->use_att) {   // softmax backward first (it adds to dh_new), then the gathers are weighted by the probabilities
+                    alpha = (const float*)e->att_buf.ptr + (size_t)(e->step_base[l] + s) * (size_t)std::max<int64_t>(e->M, 1);
+                    gemm_nt(false, dxp, D, 0, w.edge_weights, D, 0, 1, Pall, TD, V, TD, D);   // P[v, t*D+k] = <dx'[v], W_t[k, :]>
+                    attention_bwd_target_kernel<<<nodes_blocks, 256, 0, st>>>(row_ptr, csr_src, h, Pall, alpha, w.edge_type_attention_weights, dsa,
+                                                                              dh_new, gw.edge_type_attention_weights, V, D, T);
+                    attention_bwd_source_kernel<<<nodes_blocks, 256, 0, st>>>(trow, ttgt, tslot, h, dsa, dh_new, V, D, T);
+                    e->last_launches += 2;
+                }
+                GatherJob j0{row_ptr, csr_src, h, At, alpha, nullptr}, j1{trow, ttgt, dxp, Gt, alpha, alpha ? tslot : nullptr};
                 csr_gather_all_kernel<<<dim3(nodes_blocks, 2), 256, 0, st>>>(j0, j1, V, D, T);
                 ++e->last_launches;
             } else {
@@ -479,6 +494,9 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     e->D = cfg->hidden_size; e->T = cfg->num_edge_types; e->L = cfg->num_layers;
     e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
     e->cell = cfg->cell; e->act = cfg->activation; e->precision = cfg->precision; e->device = cfg->device;
+    e->use_att = cfg->use_propagation_attention != 0;
+    if (e->use_att && e->T > 16) { delete e; g_create_error = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
+    if (e->use_att) e->precision = GGNN_PREC_FP32;   // the softmax-weighted gather lives in the fp32 kernel only (the plan text says so)
     int total = 0;
     for (int l = 0; l < e->L; ++l) {
         if (cfg->layer_timesteps[l] < 0) { delete e; return bad("negative layer_timesteps entry"); }
@@ -528,7 +546,7 @@ int ggnn_destroy(ggnn_engine* e) {
     e->graph_stage.release();
     if (e->stage_done) cudaEventDestroy(e->stage_done);
     if (e->ro_stage_done) cudaEventDestroy(e->ro_stage_done);
-    e->ro_buf.release(); e->ro_stage.release();
+    e->ro_buf.release(); e->ro_stage.release(); e->att_buf.release();
     delete e;
     return GGNN_OK;
 }
@@ -541,6 +559,7 @@ int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t n
         if (!w.edge_weights || !w.cand_kernel || !w.cand_bias) return e->fail(GGNN_EINVAL, "layer %d: null edge_weights/cand_kernel/cand_bias", l);
         if (e->use_bias && !w.edge_biases) return e->fail(GGNN_EINVAL, "layer %d: use_edge_bias set but edge_biases is null", l);
         if (e->cell == CELL_GRU && (!w.gate_kernel || !w.gate_bias)) return e->fail(GGNN_EINVAL, "layer %d: GRU needs gate_kernel/gate_bias", l);
+        if (e->use_att && !w.edge_type_attention_weights) return e->fail(GGNN_EINVAL, "layer %d: use_propagation_attention set but edge_type_attention_weights is null", l);
         const void* ps[6] = {w.edge_weights, w.edge_biases, w.gate_kernel, w.gate_bias, w.cand_kernel, w.cand_bias};
         for (const void* q : ps)
             if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: weight pointers must be 16-byte aligned", l);
@@ -624,6 +643,8 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     if (e->has_transpose) {
         e->off_trow = off; off = align_up(off + sizeof(int) * ((size_t)V * T + 1), 16);
         e->off_ttgt = off; off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
+        e->off_tslot = off;
+        if (e->use_att) off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
     }
     for (int t = 0; t < T; ++t) e->edges_of_type[t] = num_edges[t];
     if (e->stage_done) CU_TRY(e, cudaEventSynchronize(e->stage_done));   // previous upload may still be reading the stage
@@ -662,8 +683,19 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
         trow[0] = 0;
         for (size_t k = 1; k <= (size_t)V * T; ++k) trow[k] = trow[k - 1] + cnt[k];
         for (size_t k = 0; k < (size_t)V * T; ++k) cnt[k] = trow[k];
+        std::vector<int> slot_of_msg;
+        int* tslot = e->use_att ? (int*)(base + e->off_tslot) : nullptr;
+        if (tslot) {
+            slot_of_msg.resize((size_t)std::max<int64_t>(M, 1));
+            for (int64_t k = 0; k < M; ++k) slot_of_msg[csr_msg[k]] = (int)k;
+        }
+        int m = 0;
         for (int t = 0; t < T; ++t)
-            for (int i = 0; i < num_edges[t]; ++i) ttgt[cnt[(size_t)adj[t][2 * i] * T + t]++] = adj[t][2 * i + 1];
+            for (int i = 0; i < num_edges[t]; ++i, ++m) {
+                const int j = cnt[(size_t)adj[t][2 * i] * T + t]++;
+                ttgt[j] = adj[t][2 * i + 1];
+                if (tslot) tslot[j] = slot_of_msg[m];
+            }
     }
     for (int v = 0; v < V; ++v) {
         float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
@@ -693,6 +725,7 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     if (!e) return GGNN_EINVAL;
     e->graph_set = false; e->saved_valid = false;
     if (b < 0 || v <= 0 || (!adjm && b > 0)) return e->fail(GGNN_EINVAL, "null/negative argument");
+    if (e->use_att) return e->fail(GGNN_EUNSUPPORTED, "propagation attention exists only in the sparse model (sparse:170-196)");
     CU_TRY(e, cudaSetDevice(e->device));
     const int T = e->T;
     if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
@@ -818,6 +851,7 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
     p.use_bias = e->use_bias; p.use_avg = e->use_avg; p.cell = e->cell; p.act = e->act;
     p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
     p.drop_keep = e->drop_keep; p.drop_seed = e->drop_seed;
+    p.use_att = e->use_att; p.att = (float*)e->att_buf.ptr; p.att_stride = e->save ? (size_t)std::max<int64_t>(e->M, 1) : 0;
     char* g = (char*)e->graph_buf.ptr;
     p.tile_start = (const int*)(g + e->off_tiles);
     p.tile_mask = (const unsigned*)(g + e->off_mask);
@@ -838,6 +872,7 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
         ld.edge_w = e->w[l].edge_weights; ld.edge_b = e->w[l].edge_biases;
         ld.gate_k = e->w[l].gate_kernel; ld.gate_b = e->w[l].gate_bias;
         ld.cand_k = e->w[l].cand_kernel; ld.cand_b = e->w[l].cand_bias;
+        ld.att_w = e->use_att ? e->w[l].edge_type_attention_weights : nullptr;
         ld.steps = e->steps[l]; ld.nres = e->nres[l];
         for (int i = 0; i < MAX_RES; ++i) ld.res[i] = e->res[l][i];
         p.step_base[l] = e->step_base[l];
@@ -995,6 +1030,10 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
         return GGNN_OK;
     }
     if (e->precision != GGNN_PREC_FP32) return forward_tc(e, h0, h_out, st);
+    if (e->use_att) {
+        if (e->gather_mode != GATHER_SPARSE) return e->fail(GGNN_EUNSUPPORTED, "propagation attention needs the sparse graph format");
+        CU_TRY(e, e->att_buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(e->M, 1) * (size_t)(e->save ? std::max(e->total_steps, 1) : 1)));
+    }
     FwdParams p;
     fill_params(e, p, h0, h_out);
     FwdKernel k = pick_fwd_kernel(e->variant, e->nb1, e->local);

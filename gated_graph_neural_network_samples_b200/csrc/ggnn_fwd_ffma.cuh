@@ -188,6 +188,51 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
             // ------------------------------------------------ message phase: agg = sum_t A_t . W_t
             float acc1[NB1][8];
             zero_acc<NB1>(acc1);
+            float* att = nullptr;
+            if (p.use_att) {
+                // ---- propagation attention (sparse:170-196): a softmax over ALL incoming messages of a node (every edge type), score =
+                // <h[source], h[target]> * edge_type_attention_weight[type].  One warp per target row; the rows v*T .. v*T+T-1 of the
+                // target-keyed CSR are contiguous, so a node's messages are one slot range.  att[slot] ends up holding the probability.
+                att = p.att + (size_t)(p.step_base[l] + s) * p.att_stride;
+                for (int r = warp; r < rows; r += NWARP) {
+                    const int v = row0 + r;
+                    const float* hv = LOCAL ? (sH + (size_t)r * D) : (p.g_in + (size_t)v * D);
+                    const int mbeg = p.row_ptr[(size_t)v * T], mend = p.row_ptr[(size_t)(v + 1) * T];
+                    float mx = -INFINITY;
+                    for (int t = 0; t < T; ++t) {
+                        const float aw = ly.att_w[t];
+                        const int beg = p.row_ptr[(size_t)v * T + t], end = p.row_ptr[(size_t)v * T + t + 1];
+                        for (int m = beg; m < end; ++m) {
+                            const int src = p.csr_src[m];
+                            const float* hp = LOCAL ? (sH + (size_t)(src - row0) * D) : (p.g_in + (size_t)src * D);
+                            float dot = 0.f;
+                            for (int c4 = lane; c4 < D4; c4 += 32) {
+                                const float4 a = *reinterpret_cast<const float4*>(hp + (c4 << 2));
+                                const float4 b = *reinterpret_cast<const float4*>(hv + (c4 << 2));
+                                dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                            const float sc = dot * aw;
+                            if (lane == 0) att[m] = sc;
+                            mx = fmaxf(mx, sc);
+                        }
+                    }
+                    __syncwarp();
+                    float sum = 0.f;
+                    for (int m = mbeg + lane; m < mend; m += 32) {
+                        const float ex = expf(att[m] - mx);
+                        att[m] = ex;
+                        sum += ex;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    const float den = sum + 1e-7f;   // SMALL_NUMBER, sparse:194
+                    for (int m = mbeg + lane; m < mend; m += 32) att[m] = att[m] / den;
+                    __syncwarp();
+                }
+                // the same warp gathers the same rows below, so __syncwarp is all the ordering the att[] values need
+            }
             for (int t = 0; t < T; ++t) {
                 if (!((tmask >> t) & 1u)) continue;
                 // A_t rows: sum of the source states of the row's incoming type-t messages (CSR order = message order)
@@ -197,6 +242,16 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
                         const int beg = p.row_ptr[(size_t)v * T + t], end = p.row_ptr[(size_t)v * T + t + 1];
                         for (int c4 = lane; c4 < D4; c4 += 32) {
                             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (att) {   // messages weighted by their attention probability (sparse:196)
+                                for (int m = beg; m < end; ++m) {
+                                    const int src = p.csr_src[m];
+                                    const float a = att[m];
+                                    const float* hp = LOCAL ? (sH + (size_t)(src - row0) * D) : (p.g_in + (size_t)src * D);
+                                    const float4 hv = *reinterpret_cast<const float4*>(hp + (c4 << 2));
+                                    sum.x = fmaf(a, hv.x, sum.x); sum.y = fmaf(a, hv.y, sum.y);
+                                    sum.z = fmaf(a, hv.z, sum.z); sum.w = fmaf(a, hv.w, sum.w);
+                                }
+                            } else
                             for (int m = beg; m < end; ++m) {
                                 const int src = p.csr_src[m];
                                 const float* hp = LOCAL ? (sH + (size_t)(src - row0) * D) : (p.g_in + (size_t)src * D);

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
-WEIGHT_FIELDS = ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias")
+WEIGHT_FIELDS = ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")
 
 
 def residual_inputs_of_layer(params: dict, layer_idx: int) -> List[int]:
@@ -33,6 +33,8 @@ def weight_shapes(params: dict, num_edge_types: int, layer_idx: int) -> Dict[str
     shapes = {"edge_weights": (T, D, D)}
     if params.get("use_edge_bias", False):
         shapes["edge_biases"] = (T, D)
+    if params.get("use_propagation_attention", False):
+        shapes["edge_type_attention_weights"] = (T,)                                            # sparse:94-96
     if params.get("graph_rnn_cell", "GRU").lower() == "gru":
         shapes.update(gate_kernel=(din + D, 2 * D), gate_bias=(2 * D,), cand_kernel=(din + D, D), cand_bias=(D,))
     else:
@@ -61,8 +63,6 @@ class PropagationEngine:
             # CudnnCompatibleGRUCell (sparse:105-108) is a different cell (reset gate applied after the
             # recurrent matmul); it is in no BASELINE config and not provided by tensorflow==1.3.0.
             raise Exception("Unknown RNN cell type '%s'." % cell)                            # sparse:112
-        if params.get("use_propagation_attention", False):
-            raise Exception("use_propagation_attention is not implemented by the B200 engine yet")
         offs, flat = [0], []
         for l in range(self.L):
             flat += residual_inputs_of_layer(params, l)
@@ -74,7 +74,7 @@ class PropagationEngine:
                               int(bool(params.get("use_edge_bias", False))),
                               int(bool(params.get("use_edge_msg_avg_aggregation", False))),
                               0 if cell == "gru" else 1, 0 if act == "tanh" else 1,
-                              PRECISIONS[precision], int(device))
+                              PRECISIONS[precision], int(device), int(bool(params.get("use_propagation_attention", False))))
         rc = self.lib.ggnn_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()

@@ -53,6 +53,7 @@ typedef struct ggnn_config {
     int32_t activation;                   /* GGNN_ACT_*                                                */
     int32_t precision;                    /* GGNN_PREC_*                                               */
     int32_t device;                       /* CUDA device ordinal                                       */
+    int32_t use_propagation_attention;    /* sparse:46,94-96,147-149,170-196 (fp32 path; <= 16 edge types) */
 } ggnn_config;
 
 /* Device pointers to one layer's trainables, fp32 row-major, shapes as created at sparse:86-115:
@@ -70,6 +71,7 @@ typedef struct ggnn_layer_weights {
     const float* gate_bias;
     const float* cand_kernel;
     const float* cand_bias;
+    const float* edge_type_attention_weights; /* [T] (sparse:94-96) or NULL when !use_propagation_attention */
 } ggnn_layer_weights;
 
 /* Same layout, device pointers the backward pass ACCUMULATES into (caller zeroes them). */
@@ -80,6 +82,7 @@ typedef struct ggnn_layer_grads {
     float* gate_bias;
     float* cand_kernel;
     float* cand_bias;
+    float* edge_type_attention_weights;
 } ggnn_layer_grads;
 
 /* prepare_specific_graph_model (sparse:63-115 / dense:68-91): fix the model shape. */

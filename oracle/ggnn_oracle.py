@@ -52,7 +52,7 @@ def residual_inputs_of_layer(params, layer_idx):
     return [] if lst is None else list(lst)
 
 
-def init_sparse_weights(params, num_edge_types, rng, edge_bias_scale=0.1):
+def init_sparse_weights(params, num_edge_types, rng, edge_bias_scale=0.1, attention_scale=0.0):
     """Per-layer weights with the shapes of chem_tensorflow_sparse.py:86-115.
 
     edge_weights:  glorot on the *stacked* [T*D, D] shape (sparse:88) reshaped to [T, D, D] (sparse:90)
@@ -69,6 +69,8 @@ def init_sparse_weights(params, num_edge_types, rng, edge_bias_scale=0.1):
         w = {"edge_weights": glorot_init([T * D, D], rng).reshape(T, D, D)}
         if params.get("use_edge_bias", False):
             w["edge_biases"] = rng.uniform(-edge_bias_scale, edge_bias_scale, size=(T, D)).astype(np.float32)
+        if params.get("use_propagation_attention", False):   # sparse:94-96: ones; attention_scale > 0 perturbs them for the tests
+            w["edge_type_attention_weights"] = (np.ones(T) + attention_scale * rng.uniform(-1, 1, T)).astype(np.float32)
         cell = params.get("graph_rnn_cell", "GRU").lower()
         if cell == "gru":
             w["gate_kernel"] = glorot_init([din + D, 2 * D], rng)
@@ -171,12 +173,25 @@ def sparse_propagation_loops(h0, adjacency_lists, num_incoming_edges_per_type, w
         for _step in range(num_timesteps):                                         # sparse:153
             h = node_states_per_layer[-1]
             incoming = np.zeros((V, D), dtype=dtype)
+            attention = None
+            if params.get("use_propagation_attention", False):                     # sparse:170-196, message by message
+                scores = {}
+                for e, adj in enumerate(adjacency_lists):
+                    for i, (src, tgt) in enumerate(np.asarray(adj).reshape(-1, 2)):
+                        scores[(e, i)] = (int(tgt), float(h[src] @ h[tgt]) * float(w["edge_type_attention_weights"][e]))
+                mx, ssum = {}, {}
+                for tgt, sc in scores.values():
+                    mx[tgt] = max(mx.get(tgt, -np.inf), sc)
+                for tgt, sc in scores.values():
+                    ssum[tgt] = ssum.get(tgt, 0.0) + np.exp(sc - mx[tgt])
+                attention = {k: np.exp(sc - mx[tgt]) / (ssum[tgt] + SMALL_NUMBER) for k, (tgt, sc) in scores.items()}
             for e, adj in enumerate(adjacency_lists):                              # sparse:159
                 adj = np.asarray(adj).reshape(-1, 2)
-                for (src, tgt) in adj:                                             # gather :161, matmul :163
+                for i, (src, tgt) in enumerate(adj):                               # gather :161, matmul :163
                     if not (0 <= src < V and 0 <= tgt < V):
                         raise IndexError("edge (%d,%d) out of range for V=%d" % (src, tgt, V))
-                    incoming[tgt] += h[src] @ w["edge_weights"][e]                 # segment_sum :198
+                    msg = h[src] @ w["edge_weights"][e]
+                    incoming[tgt] += msg if attention is None else msg * attention[(e, i)]   # segment_sum :198
             if params.get("use_edge_bias", False):                                 # sparse:202-204
                 incoming = incoming + indeg @ w["edge_biases"].reshape(-1, D)
             if params.get("use_edge_msg_avg_aggregation", False):                  # sparse:206-209
@@ -215,6 +230,14 @@ def sparse_propagation_np(h0, adjacency_lists, num_incoming_edges_per_type, weig
             h = states[-1]
             msgs = [h[a[:, 0]] @ w["edge_weights"][e] for e, a in enumerate(adjs)]
             messages = np.concatenate(msgs, axis=0) if msgs else np.zeros((0, D), dtype)
+            if params.get("use_propagation_attention", False) and messages.shape[0]:             # sparse:170-196
+                message_types = np.concatenate([np.full(a.shape[0], e, np.int64) for e, a in enumerate(adjs)])
+                src_states = np.concatenate([h[a[:, 0]] for a in adjs], axis=0)
+                scores = np.einsum("mi,mi->m", src_states, h[message_targets]) * w["edge_type_attention_weights"][message_types]
+                mx = np.full(V, -np.inf, dtype); np.maximum.at(mx, message_targets, scores)      # unsorted_segment_max
+                exped = np.exp(scores - mx[message_targets])
+                ssum = np.zeros(V, dtype); np.add.at(ssum, message_targets, exped)
+                messages = messages * (exped / (ssum[message_targets] + dtype(SMALL_NUMBER)))[:, None]
             incoming = np.zeros((V, D), dtype=dtype)
             np.add.at(incoming, message_targets, messages)
             if params.get("use_edge_bias", False):
@@ -335,6 +358,14 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
                 edge_source_states = torch.index_select(h, 0, a[:, 0])
                 msgs.append(torch.matmul(edge_source_states, w["edge_weights"][e]))
             messages = torch.cat(msgs, dim=0)
+            if params.get("use_propagation_attention", False) and messages.shape[0]:             # sparse:170-196
+                message_types = torch.cat([torch.full((a.shape[0],), e, dtype=torch.long) for e, a in enumerate(adjs)])
+                src_states = torch.cat([torch.index_select(h, 0, a[:, 0]) for a in adjs], dim=0)
+                scores = (src_states * torch.index_select(h, 0, message_targets)).sum(-1) * w["edge_type_attention_weights"][message_types]
+                mx = torch.full((V,), -float("inf"), dtype=dtype).scatter_reduce(0, message_targets, scores.detach(), reduce="amax")
+                exped = torch.exp(scores - mx[message_targets])
+                ssum = torch.zeros(V, dtype=dtype).index_add_(0, message_targets, exped)
+                messages = messages * (exped / (ssum[message_targets] + SMALL_NUMBER)).unsqueeze(-1)
             incoming = torch.zeros(V, D, dtype=dtype).index_add_(0, message_targets, messages)
             if params.get("use_edge_bias", False):
                 incoming = incoming + torch.matmul(indeg, w["edge_biases"].reshape(-1, D))

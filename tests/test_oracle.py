@@ -7,6 +7,7 @@ import pytest
 
 from gated_graph_neural_network_samples_b200 import packing, synthetic
 from oracle import ggnn_oracle as O
+from tests import _util as U
 
 PARAM_SETS = {
     "default_true": {"hidden_size": 10, "layer_timesteps": [2, 2, 1, 2, 1], "residual_connections": {"2": [0], "4": [0, 2]},
@@ -166,3 +167,25 @@ def test_golden_dense_regression(golden_dir):
     p = json.loads(str(z["params_json"]))
     w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
     np.testing.assert_allclose(O.dense_propagation_loops(z["h0"], z["adj"], w, p), z["final"], rtol=1e-12, atol=1e-14)
+
+
+def test_propagation_attention_three_statements_agree():
+    """sparse:170-196 restated message by message (loops), vectorised (NumPy) and at TF op granularity (torch) -- one result;
+    with all sources of a node equal the softmax is uniform and attention reduces to dividing by the in-degree."""
+    import torch
+    p = {"hidden_size": 12, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]}, "use_edge_bias": True,
+         "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh", "use_propagation_attention": True}
+    _, b = U.molecule_batch(6, 12, T=4, seed=3)
+    w = O.init_sparse_weights(p, 4, np.random.default_rng(1), attention_scale=0.5)
+    args = (b["initial_node_representation"] * 3, b["adjacency_lists"], b["num_incoming_edges_per_type"], w, p)
+    a = O.sparse_propagation_loops(*args)
+    np.testing.assert_allclose(O.sparse_propagation_np(*args, dtype=np.float64), a, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(O.sparse_propagation_torch(*args, dtype=torch.float64).numpy(), a, rtol=1e-12, atol=1e-13)
+    # uniform case: identical node states -> every message into a node has the same score
+    p1 = dict(p, layer_timesteps=[1], residual_connections={}, use_edge_bias=False, use_edge_msg_avg_aggregation=False)
+    w1 = O.init_sparse_weights(p1, 4, np.random.default_rng(2))
+    h_same = np.tile(np.random.default_rng(3).normal(size=(1, 12)), (b["initial_node_representation"].shape[0], 1))
+    att = O.sparse_propagation_np(h_same, args[1], args[2], w1, p1, dtype=np.float64)
+    mean = O.sparse_propagation_np(h_same, args[1], args[2], w1, dict(p1, use_propagation_attention=False, use_edge_msg_avg_aggregation=True),
+                                   dtype=np.float64)
+    np.testing.assert_allclose(att, mean, rtol=1e-6, atol=1e-7)
