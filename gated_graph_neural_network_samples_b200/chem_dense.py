@@ -46,10 +46,14 @@ class DenseGGNNChemModel(ChemModel):
         self._readout = gated_readout_function()
 
     def graph_model_variables(self):
-        out = [("graph_model/edge_weights", self.weights['edge_weights'])]
+        # TF-1.3 names of the dense graph's variables: the two unnamed tf.Variables of dense:84-86 become graph_model/Variable[_1], the
+        # GRUCell's variables are created by its first call under graph_model/gru_scope (dense:99).  Restated from knowledge of that release.
+        out = [("graph_model/Variable:0", self.weights['edge_weights'])]                         # [T, D, D]
         if 'edge_biases' in self.weights:
-            out.append(("graph_model/edge_biases", self.weights['edge_biases']))
-        out += [("graph_model/gru_scope/%s" % k, v) for k, v in self.weights['node_gru'].items()]
+            out.append(("graph_model/Variable_1:0", self.weights['edge_biases']))              # [T, 1, D]
+        tf_cell = {'gate_kernel': 'gru_cell/gates/kernel', 'gate_bias': 'gru_cell/gates/bias',
+                   'cand_kernel': 'gru_cell/candidate/kernel', 'cand_bias': 'gru_cell/candidate/bias'}
+        out += [("graph_model/gru_scope/%s:0" % tf_cell[k], v) for k, v in self.weights['node_gru'].items()]
         return out
 
     def compute_final_node_representations(self):     # dense:93-117

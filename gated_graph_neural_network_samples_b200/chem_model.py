@@ -155,9 +155,14 @@ class ChemModel(object):
     # ------------------------------------------------------------------ training step (chem_tensorflow.py:172-193)
     def trainable_variables(self):
         named = list(self.graph_model_variables())
-        for k, mlp in self.weights.items():
-            if isinstance(mlp, MLP):
-                named += [("%s/W%d" % (k, i), w) for i, w in enumerate(mlp.weights)] + [("%s/b%d" % (k, i), b) for i, b in enumerate(mlp.biases)]
+        for task_id in self.params['task_ids']:
+            # tf.Variable names of utils.py:52-55 under the scopes of chem_tensorflow.py:152-157
+            for key, scope in (('regression_gate_task%i' % task_id, 'out_layer_task%i/regression_gate' % task_id),
+                               ('regression_transform_task%i' % task_id, 'out_layer_task%i/regression' % task_id)):
+                mlp = self.weights.get(key)
+                if isinstance(mlp, MLP):
+                    named += [("%s/MLP_W_layer%i:0" % (scope, i), w) for i, w in enumerate(mlp.weights)]
+                    named += [("%s/MLP_b_layer%i:0" % (scope, i), b) for i, b in enumerate(mlp.biases)]
         return named
 
     def graph_model_variables(self):
@@ -267,7 +272,21 @@ class ChemModel(object):
 
     # ------------------------------------------------------------------ checkpoints (chem_tensorflow.py:309-359)
     def save_progress(self, model_path: str, train_step: int, valid_step: int) -> None:
+        # keys = the names TensorFlow 1.3 gives the same variables (tf.GraphKeys.GLOBAL_VARIABLES, chem_tensorflow.py:310-313), shapes as the
+        # reference creates them, plus Adam's slot variables and beta powers -- so a pickle moves between the two implementations.
         weights_to_save = {n: v.detach().cpu().numpy() for n, v in self.trainable_variables()}
+        opt = getattr(self, 'optimizer', None)
+        if opt is not None:
+            step = 0
+            for n, v in getattr(self, '_train_vars', []):
+                st = opt.state.get(v)
+                if st:
+                    weights_to_save[n[:-2] + '/Adam:0'] = st['exp_avg'].detach().cpu().numpy()
+                    weights_to_save[n[:-2] + '/Adam_1:0'] = st['exp_avg_sq'].detach().cpu().numpy()
+                    step = int(st['step'])
+            b1, b2 = opt.param_groups[0]['betas']
+            weights_to_save['beta1_power:0'] = np.float32(b1 ** (step + 1))   # tf.train.AdamOptimizer keeps beta^(t+1) after t updates
+            weights_to_save['beta2_power:0'] = np.float32(b2 ** (step + 1))
         with open(model_path, 'wb') as out_file:
             pickle.dump({"params": self.params, "weights": weights_to_save, "train_step": train_step, "valid_step": valid_step},
                         out_file, pickle.HIGHEST_PROTOCOL)
@@ -285,14 +304,28 @@ class ChemModel(object):
             if par not in ['task_ids', 'num_epochs']:
                 assert par_value == data_to_load['params'][par]
         used = set()
+        saved = data_to_load['weights']
         for n, v in self.trainable_variables():
             used.add(n)
-            if n in data_to_load['weights']:
+            if n in saved:
                 with torch.no_grad():
-                    v.copy_(torch.from_numpy(data_to_load['weights'][n]).to(v.device))
+                    v.copy_(torch.from_numpy(np.asarray(saved[n], dtype=np.float32)).reshape(v.shape).to(v.device))
             else:
                 print('Freshly initializing %s since no saved value was found.' % n)
-        for n in data_to_load['weights']:
+        # Adam slots (TF names "<variable>/Adam:0", "<variable>/Adam_1:0", "beta1_power:0"): restored when present
+        opt = getattr(self, 'optimizer', None)
+        if opt is not None and 'beta1_power:0' in saved:
+            b1 = opt.param_groups[0]['betas'][0]
+            step = max(int(round(np.log(float(saved['beta1_power:0'])) / np.log(b1))) - 1, 0)
+            used.update(('beta1_power:0', 'beta2_power:0'))
+            for n, v in self._train_vars:
+                m, s2 = n[:-2] + '/Adam:0', n[:-2] + '/Adam_1:0'
+                if m in saved and s2 in saved:
+                    used.update((m, s2))
+                    opt.state[v] = {'step': torch.tensor(float(step)),
+                                    'exp_avg': torch.from_numpy(np.asarray(saved[m], dtype=np.float32)).reshape(v.shape).to(v.device).clone(),
+                                    'exp_avg_sq': torch.from_numpy(np.asarray(saved[s2], dtype=np.float32)).reshape(v.shape).to(v.device).clone()}
+        for n in saved:
             if n not in used:
                 print('Saved weights for %s not used by model.' % n)
         self.after_weight_update()

@@ -110,16 +110,24 @@ class SparseGGNNChemModel(ChemModel):
         self._readout = gated_readout_function()
 
     def graph_model_variables(self):
+        """(name, tensor) with the names TensorFlow 1.3 gives these variables in the reference graph (what its pickles are keyed by,
+        chem_tensorflow.py:310-313): tf.Variable names under variable_scope graph_model/gnn_layer_i (sparse:87-100); the cell's variables
+        are created by its first call, inside .../timestep_0 (sparse:153-154,215), as gru_cell/{gates,candidate}/{kernel,bias} or
+        basic_rnn_cell/{kernel,bias} (TF-1.3 rnn_cell_impl).  Restated from knowledge of that release; no TF here to confirm."""
         out = []
+        tf_cell = {'gate_kernel': 'gru_cell/gates/kernel', 'gate_bias': 'gru_cell/gates/bias',
+                   'cand_kernel': 'gru_cell/candidate/kernel', 'cand_bias': 'gru_cell/candidate/bias'}
+        if self.params['graph_rnn_cell'].lower() == 'rnn':
+            tf_cell = {'cand_kernel': 'basic_rnn_cell/kernel', 'cand_bias': 'basic_rnn_cell/bias'}
         for l, w in enumerate(self.gnn_weights.edge_weights):
-            out.append(("graph_model/gnn_layer_%i/gnn_edge_weights_%i" % (l, l), w))
-        for l, b in enumerate(self.gnn_weights.edge_biases):
-            out.append(("graph_model/gnn_layer_%i/gnn_edge_biases_%i" % (l, l), b))
+            out.append(("graph_model/gnn_layer_%i/gnn_edge_weights_%i:0" % (l, l), w))            # [T*D, D], sparse:88
         for l, a in enumerate(self.gnn_weights.edge_type_attention_weights):
-            out.append(("graph_model/gnn_layer_%i/edge_type_attention_weights_%i" % (l, l), a))
+            out.append(("graph_model/gnn_layer_%i/edge_type_attention_weights_%i:0" % (l, l), a))
+        for l, b in enumerate(self.gnn_weights.edge_biases):
+            out.append(("graph_model/gnn_layer_%i/gnn_edge_biases_%i:0" % (l, l), b))
         for l, cell in enumerate(self.gnn_weights.rnn_cells):
             for k, v in cell.items():
-                out.append(("graph_model/gnn_layer_%i/cell/%s" % (l, k), v))
+                out.append(("graph_model/gnn_layer_%i/timestep_0/%s:0" % (l, tf_cell[k]), v))
         return out
 
     # ------------------------------------------------------------------ hook 2 (sparse:117-218)
