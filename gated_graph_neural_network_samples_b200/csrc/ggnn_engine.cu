@@ -117,6 +117,7 @@ struct ggnn_engine {
     float* last_out = nullptr;
     bool save = false;
     bool saved_valid = false;
+    int tc_row_budget = 128, tc_kgs = 2048;   // tensor-core plan: no tile has more rows than the budget; <= 64 selects compact operand tiles
     int use_att = 0;                 // use_propagation_attention (sparse:170-196): fp32 path only
     DevBuf att_buf;                  // attention probabilities per target-CSR slot ([steps][M] when saving for backward, else [M])
     size_t off_tslot = 0;            // source-keyed CSR entry -> target-CSR slot (attention backward)
@@ -231,10 +232,13 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
         }
         if (V == 0) tile_start.assign(1, 0);
         e->ntiles = (int)tile_start.size() - 1;
+        e->tc_row_budget = e->local ? budget : tc::TILE_M;
+        // compact operand tiles when no tile exceeds 64 rows (k-group stride 1024 instead of 2048): half the operand bytes, a ~3x deeper ring
+        e->tc_kgs = (e->tc_row_budget <= 64 && !getenv("GGNN_TC_NO_COMPACT")) ? 1024 : 2048;
         char buf[256];
-        snprintf(buf, sizeof buf, "tcgen05-%s %s tiles=%d rows/tile<=%d DP=%d max_component=%d",
+        snprintf(buf, sizeof buf, "tcgen05-%s %s tiles=%d rows/tile<=%d%s DP=%d max_component=%d",
                  e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)",
-                 e->ntiles, budget, e->DP, max_span);
+                 e->ntiles, budget, e->tc_kgs == 1024 ? " (compact 64-row operand tiles)" : "", e->DP, max_span);
         e->plan_text = buf;
         return GGNN_OK;
     }
@@ -930,7 +934,8 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     p.gather_mode = e->gather_mode; p.dense_v = e->dense_v; p.save = e->save ? 1 : 0;
     p.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
     p.drop_keep = e->drop_keep; p.drop_seed = e->drop_seed;
-    const size_t opb = (size_t)DP * 512, stage = (size_t)DP * 128;   // a ring slot = two 64*DP-byte K-step stages
+    p.kgs = e->tc_kgs;
+    const size_t opb = (size_t)DP * (size_t)p.kgs / 4, stage = (size_t)DP * 128;   // a ring slot = two 64*DP-byte K-step stages
     // tile-local sparse graphs: stage the tile's CSR slice in shared memory when it is small enough
     p.csr_cache = 0; p.csr_cap_msgs = 0;
     size_t csr_b = 0;
@@ -979,8 +984,8 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     p.error_flag = (int*)e->err_flag.ptr;
     p.dbg = nullptr;
     if (getenv("GGNN_TC_DEBUG_TIMING")) {
-        CU_TRY(e, e->dbg_buf.reserve(64 * sizeof(long long)));
-        CU_TRY(e, cudaMemsetAsync(e->dbg_buf.ptr, 0, 64 * sizeof(long long), st));
+        CU_TRY(e, e->dbg_buf.reserve(512 * sizeof(long long)));
+        CU_TRY(e, cudaMemsetAsync(e->dbg_buf.ptr, 0, 512 * sizeof(long long), st));
         p.dbg = (long long*)e->dbg_buf.ptr;
     }
     const size_t vd_bytes = (size_t)e->V * e->D * sizeof(float);
@@ -1250,7 +1255,16 @@ int ggnn_debug_timestamps(ggnn_engine* e, int64_t* out64) {
     if (!e->dbg_buf.ptr) return e->fail(GGNN_ESTATE, "no debug timestamps recorded (set GGNN_TC_DEBUG_TIMING=1)");
     CU_TRY(e, cudaSetDevice(e->device));
     CU_TRY(e, cudaDeviceSynchronize());
-    CU_TRY(e, cudaMemcpy(out64, e->dbg_buf.ptr, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU_TRY(e, cudaMemcpy(out64, e->dbg_buf.ptr, 64 * sizeof(long long), cudaMemcpyDeviceToHost));   // the phase stamps; ggnn_debug_trace returns everything
+    return GGNN_OK;
+}
+
+int ggnn_debug_trace(ggnn_engine* e, int64_t* out, int32_t capacity) {
+    if (!e || !out || capacity <= 0) return GGNN_EINVAL;
+    if (!e->dbg_buf.ptr) return e->fail(GGNN_ESTATE, "no debug trace recorded (set GGNN_TC_DEBUG_TIMING=1)");
+    CU_TRY(e, cudaSetDevice(e->device));
+    CU_TRY(e, cudaDeviceSynchronize());
+    CU_TRY(e, cudaMemcpy(out, e->dbg_buf.ptr, sizeof(long long) * (size_t)std::min(capacity, 512), cudaMemcpyDeviceToHost));
     return GGNN_OK;
 }
 

@@ -12,7 +12,8 @@
 // the fp32 master copy of the node states also lives in TMEM, so the recurrence never leaves the SM in LOCAL mode.
 //
 // Shared memory: three A-operand tiles (h, agg, A_t / r*h), each hi+lo in the canonical K-major no-swizzle UMMA
-// layout  byte(row, k) = part*(DP*256) + (k/8)*2048 + row*16 + (k%8)*2 ,  plus a ring of weight stages that a
+// layout  byte(row, k) = part*(DP*256) + (k/8)*2048 + row*16 + (k%8)*2  (half of both strides when every tile has <= 64 rows:
+// compact tiles, see KGS below),  plus a ring of weight stages that a
 // producer thread fills with cp.async.bulk (1-D TMA) from a pre-split, pre-tiled bf16 copy of the weights.  The stream is
 // latency bound (bytes in flight / slot round trip), so the ring is extended into A-operand tiles while they hold no live
 // operand: the A_t / r*h tile during the gate GEMM, the h tile during the candidate GEMM.
@@ -36,10 +37,14 @@ constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane qu
 #endif
 constexpr int NUM_ISSUERS = GGNN_TC_ISSUERS;            // MMA-issuing warps; issuer i owns the weight slots s with s % NUM_ISSUERS == i (2 and 3 verified, 4 deadlocks)
 constexpr int WARP_MMA = 16;              // first issuer warp
-constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // weight producer (one thread, strictly in order) + TMEM allocator
-constexpr int NTHREADS = (WARP_PROD + 1) * 32;
-constexpr int MAX_STAGES = 4;             // ring slots proper; a slot holds TWO K-step stages (2 x 64*DP bytes, one bulk copy)
-constexpr int EXT_SLOTS = 4;              // an idle A-operand tile holds exactly 4 more slots (DP*512 / DP*128)
+#ifndef GGNN_TC_PRODUCERS
+#define GGNN_TC_PRODUCERS 2
+#endif
+constexpr int NUM_PRODUCERS = GGNN_TC_PRODUCERS;   // weight-producer warps (one thread each); producer j owns the slots s with s % NUM_PRODUCERS == j
+constexpr int WARP_PROD = WARP_MMA + NUM_ISSUERS;   // first producer warp (also the TMEM allocator)
+constexpr int NTHREADS = (WARP_PROD + NUM_PRODUCERS) * 32;
+constexpr int MAX_STAGES = 10;            // ring slots proper; a slot holds TWO K-step stages (2 x 64*DP bytes, one bulk copy)
+constexpr int EXT_SLOTS = 4;              // an idle 128-row A-operand tile holds 4 more slots (DP*512 / DP*128); a compact 64-row tile holds 2
 constexpr int MAX_SLOTS = MAX_STAGES + 2 * EXT_SLOTS;
 enum { SET_BASE = 0, SET_XA = 1, SET_XH = 2 };   // ring only | ring + opA tile (gate phase) | ring + opH tile (candidate phase)
 
@@ -62,6 +67,7 @@ struct TcParams {
     int gather_mode, dense_v, save;
     int nparts;   // 3: bf16x3 (fp32-accurate), 1: single bf16 MMA
     int nstages;  // weight ring depth
+    int kgs;            // A-operand k-group stride in bytes: 2048 (128-row tiles) or 1024 (compact: every tile has <= 64 rows)
     int csr_cache;      // LOCAL sparse only: the tile's CSR slice is staged in shared memory (uint16 row offsets, uint8 local sources)
     int csr_cap_msgs;   // capacity of the shared source array
     const int* tile_start;
@@ -83,7 +89,8 @@ struct TcParams {
     float drop_keep;                // state dropout (ggnn_common.cuh dropout_apply); off when >= 1
     unsigned long long drop_seed;
     int* error_flag;
-    long long* dbg;  // optional [64] clock64 stamps written by tile 0 / thread 0 (profiling aid), or nullptr
+    long long* dbg;  // optional [512] profiling aid written by tile 0, or nullptr: [0,64) phase stamps (see tools/tc_phase_timing.py),
+                     // then (code, clock64) event pairs of the SECOND timestep: [64,192) worker thread 0, [192,320) issuer 0, [320,448) producer 0
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -204,12 +211,14 @@ __device__ __forceinline__ float act_fast(float v, int act) {
 }
 
 // store one [row, 8-column chunk] of an A operand (both parts)
-__device__ __forceinline__ void store_operand_chunk(uint8_t* op, int DP, int kc, int row, const float (&x)[8]) {
+// (rows at or beyond the allocated row count of a compact tile are not stored: they would alias the next k-group)
+__device__ __forceinline__ void store_operand_chunk(uint8_t* op, uint32_t kgs, uint32_t part_b, int kc, int row, const float (&x)[8]) {
+    if ((uint32_t)row * 16u >= kgs) return;
     uint4 hi, lo;
     split8(x, hi, lo);
-    uint8_t* p = op + (size_t)kc * 2048 + (size_t)row * 16;
+    uint8_t* p = op + (size_t)kc * kgs + (size_t)row * 16;
     *reinterpret_cast<uint4*>(p) = hi;
-    *reinterpret_cast<uint4*>(p + (size_t)DP * 256) = lo;
+    *reinterpret_cast<uint4*>(p + part_b) = lo;
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -253,7 +262,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     const int D = p.D, DP = p.DP, T = p.T;
     const int NKC = DP >> 3;   // 8-column chunks per DP
     const int NKS = DP >> 4;   // UMMA K-steps (16) per DP-wide operand
-    const uint32_t OPB = (uint32_t)DP * 512u;          // bytes per A operand (hi + lo)
+    // A operand tile: byte(row, k) = part*PART_B + (k/8)*KGS + row*16 + (k%8)*2.  KGS = 16 * allocated rows.  A compact tile (64 rows) is
+    // still multiplied with M = 128: the MMA's rows 64..127 of k-group g alias rows 0..63 of k-group g+1 -- in-bounds bytes whose products land
+    // in TMEM lanes 64..127, which nobody reads.  Half the operand bytes leave room for a ~3x deeper weight ring.
+    const uint32_t KGS = (uint32_t)p.kgs;
+    const uint32_t PART_B = (uint32_t)DP * KGS / 8u;   // bytes per part (hi or lo)
+    const uint32_t OPB = 2u * PART_B;                  // bytes per A operand (hi + lo)
+    const uint32_t EXT = KGS / 512u;                   // ring slots an idle operand tile can hold
     const uint32_t STAGE_B = (uint32_t)DP * 64u;       // bytes per weight stage (K = 16 x N = DP, hi + lo)
     uint8_t* opH = smem;
     uint8_t* opX = opH + OPB;
@@ -301,6 +316,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     if (warp < NUM_WORKERS / 32) {
         // =============================================================================== WORKERS
         const int q = warp & 3, cg = warp >> 2;      // TMEM lane quarter, column-chunk group
+        // compact tiles (<= 64 rows): the warps of lane quarters 2 and 3 own no rows -- they keep every rendezvous but skip the column loops
+        const int nkc_tile = NKC;
+        const int NKC = ((uint32_t)(q * 32) * 16u < KGS) ? nkc_tile : 0;
         constexpr int NCG = NUM_WORKERS / 128;       // chunk groups (warps per lane quarter)
         const int row = q * 32 + lane;               // tile row == TMEM lane
         const bool row_ok = row < rows;
@@ -316,9 +334,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory");
             if (*abortp) ok = false;
         };
+        int* ev_ip = nullptr; int* ev_sp = nullptr;   // set below (the event log of thread 0)
+        auto ev_raw = [&](int code) {
+            if (ev_ip && p.dbg && tile == 0 && tid == 0 && *ev_sp == 1 && *ev_ip < 64) { p.dbg[64 + 2 * *ev_ip] = code; p.dbg[65 + 2 * *ev_ip] = clock64(); ++*ev_ip; }
+        };
         auto wait_on = [&](uint64_t* bar, uint32_t parity) {
+            ev_raw(1);
             if (warp == 0 && ok) { if (!mbar_wait(bar, parity, abortp)) *abortp = 1; }
+            ev_raw(2);
             asm volatile("bar.sync 1, %0;" ::"n"(NUM_WORKERS) : "memory");
+            ev_raw(3);
             if (*abortp) ok = false;
             if (ok) tc_fence_after();
         };
@@ -330,7 +355,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         const float zeros8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float* res_pre = p.res_pre + (size_t)tile * TILE_M * 3 * DP + (size_t)row * 3 * DP;
         int dbg_i = 0;
-        auto stamp = [&]() { if (p.dbg && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); };
+        int ev_i = 0, ev_step = -1;
+        ev_ip = &ev_i; ev_sp = &ev_step;
+        auto ev = [&](int code) {
+            if (p.dbg && tile == 0 && tid == 0 && ev_step == 1 && ev_i < 64) { p.dbg[64 + 2 * ev_i] = code; p.dbg[65 + 2 * ev_i] = clock64(); ++ev_i; }
+        };
+        auto stamp = [&]() { if (p.dbg && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); ev(9); };
         stamp();   // 0: start
 
         // ---- initial state: global fp32 -> TMEM (fp32 master) + opH (bf16 hi/lo)
@@ -340,7 +370,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 float v[8];
                 load8_guarded_cg(hin, kc * 8, row_ok ? D : 0, v);
                 tmem_st8(TM_H + lane_addr + kc * 8, v);
-                store_operand_chunk(opH, DP, kc, row, v);
+                store_operand_chunk(opH, KGS, PART_B, kc, row, v);
             }
             for (int c = cg; c < 3 * NKC; c += NCG) tmem_st8(TM_ACC + lane_addr + c * 8, zeros8);   // acc + gate accumulators start at zero
             tmem_st_wait();
@@ -378,7 +408,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     for (int kc = cg; kc < NKC; kc += NCG) {
                         float v[8];
                         load8_guarded_cg(rs, kc * 8, row_ok ? D : 0, v);
-                        store_operand_chunk(opA, DP, kc, row, v);
+                        store_operand_chunk(opA, KGS, PART_B, kc, row, v);
                     }
                     publish();
                 }
@@ -400,10 +430,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 }
             }
             for (int s = s_begin; s < s_end && ok; ++s) {
+                ev_step = (l == l_begin) ? s - s_begin : -1;
+                ev(8);   // step start
                 const size_t save_off = (size_t)(p.step_base[l] + s) * VD + (size_t)grow * D;
                 // ------------------------------------------------------------ gather + G1 per present type
                 // A_t tiles alternate between opA and opX so that gathering type n+1 overlaps the MMAs of type n
                 int nty = 0;
+                // The gather touches shared memory only (no TMEM lane-quarter restriction), so with compact tiles -- rows live in lane
+                // quarters 0 and 1 only -- all 16 worker warps share it: row group = warp & 1, eight column-chunk groups instead of four.
+                const bool gsplit = KGS == 1024u;
+                const int g_row = gsplit ? ((warp & 1) * 32 + lane) : row;
+                const bool g_row_ok = g_row < rows;
+                const int g_grow = g_row_ok ? row0 + g_row : row0;
+                const int g_cg = gsplit ? (warp >> 1) : cg, g_ncg = gsplit ? NUM_WORKERS / 64 : NCG;
+                const int g_nkc = gsplit ? nkc_tile : NKC;
                 for (int t = 0; t < T && ok; ++t) {
                     if (!((tmask >> t) & 1u)) continue;
                     const int b = nty & 1;
@@ -411,20 +451,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     uint8_t* gdst = b ? opX : opA;
                     ++nty;
                     int beg = 0, end = 0, dg = 0, di = 0;
-                    if (row_ok) {
+                    if (g_row_ok) {
                         if (p.gather_mode == GATHER_SPARSE) {
-                            if (csr_smem) { beg = sRowPtr[row * T + t]; end = sRowPtr[row * T + t + 1]; }
-                            else { beg = p.row_ptr[(size_t)grow * T + t]; end = p.row_ptr[(size_t)grow * T + t + 1]; }
-                        } else { dg = grow / p.dense_v; di = grow - dg * p.dense_v; }
+                            if (csr_smem) { beg = sRowPtr[g_row * T + t]; end = sRowPtr[g_row * T + t + 1]; }
+                            else { beg = p.row_ptr[(size_t)g_grow * T + t]; end = p.row_ptr[(size_t)g_grow * T + t + 1]; }
+                        } else { dg = g_grow / p.dense_v; di = g_grow - dg * p.dense_v; }
                     }
-                    for (int kc = cg; kc < NKC; kc += NCG) {
+                    for (int kc = g_cg; kc < g_nkc; kc += g_ncg) {
                         float acc[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
                         if (LOCAL && csr_smem) {
                             // fast path: local source indices from shared memory, two messages in flight
-                            const uint8_t* colbase = opH + (size_t)kc * 2048;
-                            const uint32_t lo_off = (uint32_t)DP * 256u;
+                            const uint8_t* colbase = opH + (size_t)kc * KGS;
+                            const uint32_t lo_off = PART_B;
                             int m = beg;
                             if (p.nparts == 3) {
                                 for (; m + 1 < end; m += 2) {
@@ -447,9 +487,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                             for (int m = beg; m < end; ++m) {
                                 if (LOCAL) {
                                     const int sl = csr_smem ? (int)sSrc[m] : (p.csr_src[m] - row0);
-                                    const uint8_t* sp = opH + (size_t)kc * 2048 + (size_t)sl * 16;
+                                    const uint8_t* sp = opH + (size_t)kc * KGS + (size_t)sl * 16;
                                     unpack8_add(*reinterpret_cast<const uint4*>(sp), acc, 1.0f);
-                                    if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + (size_t)DP * 256), acc, 1.0f);
+                                    if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + PART_B), acc, 1.0f);
                                 } else {
                                     // GLOBAL mode: source rows come from the previous step's fp32 state in L2; keep 4 rows in flight
                                     float hv[4][8];
@@ -466,7 +506,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                     m += nb - 1;
                                 }
                             }
-                        } else if (row_ok) {
+                        } else if (g_row_ok) {
                             const int nv = p.dense_v;
                             const float* arow = p.dense_adj + (((size_t)dg * T + t) * nv + di) * nv;
                             for (int jn = 0; jn < nv; ++jn) {
@@ -474,9 +514,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                 if (a != 0.0f) {
                                     const int src = dg * nv + jn;
                                     if (LOCAL) {
-                                        const uint8_t* sp = opH + (size_t)kc * 2048 + (size_t)(src - row0) * 16;
+                                        const uint8_t* sp = opH + (size_t)kc * KGS + (size_t)(src - row0) * 16;
                                         unpack8_add(*reinterpret_cast<const uint4*>(sp), acc, a);
-                                        if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + (size_t)DP * 256), acc, a);
+                                        if (p.nparts == 3) unpack8_add(*reinterpret_cast<const uint4*>(sp + PART_B), acc, a);
                                     } else {
                                         float hv[8];
                                         load8_guarded_cg(p.g_in + (size_t)src * D, kc * 8, D, hv);
@@ -486,7 +526,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                 }
                             }
                         }
-                        store_operand_chunk(gdst, DP, kc, row, acc);
+                        store_operand_chunk(gdst, KGS, PART_B, kc, g_row, acc);
                     }
                     publish_g(b);
                     stamp();   // gather of one type done
@@ -520,7 +560,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = row_ok ? v[j] * inv_den : 0.0f;
                         if (p.save && row_ok) store8_guarded(p.save_buf.agg + save_off, kc * 8, D, v);
-                        store_operand_chunk(opX, DP, kc, row, v);
+                        store_operand_chunk(opX, KGS, PART_B, kc, row, v);
                     }
                     publish();
                 }
@@ -548,10 +588,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                             store8_guarded(p.save_buf.r + save_off, kc * 8, D, g);
                             store8_guarded(p.save_buf.h_in + save_off, kc * 8, D, h);
                         }
-                        store_operand_chunk(opA, DP, kc, row, rh);
+                        store_operand_chunk(opA, KGS, PART_B, kc, row, rh);
                     }
                     publish();
                     stamp();   // r*h epilogue done
+                    // u = sigmoid(gate_u + b_u) while the candidate's recurrent MMAs run; parked in the gate-u accumulator columns (the candidate
+                    // GEMM only touches the agg/cand accumulator) so that the state update below is just tanh + blend
+                    for (int kc = cg; kc < NKC; kc += NCG) {
+                        float u[8], bu[8];
+                        tmem_ld8_nowait(TM_GATE + lane_addr + DP + kc * 8, u);
+                        lds8(sBias + DP + kc * 8, bu);
+                        if (ly.nres > 0) {
+                            float rp[8];
+                            lds8(res_pre + DP + kc * 8, rp);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) bu[j] += rp[j];
+                        }
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) u[j] = sigmoid_fast(u[j] + bu[j]);
+                        if (p.save && row_ok) store8_guarded(p.save_buf.u + save_off, kc * 8, D, u);
+                        tmem_st8(TM_GATE + lane_addr + DP + kc * 8, u);
+                    }
+                    tmem_st_wait();
                 }
                 // ------------------------------------------------------------ candidate ready: new state
                 wait_mma(); if (!ok) break;
@@ -564,15 +623,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                         tmem_ld8_nowait(TM_ACC + lane_addr + kc * 8, c);
                         lds8(sBias + 2 * DP + kc * 8, bc);
                         if (gru) {
-                            float bu[8];
-                            tmem_ld8_nowait(TM_GATE + lane_addr + DP + kc * 8, u);
+                            tmem_ld8_nowait(TM_GATE + lane_addr + DP + kc * 8, u);   // already sigmoid(gate_u + b_u), see above
                             tmem_ld8_nowait(TM_H + lane_addr + kc * 8, h);
-                            lds8(sBias + DP + kc * 8, bu);
                             if (ly.nres > 0) {
                                 float rp[8];
-                                lds8(res_pre + DP + kc * 8, rp);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) bu[j] += rp[j];
                                 lds8(res_pre + 2 * DP + kc * 8, rp);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) bc[j] += rp[j];
@@ -582,14 +636,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                             tmem_st8(TM_GATE + lane_addr + DP + kc * 8, zeros8);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                u[j] = sigmoid_fast(u[j] + bu[j]);
                                 c[j] = act_fast(c[j] + bc[j], p.act);
                                 hn[j] = fmaf(u[j], h[j] - c[j], c[j]);   // u*h + (1-u)*c
                             }
-                            if (p.save && row_ok) {
-                                store8_guarded(p.save_buf.u + save_off, kc * 8, D, u);
-                                store8_guarded(p.save_buf.c + save_off, kc * 8, D, c);
-                            }
+                            if (p.save && row_ok) store8_guarded(p.save_buf.c + save_off, kc * 8, D, c);
                         } else {
                             if (p.save) tmem_ld8_nowait(TM_H + lane_addr + kc * 8, h);
                             if (ly.nres > 0) {
@@ -610,7 +660,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                                 hn[j] = dropout_apply(hn[j], p.drop_seed, p.step_base[l] + s, p.V, D, grow, kc * 8 + j, p.drop_keep);
                         }
                         tmem_st8(TM_H + lane_addr + kc * 8, hn);
-                        store_operand_chunk(opH, DP, kc, row, hn);
+                        store_operand_chunk(opH, KGS, PART_B, kc, row, hn);
                         if (outp && row_ok) store8_guarded(outp + (size_t)grow * D, kc * 8, D, hn);
                     }
                     tmem_st_wait();
@@ -637,10 +687,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             const bool x3 = p.nparts == 3;
             const uint32_t nstg = (uint32_t)nst;
             const uint32_t iw = (uint32_t)(warp - WARP_MMA);
-            const uint32_t a_lo16 = ((uint32_t)DP * 256u) >> 4;   // hi -> lo part of an A operand (16-byte units)
+            const uint32_t a_lo16 = PART_B >> 4;                   // hi -> lo part of an A operand (16-byte units)
+            const uint32_t a_k16 = KGS >> 3;                       // one K-step (16 columns = two k-groups) of an A operand (16-byte units)
             const uint32_t b_lo16 = ((uint32_t)DP * 32u) >> 4;    // hi -> lo part of a narrow weight slot
             const uint32_t stage16 = STAGE_B >> 4;
-            const uint64_t descA = make_desc(0, 2048, 128);
+            const uint64_t descA = make_desc(0, KGS, 128);
             const uint64_t descB1 = make_desc(0, 16u * (uint32_t)DP, 128);   // N = DP   operand: K-chunk stride 16*DP
             const uint64_t descB2 = make_desc(0, 32u * (uint32_t)DP, 128);   // N = 2*DP operand: K-chunk stride 32*DP
             const uint32_t opH16 = smem_u32(opH) >> 4, opX16 = smem_u32(opX) >> 4, opA16 = smem_u32(opA) >> 4, ring16 = smem_u32(ring) >> 4;
@@ -651,19 +702,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             long long dbg_ready = 0;
             const long long dbg_t0 = clock64();
             int dbg_g = 0;
+            int iev_i = 0, iev_step = -1;
+            auto iev = [&](int code) {
+                if (dbg_on && iev_step == 1 && iev_i < 64) { p.dbg[192 + 2 * iev_i] = code; p.dbg[193 + 2 * iev_i] = clock64(); ++iev_i; }
+            };
             uint32_t ph_ready = 0, ph_g = 0;
             uint32_t cur[3] = {0, 0, 0};   // round-robin cursor of each slot set
             uint32_t fpar = 0;             // bit s = parity to wait for on bar_w_full[s]
             bool ok = true;
             auto next_slot = [&](int set) -> uint32_t {
-                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT_SLOTS;
+                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT;
                 const uint32_t i = cur[set];
                 cur[set] = (i + 1 == n) ? 0u : i + 1;
-                return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
+                return (set == SET_XH && i >= nstg) ? i + EXT : i;
             };
             auto slot16 = [&](uint32_t sl) -> uint32_t {
                 return sl < nstg ? ring16 + sl * 2u * stage16
-                     : sl < nstg + EXT_SLOTS ? opA16 + (sl - nstg) * 2u * stage16 : opH16 + (sl - nstg - EXT_SLOTS) * 2u * stage16;
+                     : sl < nstg + EXT ? opA16 + (sl - nstg) * 2u * stage16 : opH16 + (sl - nstg - EXT) * 2u * stage16;
             };
             auto wait_full = [&](uint32_t sl) {
                 const uint32_t par = (fpar >> sl) & 1u;
@@ -684,6 +739,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             auto gemm = [&](uint32_t op16, uint32_t tm_col, bool wide, int set) {
                 if (!ok) return;
                 if (dbg_on && dbg_g < 20) p.dbg[40 + dbg_g++] = clock64();   // start of each of the first 20 GEMM blocks
+                iev(10);
+                bool first_w = true;
                 const uint32_t tm_d = tmem_u + tm_col;
                 const int nslots = wide ? NKS : (NKS + 1) / 2;
 #pragma unroll 1
@@ -695,11 +752,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     if (sl % NUM_ISSUERS != iw) continue;
                     wait_full(sl);
                     if (!ok) return;
+                    if (first_w) { iev(11); first_w = false; }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t b16 = slot16(sl);
                         if (wide) {
-                            const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)i * 256u);
+                            const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)i * a_k16);
                             const uint64_t bh = descB2 | (uint64_t)b16, bl = descB2 | (uint64_t)(b16 + stage16);
                             umma_bf16(tm_d, ad, bh, idesc2, 1u);
                             if (x3) {
@@ -709,7 +767,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                         } else {
                             const int nk = (2 * i + 1 < NKS) ? 2 : 1;
                             for (int h = 0; h < nk; ++h) {
-                                const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)(2 * i + h) * 256u);
+                                const uint64_t ad = descA | (uint64_t)(op16 + (uint32_t)(2 * i + h) * a_k16);
                                 const uint64_t bd = descB1 | (uint64_t)(b16 + (uint32_t)h * stage16);
                                 umma_bf16(tm_d, ad, bd, idesc, 1u);
                                 if (x3) {
@@ -722,10 +780,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     }
                     __syncwarp();
                 }
+                iev(12);
             };
             auto commit_to = [&](uint64_t* bar) { if (ok) { if (elect_one()) umma_commit(bar); __syncwarp(); } };
             auto wait_bar = [&](uint32_t rb, uint32_t par) {
                 if (!ok) return;
+                iev(13);
                 if (!mbar_try(rb, par)) {
                     const long long w0 = dbg_on ? clock64() : 0;
                     if (!mbar_wait_slow(rb, par, abortp)) ok = false;
@@ -733,6 +793,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 }
                 ok = __all_sync(0xffffffffu, ok);
                 tc_fence_after();
+                iev(14);
             };
             auto wait_ready = [&]() { wait_bar(smem_u32(&bar_a_ready), ph_ready & 1); ++ph_ready; };
             auto wait_g_ready = [&](int b) { wait_bar(smem_u32(&bar_g_ready[b]), (ph_g >> b) & 1u); ph_g ^= 1u << b; };
@@ -751,6 +812,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     }
                 }
                 for (int s = s_begin; s < s_end && ok; ++s) {
+                    iev_step = (l == l_begin) ? s - s_begin : -1;
                     int nty = 0;
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
@@ -779,29 +841,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         }
     } else {
         // =============================================================================== WEIGHT PRODUCER
-        // One thread, strictly in order.  The stream is bound by the per-push issue cost (wait, expect_tx, bulk copy: ~430 cycles),
-        // so a push moves a whole slot = two stages (2 x 64*DP bytes, contiguous in the pre-tiled weights) with one bulk copy.
+        // One thread per producer warp.  The stream is bound by the per-push issue cost (wait, expect_tx, bulk copy: ~430 cycles),
+        // so a push moves a whole slot = two stages (2 x 64*DP bytes, contiguous in the pre-tiled weights) with one bulk copy, and the
+        // slots are dealt statically to NUM_PRODUCERS threads (a slot always has the same producer and the same issuer, so every mbarrier
+        // is waited on phase by phase -- parity waits alias when an agent can lap another).
         if (lane == 0) {
             const uint32_t nstg = (uint32_t)nst;
+            const uint32_t pw = (uint32_t)(warp - WARP_PROD);   // every producer walks the whole push sequence and fills the slots it owns
             uint32_t cur[3] = {0, 0, 0};
             uint32_t used = 0, epar = 0;   // bit s: slot s has been filled before / parity to wait for on bar_w_empty[s]
             uint32_t ph_xa = 0, ph_xh = 0;
             bool ok = true;
+            int pev_i = 0, pev_step = -1;
+            auto pev = [&](int code) {
+                if (p.dbg && tile == 0 && pw == 0 && pev_step == 1 && pev_i < 64) { p.dbg[320 + 2 * pev_i] = code; p.dbg[321 + 2 * pev_i] = clock64(); ++pev_i; }
+            };
             auto next_slot = [&](int set) -> uint32_t {
-                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT_SLOTS;
+                const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT;
                 const uint32_t i = cur[set];
                 cur[set] = (i + 1 == n) ? 0u : i + 1;
-                return (set == SET_XH && i >= nstg) ? i + EXT_SLOTS : i;
+                return (set == SET_XH && i >= nstg) ? i + EXT : i;
             };
             auto slot_ptr = [&](uint32_t sl) -> uint8_t* {
                 return sl < nstg ? ring + sl * 2u * STAGE_B
-                     : sl < nstg + EXT_SLOTS ? opA + (sl - nstg) * 2u * STAGE_B : opH + (sl - nstg - EXT_SLOTS) * 2u * STAGE_B;
+                     : sl < nstg + EXT ? opA + (sl - nstg) * 2u * STAGE_B : opH + (sl - nstg - EXT) * 2u * STAGE_B;
             };
             // stream `nstages` consecutive 64*DP-byte stages of a pre-tiled matrix, two per slot, into the next slots of `set`
             auto push = [&](const uint8_t* src, int nstages, int set) {
+                pev(20);
                 for (int i = 0; i < nstages && ok; i += 2) {
                     const uint32_t bytes = (i + 1 < nstages) ? 2u * STAGE_B : STAGE_B;
                     const uint32_t sl = next_slot(set);
+                    if (sl % NUM_PRODUCERS != pw) continue;   // static ownership: each slot's barriers see ONE producer, in order
                     // a slot is free once the MMAs that read its previous contents have completed (first use: free)
                     if ((used >> sl) & 1u) {
                         if (!mbar_wait(&bar_w_empty[sl], (epar >> sl) & 1u, abortp)) { ok = false; break; }
@@ -811,6 +882,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     mbar_arrive_expect_tx(&bar_w_full[sl], bytes);
                     bulk_copy_g2s(slot_ptr(sl), src + (size_t)i * STAGE_B, bytes, &bar_w_full[sl]);
                 }
+                pev(21);
             };
             for (int l = l_begin; l < l_end && ok; ++l) {
                 const TcLayer& ly = p.layer[l];
@@ -826,16 +898,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 }
                 const size_t kx = (size_t)ly.nres, kh = (size_t)ly.nres + 1;
                 for (int s = s_begin; s < s_end && ok; ++s) {
+                    pev_step = (l == l_begin) ? s - s_begin : -1;
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
                         push(ly.w_edge + (size_t)t * blk, NKS, SET_BASE);
                     }
                     // the opA tile joins the ring once no MMA reads it any more (this step's G1 / last step's candidate are complete)
+                    pev(22);
                     if (ok) { ok = mbar_wait(&bar_xa_free, ph_xa & 1, abortp); ++ph_xa; }
+                    pev(23);
                     if (gru) {
                         push(ly.w_gate + kx * 2 * blk, 2 * NKS, SET_XA); push(ly.w_gate + kh * 2 * blk, 2 * NKS, SET_XA);
                         // the opH tile joins the ring once the gate GEMM (its last reader) is complete
+                        pev(24);
                         if (ok) { ok = mbar_wait(&bar_xh_free, ph_xh & 1, abortp); ++ph_xh; }
+                        pev(25);
                         push(ly.w_cand + kx * blk, NKS, SET_XH); push(ly.w_cand + kh * blk, NKS, SET_XH);
                     } else {
                         push(ly.w_cand + kx * blk, NKS, SET_XA); push(ly.w_cand + kh * blk, NKS, SET_XA);

@@ -175,6 +175,9 @@ const char* ggnn_plan_description(const ggnn_engine* e);
 /* Profiling aid: with GGNN_TC_DEBUG_TIMING=1 tile 0 of the tensor-core kernel records clock64() at its phase
  * boundaries; this copies the 64 stamps of the last launch to out64[64]. */
 int ggnn_debug_timestamps(ggnn_engine* e, int64_t* out64);
+/* ... and the full trace buffer (up to 512 entries): the phase stamps followed by (code, clock64) event pairs of the second
+ * timestep for worker thread 0, MMA issuer 0 and weight producer 0 of tile 0 (tools/tc_trace.py decodes them). */
+int ggnn_debug_trace(ggnn_engine* e, int64_t* out, int32_t capacity);
 
 #ifdef __cplusplus
 }
