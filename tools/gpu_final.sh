@@ -19,4 +19,6 @@ echo "== ncu launch list (default bench)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/launches_cfg2.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
 echo "== ncu full (tc kernel, cfg2)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ggnn_fwd_tc -s 3 -c 1 -o $OUT/prof_tc_cfg2 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
+timeout 100 python tools/tc_trace.py cfg2 > $OUT/tc_trace_cfg2.txt 2>&1
+timeout 100 python tools/tc_phase_timing.py cfg2 bf16x3 > $OUT/tc_phase_timing_cfg2.txt 2>&1
 ls -la $OUT | head -40
