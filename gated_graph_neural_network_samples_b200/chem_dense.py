@@ -102,6 +102,8 @@ class DenseGGNNChemModel(ChemModel):
             bucket_sizes = packing.DEFAULT_BUCKET_SIZES
         bucketed = defaultdict(list)
         for d in raw_data:
+            # arrays once, not once per batch: pack_dense_batch's np.asarray calls become no-ops (the dicts themselves are copies)
+            d = dict(d, graph=np.asarray(d['graph'], dtype=np.int64).reshape(-1, 3), node_features=np.asarray(d['node_features'], dtype=np.float32))
             bucketed[packing.choose_bucket(d['graph'], bucket_sizes)].append(d)
         if is_training_data:
             for _, bucket in bucketed.items():
