@@ -24,7 +24,8 @@ PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden vectors o
 TensorFlow 1.3 cannot run here, so this oracle is pinned only by (1) its own float64 loop-level
 statement vs. its vectorised fp32 statements, (2) the sparse == dense cross-implementation identity the
 reference's two model files imply, (3) hand-derived closed-form tiny graphs, and (4) batches produced
-by the reference's *own* NumPy packing code (tests/golden/make_golden.py imports it with TF stubbed).
+by the reference's *own* NumPy packing code (tests/golden/make_golden.py imports it with TF stubbed), and (5) an independent
+plain-C restatement (oracle/ggnn_oracle.c, message by message in double precision, no shared code) that must agree to 1e-12.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
 module.  The product path (``gated_graph_neural_network_samples_b200``) never does.

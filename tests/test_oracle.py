@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 from gated_graph_neural_network_samples_b200 import packing, synthetic
+from oracle import c_oracle as CO
 from oracle import ggnn_oracle as O
 from tests import _util as U
 
@@ -43,6 +44,7 @@ def test_loops_vs_vectorised_vs_torch(name):
     np.testing.assert_allclose(O.sparse_propagation_np(*args, dtype=np.float64), ref, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(O.sparse_propagation_np(*args, dtype=np.float32), ref, rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(O.sparse_propagation_torch(*args).numpy(), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(CO.sparse_propagation_c(*args), ref, rtol=1e-12, atol=1e-12)   # the independent plain-C restatement
 
 
 def test_sparse_equals_dense_cross_implementation():
@@ -134,6 +136,8 @@ def test_out_of_range_edge_raises():
     w = O.init_sparse_weights(p, 1, np.random.default_rng(2))
     with pytest.raises(IndexError):
         O.sparse_propagation_np(np.zeros((2, 9), np.float32), [np.array([[0, 2]], np.int32)], np.zeros((2, 1)), w, p)
+    with pytest.raises(IndexError):
+        CO.sparse_propagation_c(np.zeros((2, 9), np.float32), [np.array([[0, 2]], np.int32)], np.zeros((2, 1)), w, p)
 
 
 def test_stable_target_csr_is_message_order_within_target():
@@ -158,6 +162,7 @@ def test_golden_sparse_regression(golden_dir, name):
     states = O.sparse_propagation_loops(z["h0"], adj, z["indeg"], w, p, return_all_layers=True)
     for li, s in enumerate(states):
         np.testing.assert_allclose(s, z["state%d" % li], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(CO.sparse_propagation_c(z["h0"], adj, z["indeg"], w, p), z["final"], rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(O.sparse_propagation_torch(z["h0"], adj, z["indeg"], w, p).numpy(), z["final"],
                                rtol=2e-5, atol=2e-6)
 
@@ -167,6 +172,7 @@ def test_golden_dense_regression(golden_dir):
     p = json.loads(str(z["params_json"]))
     w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
     np.testing.assert_allclose(O.dense_propagation_loops(z["h0"], z["adj"], w, p), z["final"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(CO.dense_propagation_c(z["h0"], z["adj"], w, p), z["final"], rtol=1e-12, atol=1e-13)
 
 
 def test_propagation_attention_three_statements_agree():
@@ -181,6 +187,7 @@ def test_propagation_attention_three_statements_agree():
     a = O.sparse_propagation_loops(*args)
     np.testing.assert_allclose(O.sparse_propagation_np(*args, dtype=np.float64), a, rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(O.sparse_propagation_torch(*args, dtype=torch.float64).numpy(), a, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(CO.sparse_propagation_c(*args), a, rtol=1e-12, atol=1e-13)
     # uniform case: identical node states -> every message into a node has the same score
     p1 = dict(p, layer_timesteps=[1], residual_connections={}, use_edge_bias=False, use_edge_msg_avg_aggregation=False)
     w1 = O.init_sparse_weights(p1, 4, np.random.default_rng(2))
