@@ -59,7 +59,10 @@ class ChemModel(object):
         random.seed(params['random_seed'])                               # chem_tensorflow.py:69-70
         np.random.seed(params['random_seed'])
         torch.manual_seed(params['random_seed'])                         # tf.set_random_seed, :85
-        self.device = torch.device("cuda", int(args.get('--device') or 0))
+        dev = args.get('--device')
+        # the engine exists on CUDA only and refuses to be created elsewhere; "cpu" merely lets the host-side logic be unit-tested
+        # against a stand-in engine (tests/test_chem_model_cpu.py)
+        self.device = torch.device("cpu") if dev == "cpu" else torch.device("cuda", int(dev or 0))
         self.precision = args.get('--precision') or "fp32"
 
         self.max_num_vertices = 0
@@ -225,8 +228,8 @@ class ChemModel(object):
             else:
                 with torch.no_grad():
                     batch_loss, batch_accs = self.forward_batch(batch_data)
-            loss += float(batch_loss) * num_graphs
-            accuracies.append(np.array([float(a) for a in batch_accs]) * num_graphs)
+            loss += float(batch_loss.detach()) * num_graphs
+            accuracies.append(np.array([float(a.detach()) for a in batch_accs]) * num_graphs)
             print("Running %s, batch %i (has %i graphs). Loss so far: %.4f" % (epoch_name, step, num_graphs, loss / processed_graphs), end='\r')
             steps += 1
         accuracies = np.sum(accuracies, axis=0) / processed_graphs

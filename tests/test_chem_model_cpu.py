@@ -1,0 +1,104 @@
+"""CPU: the host-side logic of the ChemModel mirror and its two plug-ins (data loading, the flattened packer, feed dicts, readout
+fallback, loss, per-variable clipping + Adam, checkpoints keyed by TF variable names) driven end to end with a STAND-IN engine that
+answers ``compute_final_node_representations`` from the oracle.  The real engine has no CPU path (see test_abi_cpu.py); this file only
+makes sure the Python around it is exercised without a GPU."""
+import pickle
+
+import numpy as np
+import pytest
+
+from gated_graph_neural_network_samples_b200 import chem_dense, chem_sparse, synthetic
+from oracle import ggnn_oracle as O
+
+
+class StandInEngine:
+    def __init__(self, params, num_edge_types, device=0, precision="fp32"):
+        self.params, self.T, self.D = params, num_edge_types, int(params["hidden_size"])
+        self.drop = None
+
+    def set_save_for_backward(self, enable):
+        pass
+
+    def set_graph_sparse(self, adjacency_lists, indeg):
+        self.adj, self.indeg = adjacency_lists, indeg
+
+    def set_graph_dense(self, adjacency_matrix):
+        self.adjm = np.asarray(adjacency_matrix)
+
+    def set_state_dropout(self, keep, seed=0):
+        self.drop = (keep, seed) if keep < 1.0 else None
+
+
+class StandInPropagation:
+    @staticmethod
+    def apply(engine, layout, h0, *flat):
+        weights = [{k: flat[i] for k, i in lay.items()} for lay in layout]
+        if hasattr(engine, "adjm"):      # dense plug-in: one layer, [b*v, D] states
+            b, _, v, _ = engine.adjm.shape
+            w = dict(weights[0])
+            p = {"num_timesteps": engine.params["layer_timesteps"][0], "use_edge_bias": "edge_biases" in w}
+            return O.dense_propagation_torch(h0.reshape(b, v, engine.D), engine.adjm, w, p).reshape(b * v, engine.D)
+        if engine.params.get("graph_rnn_cell", "GRU").lower() == "rnn":
+            weights = [{{"cand_kernel": "rnn_kernel", "cand_bias": "rnn_bias"}.get(k, k): v for k, v in w.items()} for w in weights]
+        return O.sparse_propagation_torch(h0, engine.adj, engine.indeg, weights, engine.params, state_dropout=engine.drop)
+
+
+@pytest.fixture
+def stand_in(monkeypatch):
+    monkeypatch.setattr(chem_sparse, "PropagationEngine", StandInEngine)
+    monkeypatch.setattr(chem_sparse, "_propagation_function", lambda: StandInPropagation)
+    monkeypatch.setattr(chem_dense, "PropagationEngine", StandInEngine)
+    monkeypatch.setattr(chem_dense, "_propagation_function", lambda: StandInPropagation)
+
+
+def _args(tmp_path, mols, **cfg):
+    base = {"hidden_size": 16, "batch_size": 300, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]},
+            "edge_weight_dropout_keep_prob": 0.9, "graph_state_dropout_keep_prob": 0.9, "learning_rate": 0.01, "num_epochs": 2,
+            "use_edge_bias": True}
+    base.update(cfg)
+    return {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:48], "--valid_data": mols[48:], "--config": base}
+
+
+@pytest.mark.parametrize("cfg", [{}, {"use_propagation_attention": True}, {"graph_rnn_cell": "RNN", "graph_rnn_activation": "ReLU"}])
+def test_sparse_model_trains_saves_and_restores_on_the_host(tmp_path, stand_in, cfg):
+    mols = synthetic.make_molecules(64, seed=1)
+    m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, **cfg))
+    l0 = m.run_epoch("valid0", m.valid_data, False)[0]
+    for ep in range(5):
+        train_loss, accs, errs, speed, steps = m.run_epoch("train%d" % ep, m.train_data, True)
+        assert steps >= 3 and np.isfinite(train_loss)          # 48 molecules at <300 nodes per batch: several minibatches per epoch
+    l1 = m.run_epoch("valid1", m.valid_data, False)[0]
+    assert np.isfinite(l1) and l1 < l0
+    path = str(tmp_path / "ckpt.pickle")
+    m.save_progress(path, 3, 1)
+    saved = pickle.load(open(path, "rb"))["weights"]
+    assert "graph_model/gnn_layer_0/gnn_edge_weights_0:0" in saved and "out_layer_task0/regression/MLP_W_layer0:0" in saved
+    assert "beta1_power:0" in saved and any(k.endswith("/Adam_1:0") for k in saved)
+    m2 = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, **cfg))
+    assert m2.restore_progress(path) == (3, 1)
+    for (n, a), (_, b) in zip(m.trainable_variables(), m2.trainable_variables()):
+        np.testing.assert_array_equal(a.detach().numpy(), b.detach().numpy(), err_msg=n)
+    assert abs(m2.run_epoch("valid2", m2.valid_data, False)[0] - l1) < 1e-5 * max(1.0, abs(l1))
+    m.train()                                                   # the epoch loop with early stopping and best-model checkpointing
+    assert pickle.load(open(m.best_model_file, "rb"))["params"]["hidden_size"] == 16
+
+
+def test_dense_model_trains_on_the_host(tmp_path, stand_in):
+    mols = synthetic.make_molecules(64, seed=2)
+    args = {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:48], "--valid_data": mols[48:],
+            "--config": {"hidden_size": 16, "batch_size": 4, "num_timesteps": 2, "learning_rate": 0.01, "num_epochs": 1}}
+    m = chem_dense.DenseGGNNChemModel(args)
+    l0 = m.run_epoch("valid0", m.valid_data, False)[0]
+    for ep in range(4):
+        m.run_epoch("train%d" % ep, m.train_data, True)
+    l1 = m.run_epoch("valid1", m.valid_data, False)[0]
+    assert np.isfinite(l1) and l1 < l0
+    assert "graph_model/gru_scope/gru_cell/gates/kernel:0" in dict(m.trainable_variables())
+
+
+def test_the_real_engine_still_refuses_the_cpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(Exception, match="CUDA"):
+        chem_sparse.SparseGGNNChemModel(_args(tmp_path, synthetic.make_molecules(64, seed=1)))
