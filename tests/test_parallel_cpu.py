@@ -63,3 +63,61 @@ def test_single_allreduce_is_weighted_mean_of_rank_gradients():
         for r in range(2):
             np.testing.assert_allclose(res[r][i], want.numpy(), rtol=1e-6, atol=1e-7)
     assert res[0][2] is None and res[1][2] is None          # parameters without a gradient are left alone
+
+
+def _dp_worker(rank, world, port, tmp, out_q):
+    """tools/dp_check.py on the CPU: the ChemModel mirror (stand-in engine answering from the oracle, see test_chem_model_cpu.py)
+    on this rank's shard of graphs, ONE all-reduce, compared with the union batch computed locally."""
+    import torch
+    import torch.distributed as dist
+    from gated_graph_neural_network_samples_b200 import chem_sparse, synthetic
+    from tests.test_chem_model_cpu import StandInEngine, StandInPropagation
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    chem_sparse.PropagationEngine = StandInEngine
+    chem_sparse._propagation_function = lambda: StandInPropagation
+    mols = synthetic.make_molecules(40, seed=11)
+    args = {"--log_dir": os.path.join(tmp, "r%d" % rank), "--device": "cpu", "--train_data": mols, "--valid_data": mols[:4],
+            "--config": {"hidden_size": 12, "batch_size": 100000, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]},
+                         "edge_weight_dropout_keep_prob": 1.0, "random_seed": 3}}
+    model = chem_sparse.SparseGGNNChemModel(args)            # same seed on every rank -> identical replicas
+
+    def grads_of(graphs):
+        proc = model.process_raw_graphs(graphs, is_training_data=False)
+        batch = next(iter(model.make_minibatch_iterator(proc, is_training=False)))
+        batch["out_layer_dropout_keep_prob"] = 1.0
+        for _, v in model._train_vars:
+            v.grad = None
+        loss, _ = model.forward_batch(batch)
+        loss.backward()
+        return batch["num_graphs"]
+
+    n_r = grads_of(parallel.shard_graphs(mols, rank, world))
+    parallel.allreduce_gradients([v for _, v in model._train_vars], weight=float(n_r))
+    got = [None if v.grad is None else v.grad.clone() for _, v in model._train_vars]
+    grads_of(mols)                                            # the union batch on one rank
+    worst = 0.0
+    for (_, v), g in zip(model._train_vars, got):
+        if v.grad is not None:
+            worst = max(worst, float((g - v.grad).abs().max()) / (float(v.grad.abs().max()) + 1e-12))
+    out_q.put((rank, n_r, worst))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_equals_the_union_batch(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert sum(n for _, n, _ in res) == 40 and all(n > 0 for _, n, _ in res)      # every graph on exactly one rank
+    for rank, _, worst in res:
+        assert worst < 1e-4, (rank, worst)
