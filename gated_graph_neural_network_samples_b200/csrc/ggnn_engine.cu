@@ -589,6 +589,46 @@ static int reserve_states(ggnn_engine* e) {
     return GGNN_OK;
 }
 
+// Stable counting sort of the messages by (target, type): counts[k + 1] holds the number of messages of row k = target*T + type on
+// entry (it is reused as the write cursors).  Messages are visited in the reference's order (type-major, then list order,
+// sparse:124-129), so within a row they stay in message order -- this IS NumPy's stable argsort by target.
+static void fill_target_csr(int V, int T, const int32_t* const* adj, const int32_t* num_edges, std::vector<int>& counts, int* row_ptr,
+                            int* csr_src, int* csr_msg) {
+    row_ptr[0] = 0;
+    for (size_t k = 1; k <= (size_t)V * T; ++k) row_ptr[k] = row_ptr[k - 1] + counts[k];
+    std::vector<int>& pos = counts;
+    for (size_t k = 0; k < (size_t)V * T; ++k) pos[k] = row_ptr[k];
+    int m = 0;
+    for (int t = 0; t < T; ++t) {
+        const int32_t* a = adj[t];
+        for (int i = 0; i < num_edges[t]; ++i, ++m) {
+            const int slot = pos[(size_t)a[2 * i + 1] * T + t]++;
+            csr_src[slot] = a[2 * i];
+            csr_msg[slot] = m;
+        }
+    }
+}
+
+// The same CSR build without an engine or a GPU (host arithmetic only): lets the CPU test-suite pin the integer path bit for bit.
+int ggnn_host_target_csr(int32_t V, int32_t T, const int32_t* const* adj, const int32_t* num_edges, int32_t* row_ptr, int32_t* src,
+                         int32_t* msg) {
+    if (V < 0 || T <= 0 || !adj || !num_edges || !row_ptr) return GGNN_EINVAL;
+    std::vector<int> counts((size_t)V * T + 1, 0);
+    int64_t M = 0;
+    for (int t = 0; t < T; ++t) {
+        if (num_edges[t] < 0 || (num_edges[t] > 0 && !adj[t])) return GGNN_EINVAL;
+        M += num_edges[t];
+        for (int i = 0; i < num_edges[t]; ++i) {
+            const int s = adj[t][2 * i], d = adj[t][2 * i + 1];
+            if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) return GGNN_ERANGE;
+            ++counts[(size_t)d * T + t + 1];
+        }
+    }
+    if (M > 0 && (!src || !msg)) return GGNN_EINVAL;
+    fill_target_csr(V, T, adj, num_edges, counts, row_ptr, src, msg);
+    return GGNN_OK;
+}
+
 int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
                           const float* indeg, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
@@ -663,21 +703,7 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     unsigned* h_mask = (unsigned*)(base + e->off_mask);
 
     // ---- pass 2: exclusive scan + stable fill (iteration in message order keeps the reference's order per row)
-    row_ptr[0] = 0;
-    for (size_t k = 1; k <= (size_t)V * T; ++k) row_ptr[k] = row_ptr[k - 1] + counts[k];
-    {
-        std::vector<int>& pos = counts;  // reuse as write cursors
-        for (size_t k = 0; k < (size_t)V * T; ++k) pos[k] = row_ptr[k];
-        int m = 0;
-        for (int t = 0; t < T; ++t) {
-            const int32_t* a = adj[t];
-            for (int i = 0; i < num_edges[t]; ++i, ++m) {
-                const int slot = pos[(size_t)a[2 * i + 1] * T + t]++;
-                csr_src[slot] = a[2 * i];
-                csr_msg[slot] = m;
-            }
-        }
-    }
+    fill_target_csr(V, T, adj, num_edges, counts, row_ptr, csr_src, csr_msg);
     if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
         int* trow = (int*)(base + e->off_trow);
         int* ttgt = (int*)(base + e->off_ttgt);

@@ -161,6 +161,12 @@ int ggnn_set_save_for_backward(ggnn_engine* e, int32_t enable);
 int ggnn_backward(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* grads, int32_t num_layers,
                   float* d_h0, ggnn_stream_t stream);
 
+/* The CSR build of ggnn_set_graph_sparse on its own -- host arithmetic only, no engine, no GPU: row_ptr [V*T+1], src [M], msg [M]
+ * (msg = position of the slot's message in the reference's type-major message order, sparse:124-129).  Returns GGNN_ERANGE for an
+ * out-of-range edge.  Used by the CPU test-suite to pin the integer path against NumPy's stable sort. */
+int ggnn_host_target_csr(int32_t num_nodes, int32_t num_edge_types, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                         int32_t* row_ptr, int32_t* src, int32_t* msg);
+
 /* Introspection used by the parity tests and the benchmark. */
 int ggnn_num_messages(const ggnn_engine* e, int64_t* out);
 /* Copies the engine's device CSR back: row_ptr [V*T+1] (rows keyed target*T+type), src [M], msg [M]. */

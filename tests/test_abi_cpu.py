@@ -66,3 +66,44 @@ def test_state_dropout_mask_host_restatement_matches_oracle():
         np.testing.assert_array_equal(m.astype(bool), O.state_dropout_mask(seed, step, V, D, keep))
         if V * D > 1000:
             assert abs(m.mean() - keep) < 0.03
+
+
+def test_host_csr_build_is_numpys_stable_sort_bit_for_bit():
+    """Integer path without a GPU: ggnn_host_target_csr (the CSR fill ggnn_set_graph_sparse uses) == NumPy's stable argsort of the
+    type-major message list by target -- row offsets, sources and original message ids; empty edge types, isolated nodes,
+    multi-edges, self-loops, an empty batch; an out-of-range edge is refused like TF's CPU gather does."""
+    import ctypes as C
+    from gated_graph_neural_network_samples_b200 import _lib, packing, synthetic
+    from oracle import ggnn_oracle as O
+    lib = _lib.load()
+
+    def host_csr(adjs, V):
+        T = len(adjs)
+        adjs = [np.ascontiguousarray(np.asarray(a, np.int32).reshape(-1, 2)) for a in adjs]
+        M = sum(a.shape[0] for a in adjs)
+        ptrs = (C.c_void_p * T)(*[a.ctypes.data for a in adjs])
+        counts = (C.c_int32 * T)(*[a.shape[0] for a in adjs])
+        row_ptr, src, msg = np.empty(V * T + 1, np.int32), np.empty(max(M, 1), np.int32), np.empty(max(M, 1), np.int32)
+        rc = lib.ggnn_host_target_csr(V, T, ptrs, counts, row_ptr.ctypes.data, src.ctypes.data, msg.ctypes.data)
+        return rc, row_ptr, src[:M], msg[:M]
+
+    cases = []
+    for seed, n, T in [(13, 50, 4), (2, 7, 8), (5, 300, 4)]:
+        mols = synthetic.make_molecules(n, seed=seed, num_bond_types=T)
+        b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), 8, T)
+        cases.append((b["adjacency_lists"], b["initial_node_representation"].shape[0]))
+    cases.append(([np.array([[0, 1], [0, 1], [2, 2], [4, 1]], np.int32), np.zeros((0, 2), np.int32), np.array([[1, 0]], np.int32)], 6))
+    cases.append(([np.zeros((0, 2), np.int32)], 0))
+    for adjs, V in cases:
+        T = len(adjs)
+        rc, row_ptr, src, msg = host_csr(adjs, V)
+        assert rc == 0
+        ref_ptr, ref_src, ref_typ, ref_order = O.stable_target_csr(adjs, V)
+        np.testing.assert_array_equal(row_ptr[::T], ref_ptr)
+        np.testing.assert_array_equal(src, ref_src)
+        np.testing.assert_array_equal(msg, ref_order)
+        # rows are keyed target*T + type: the per-row type of every slot follows from row_ptr
+        typ = np.repeat(np.tile(np.arange(T, dtype=np.int32), V), np.diff(row_ptr))
+        np.testing.assert_array_equal(typ, ref_typ)
+    rc, *_ = host_csr([np.array([[0, 3]], np.int32)], 3)
+    assert rc == -5                                            # GGNN_ERANGE
