@@ -20,12 +20,20 @@ SURVEY.md section 8c):
     BasicRNNCell:  h'    = act([x, h] . K + b)
     DropoutWrapper(state_keep_prob=1.0): identity on the new state.
 
-PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, golden vectors or fixtures, and
-TensorFlow 1.3 cannot run here, so this oracle is pinned only by (1) its own float64 loop-level
-statement vs. its vectorised fp32 statements, (2) the sparse == dense cross-implementation identity the
-reference's two model files imply, (3) hand-derived closed-form tiny graphs, and (4) batches produced
-by the reference's *own* NumPy packing code (tests/golden/make_golden.py imports it with TF stubbed), and (5) an independent
-plain-C restatement (oracle/ggnn_oracle.c, message by message in double precision, no shared code) that must agree to 1e-12.
+PARITY: the reference ships no tests, golden vectors or fixtures and TensorFlow 1.3 cannot run here, so the reference itself pins
+nothing ("parity unpinned" in the strict sense).  What pins this oracle instead:
+(1) fixtures computed by the reference's OWN graph-building code: ``prepare_specific_graph_model`` /
+    ``compute_final_node_representations`` / ``gated_regression`` of both model files are imported unmodified and evaluated in float64
+    over a NumPy stand-in for the ``tf.*`` calls they make (tests/golden/tf_shim.py, generator make_reference_graph_golden.py, batches
+    from the reference's own packers); every statement of this oracle reproduces them to 1e-12 (tests/test_oracle.py).  That fixes
+    the dataflow -- gather/matmul/concat/segment-sum order, bias and mean, residual selection, the attention softmax, the readout --
+    to the reference's code.  NOT covered: the arithmetic inside TensorFlow's own ops (GRUCell / BasicRNNCell, see above), restated
+    from the 1.3 release in both places;
+(2) its own float64 loop-level statement vs. its vectorised fp32 statements, and an independent plain-C restatement
+    (oracle/ggnn_oracle.c, message by message in double precision, no shared code) that must agree to 1e-12;
+(3) the sparse == dense cross-implementation identity the reference's two model files imply;
+(4) hand-derived closed-form tiny graphs;
+(5) batches produced by the reference's *own* NumPy packing code (tests/golden/make_golden.py).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import this
 module.  The product path (``gated_graph_neural_network_samples_b200``) never does.

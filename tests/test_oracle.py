@@ -196,3 +196,43 @@ def test_propagation_attention_three_statements_agree():
     mean = O.sparse_propagation_np(h_same, args[1], args[2], w1, dict(p1, use_propagation_attention=False, use_edge_msg_avg_aggregation=True),
                                    dtype=np.float64)
     np.testing.assert_allclose(att, mean, rtol=1e-6, atol=1e-7)
+
+
+REFGRAPH_SPARSE = ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg"]
+
+
+def _load_refgraph_sparse(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "refgraph_sparse_%s.npz" % name))
+    p = json.loads(str(z["params_json"]))
+    w = [{k[len("w%d_" % l):]: z[k] for k in z.files if k.startswith("w%d_" % l)} for l in range(len(p["layer_timesteps"]))]
+    return z, p, w, [z["adj%d" % e] for e in range(4)]
+
+
+@pytest.mark.parametrize("name", REFGRAPH_SPARSE)
+def test_oracle_reproduces_the_reference_graph_code_sparse(golden_dir, name):
+    """refgraph_*.npz were computed by the reference's OWN prepare_specific_graph_model / compute_final_node_representations /
+    gated_regression (imported unmodified, tf.* served by tests/golden/tf_shim.py in float64, batch from the reference's own packer):
+    all three statements of the oracle and its readout reproduce them to rounding."""
+    import torch
+    z, p, w, adj = _load_refgraph_sparse(golden_dir, name)
+    for got in (O.sparse_propagation_loops(z["h0"], adj, z["indeg"], w, p),
+                O.sparse_propagation_np(z["h0"], adj, z["indeg"], w, p, dtype=np.float64),
+                O.sparse_propagation_torch(z["h0"], adj, z["indeg"], w, p, dtype=torch.float64).numpy(),
+                CO.sparse_propagation_c(z["h0"], adj, z["indeg"], w, p)):
+        np.testing.assert_allclose(got, z["final"], rtol=1e-11, atol=1e-12)
+    ro = O.gated_regression_torch(z["final"], z["h0"], z["ro_w_gate"], z["ro_b_gate"], z["ro_w_trans"], z["ro_b_trans"],
+                                  graph_nodes_list=z["graph_nodes_list"], num_graphs=int(z["num_graphs"]), dtype=torch.float64).numpy()
+    np.testing.assert_allclose(ro, z["readout"], rtol=1e-11, atol=1e-12)
+
+
+def test_oracle_reproduces_the_reference_graph_code_dense(golden_dir):
+    import torch
+    z = np.load(os.path.join(golden_dir, "refgraph_dense.npz"))
+    p = json.loads(str(z["params_json"]))
+    w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
+    for got in (O.dense_propagation_loops(z["h0"], z["adj"], w, p), O.dense_propagation_torch(z["h0"], z["adj"], w, p, dtype=torch.float64).numpy(),
+                CO.dense_propagation_c(z["h0"], z["adj"], w, p)):
+        np.testing.assert_allclose(got, z["final"], rtol=1e-11, atol=1e-12)
+    ro = O.gated_regression_torch(z["final"], z["h0"], z["ro_w_gate"], z["ro_b_gate"], z["ro_w_trans"], z["ro_b_trans"],
+                                  node_mask=z["node_mask"], dtype=torch.float64).numpy()
+    np.testing.assert_allclose(ro, z["readout"], rtol=1e-11, atol=1e-12)
