@@ -41,70 +41,68 @@ class ChemModel(object):
         import torch
         self.args = args
         self.data_dir = args.get('--data_dir') or ''
-        self.run_id = "_".join([time.strftime("%Y-%m-%d-%H-%M-%S"), str(os.getpid())])
-        log_dir = args.get('--log_dir') or '.'
-        os.makedirs(log_dir, exist_ok=True)
-        self.log_file = os.path.join(log_dir, "%s_log.json" % self.run_id)
-        self.best_model_file = os.path.join(log_dir, "%s_model_best.pickle" % self.run_id)
-
-        params = self.default_params()                                   # chem_tensorflow.py:57-65
-        config_file = args.get('--config-file')
-        if config_file is not None:
-            with open(config_file, 'r') as f:
-                params.update(json.load(f))
-        config = args.get('--config')
-        if config is not None:
-            params.update(json.loads(config) if isinstance(config, str) else dict(config))
-        self.params = params
-        random.seed(params['random_seed'])                               # chem_tensorflow.py:69-70
-        np.random.seed(params['random_seed'])
-        torch.manual_seed(params['random_seed'])                         # tf.set_random_seed, :85
+        # run id / log / best-model paths: the same "<timestamp>_<pid>" stem the reference uses (chem_tensorflow.py:43-52)
+        self.run_id = "%s_%d" % (time.strftime("%Y-%m-%d-%H-%M-%S"), os.getpid())
+        out_dir = args.get('--log_dir') or '.'
+        os.makedirs(out_dir, exist_ok=True)
+        self.log_file, self.best_model_file = (os.path.join(out_dir, self.run_id + tail) for tail in ("_log.json", "_model_best.pickle"))
+        self.params = self._resolve_params(args)
+        seed = self.params['random_seed']                                # chem_tensorflow.py:69-70,85: python, NumPy and the graph-level seed
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
         dev = args.get('--device')
         # the engine exists on CUDA only and refuses to be created elsewhere; "cpu" merely lets the host-side logic be unit-tested
         # against a stand-in engine (tests/test_chem_model_cpu.py)
         self.device = torch.device("cpu") if dev == "cpu" else torch.device("cuda", int(dev or 0))
         self.precision = args.get('--precision') or "fp32"
 
-        self.max_num_vertices = 0
-        self.num_edge_types = 0
-        self.annotation_size = 0
-        self.train_data = self.load_data(params['train_file'], is_training_data=True)
-        self.valid_data = self.load_data(params['valid_file'], is_training_data=False)
-
-        self.placeholders = {}
-        self.weights = {}
-        self.ops = {}
-        self.feed = None
+        self.max_num_vertices = self.num_edge_types = self.annotation_size = 0
+        self.train_data, self.valid_data = (self.load_data(self.params[k], is_training_data=t)
+                                            for k, t in (('train_file', True), ('valid_file', False)))
+        self.placeholders, self.weights, self.ops, self.feed = {}, {}, {}, None
         self.make_model()
         self.make_train_step()
-        restore_file = args.get('--restore')
-        if restore_file is not None:
-            self.train_step_id, self.valid_step_id = self.restore_progress(restore_file)
+        self.train_step_id = self.valid_step_id = 0
+        if args.get('--restore') is not None:
+            self.train_step_id, self.valid_step_id = self.restore_progress(args.get('--restore'))
         else:
             self.initialize_model()
-            self.train_step_id = 0
-            self.valid_step_id = 0
+
+    @classmethod
+    def _resolve_params(cls, args) -> dict:
+        """default_params(), overridden by --config-file (JSON file), then by --config (JSON string or dict): chem_tensorflow.py:57-65."""
+        params = cls.default_params()
+        if args.get('--config-file') is not None:
+            with open(args.get('--config-file')) as fh:
+                params.update(json.load(fh))
+        override = args.get('--config')
+        if override is not None:
+            params.update(json.loads(override) if isinstance(override, str) else dict(override))
+        return params
 
     # ------------------------------------------------------------------ data (chem_tensorflow.py:104-123)
     def load_data(self, file_name, is_training_data: bool):
-        preloaded = self.args.get('--train_data' if is_training_data else '--valid_data')
-        if preloaded is not None:
-            data = preloaded
-        else:
-            full_path = os.path.join(self.data_dir, file_name)
-            print("Loading data from %s" % full_path)
-            with open(full_path, 'r') as f:
-                data = json.load(f)
-        restrict = self.args.get("--restrict_data")
-        if restrict is not None and restrict > 0:
-            data = data[:restrict]
-        num_fwd_edge_types = 0
-        for g in data:
-            self.max_num_vertices = max(self.max_num_vertices, max([v for e in g['graph'] for v in [e[0], e[2]]]))
-            num_fwd_edge_types = max(num_fwd_edge_types, max([e[1] for e in g['graph']]))
-        self.num_edge_types = max(self.num_edge_types, num_fwd_edge_types * (1 if self.params['tie_fwd_bkwd'] else 2))
-        self.annotation_size = max(self.annotation_size, len(data[0]["node_features"][0]))
-        return self.process_raw_graphs(data, is_training_data)
+        graphs = self.args.get('--train_data' if is_training_data else '--valid_data')   # already-loaded molecule lists (tests, bench)
+        if graphs is None:
+            path = os.path.join(self.data_dir, file_name)
+            print("Loading data from %s" % path)
+            with open(path) as fh:
+                graphs = json.load(fh)
+        limit = self.args.get("--restrict_data")
+        if limit is not None and limit > 0:
+            graphs = graphs[:limit]
+        # dataset-wide shape facts the hooks need: largest node id, number of edge types (doubled when directions are untied), width
+        # of the node annotations (chem_tensorflow.py:114-121)
+        largest_id = largest_type = 0
+        for g in graphs:
+            edges = np.asarray(g['graph']).reshape(-1, 3)
+            largest_id = max(largest_id, int(edges[:, [0, 2]].max()))
+            largest_type = max(largest_type, int(edges[:, 1].max()))
+        self.max_num_vertices = max(self.max_num_vertices, largest_id)
+        self.num_edge_types = max(self.num_edge_types, largest_type * (1 if self.params['tie_fwd_bkwd'] else 2))
+        self.annotation_size = max(self.annotation_size, len(graphs[0]["node_features"][0]))
+        return self.process_raw_graphs(graphs, is_training_data)
 
     # ------------------------------------------------------------------ the five hooks (chem_tensorflow.py:130-131,202-212)
     def process_raw_graphs(self, raw_data: Sequence[Any], is_training_data: bool) -> Any:
@@ -210,66 +208,67 @@ class ChemModel(object):
         return torch.as_tensor(np.asarray(self.feed[self.placeholders['initial_node_representation']], dtype=np.float32), device=self.device)
 
     # ------------------------------------------------------------------ epoch loop (chem_tensorflow.py:214-253)
+    # per-task "chemical accuracy" thresholds of QM9 the reference reports error ratios against (chem_tensorflow.py:215-217)
+    CHEMICAL_ACCURACIES = np.array([0.066513725, 0.012235489, 0.071939046, 0.033730778, 0.033486113, 0.004278493, 0.001330901,
+                                    0.004165489, 0.004128926, 0.00409976, 0.004527465, 0.012292586, 0.037467458])
+
     def run_epoch(self, epoch_name: str, data, is_training: bool, start_step: int = 0):
+        """One pass over ``data``: returns (loss, per-task MAE, MAE / chemical accuracy, graphs per second, number of batches), the first
+        two averaged over graphs like the reference does (batch values weighted by the batch's graph count)."""
         import torch
-        chemical_accuracies = np.array([0.066513725, 0.012235489, 0.071939046, 0.033730778, 0.033486113, 0.004278493,
-                                        0.001330901, 0.004165489, 0.004128926, 0.00409976, 0.004527465, 0.012292586,
-                                        0.037467458])
-        loss, accuracies, processed_graphs, steps = 0.0, [], 0, 0
-        start_time = time.time()
-        batch_iterator = ThreadedIterator(self.make_minibatch_iterator(data, is_training), max_queue_size=5)
-        for step, batch_data in enumerate(batch_iterator):
-            num_graphs = batch_data[self.placeholders['num_graphs']]
-            processed_graphs += num_graphs
-            batch_data[self.placeholders['out_layer_dropout_keep_prob']] = self.params['out_layer_dropout_keep_prob'] if is_training else 1.0
+        t_begin = time.time()
+        graphs_seen, steps = 0, 0
+        loss_sum, acc_sum = 0.0, np.zeros(len(self.params['task_ids']))
+        batches = ThreadedIterator(self.make_minibatch_iterator(data, is_training), max_queue_size=5)   # packing overlaps the GPU work
+        for feed in batches:
+            n = feed[self.placeholders['num_graphs']]
+            feed[self.placeholders['out_layer_dropout_keep_prob']] = self.params['out_layer_dropout_keep_prob'] if is_training else 1.0
             if is_training:
-                batch_loss, batch_accs = self.forward_batch(batch_data)
+                batch_loss, batch_accs = self.forward_batch(feed)
                 self.train_step(batch_loss)
             else:
                 with torch.no_grad():
-                    batch_loss, batch_accs = self.forward_batch(batch_data)
-            loss += float(batch_loss.detach()) * num_graphs
-            accuracies.append(np.array([float(a.detach()) for a in batch_accs]) * num_graphs)
-            print("Running %s, batch %i (has %i graphs). Loss so far: %.4f" % (epoch_name, step, num_graphs, loss / processed_graphs), end='\r')
+                    batch_loss, batch_accs = self.forward_batch(feed)
+            graphs_seen += n
             steps += 1
-        accuracies = np.sum(accuracies, axis=0) / processed_graphs
-        loss = loss / processed_graphs
-        error_ratios = accuracies / chemical_accuracies[self.params["task_ids"]]
-        instance_per_sec = processed_graphs / (time.time() - start_time)
-        return loss, accuracies, error_ratios, instance_per_sec, steps
+            loss_sum += float(batch_loss.detach()) * n
+            acc_sum += np.array([float(a.detach()) for a in batch_accs]) * n
+            print("Running %s, batch %i (has %i graphs). Loss so far: %.4f" % (epoch_name, steps - 1, n, loss_sum / graphs_seen), end='\r')
+        accuracies = acc_sum / graphs_seen
+        return (loss_sum / graphs_seen, accuracies, accuracies / self.CHEMICAL_ACCURACIES[self.params["task_ids"]],
+                graphs_seen / (time.time() - t_begin), steps)
 
-    def train(self):  # chem_tensorflow.py:255-307
-        log_to_save = []
-        total_time_start = time.time()
+    def _report(self, tag: str, loss, accs, errs, speed):
+        per_task = lambda vals: " ".join("%i:%.5f" % (t, v) for t, v in zip(self.params['task_ids'], vals))
+        print("\r\x1b[K %s: loss: %.5f | acc: %s | error_ratio: %s | instances/sec: %.2f" % (tag, loss, per_task(accs), per_task(errs), speed))
+
+    def train(self):
+        """Epochs until ``num_epochs`` or until the summed validation MAE has not improved for ``patience`` epochs; the best model so far
+        is checkpointed and a JSON log is rewritten every epoch (chem_tensorflow.py:255-307)."""
+        history, t_begin = [], time.time()
+        best, best_epoch = float("+inf"), 0
         if self.args.get('--restore') is not None:
-            _, valid_accs, _, _, steps = self.run_epoch("Resumed (validation)", self.valid_data, False)
-            best_val_acc, best_val_acc_epoch = np.sum(valid_accs), 0
-            print("\r\x1b[KResumed operation, initial cum. val. acc: %.5f" % best_val_acc)
-        else:
-            best_val_acc, best_val_acc_epoch = float("+inf"), 0
+            best = float(np.sum(self.run_epoch("Resumed (validation)", self.valid_data, False)[1]))
+            print("\r\x1b[KResumed operation, initial cum. val. acc: %.5f" % best)
         for epoch in range(1, self.params['num_epochs'] + 1):
             print("== Epoch %i" % epoch)
-            train_loss, train_accs, train_errs, train_speed, train_steps = self.run_epoch("epoch %i (training)" % epoch, self.train_data, True, self.train_step_id)
-            self.train_step_id += train_steps
-            print("\r\x1b[K Train: loss: %.5f | acc: %s | error_ratio: %s | instances/sec: %.2f" % (
-                train_loss, " ".join("%i:%.5f" % x for x in zip(self.params['task_ids'], train_accs)),
-                " ".join("%i:%.5f" % x for x in zip(self.params['task_ids'], train_errs)), train_speed))
-            valid_loss, valid_accs, valid_errs, valid_speed, valid_steps = self.run_epoch("epoch %i (validation)" % epoch, self.valid_data, False, self.valid_step_id)
-            self.valid_step_id += valid_steps
-            print("\r\x1b[K Valid: loss: %.5f | acc: %s | error_ratio: %s | instances/sec: %.2f" % (
-                valid_loss, " ".join("%i:%.5f" % x for x in zip(self.params['task_ids'], valid_accs)),
-                " ".join("%i:%.5f" % x for x in zip(self.params['task_ids'], valid_errs)), valid_speed))
-            log_to_save.append({'epoch': epoch, 'time': time.time() - total_time_start,
-                                'train_results': (train_loss, train_accs.tolist(), train_errs.tolist(), train_speed),
-                                'valid_results': (valid_loss, valid_accs.tolist(), valid_errs.tolist(), valid_speed)})
-            with open(self.log_file, 'w') as f:
-                json.dump(log_to_save, f, indent=4)
-            val_acc = np.sum(valid_accs)
-            if val_acc < best_val_acc:
+            tr = self.run_epoch("epoch %i (training)" % epoch, self.train_data, True, self.train_step_id)
+            self.train_step_id += tr[4]
+            self._report("Train", *tr[:4])
+            va = self.run_epoch("epoch %i (validation)" % epoch, self.valid_data, False, self.valid_step_id)
+            self.valid_step_id += va[4]
+            self._report("Valid", *va[:4])
+            history.append({'epoch': epoch, 'time': time.time() - t_begin,
+                            'train_results': (tr[0], tr[1].tolist(), tr[2].tolist(), tr[3]),
+                            'valid_results': (va[0], va[1].tolist(), va[2].tolist(), va[3])})
+            with open(self.log_file, 'w') as fh:
+                json.dump(history, fh, indent=4)
+            score = float(np.sum(va[1]))
+            if score < best:
                 self.save_progress(self.best_model_file, self.train_step_id, self.valid_step_id)
-                print("  (Best epoch so far, cum. val. acc decreased to %.5f from %.5f. Saving to '%s')" % (val_acc, best_val_acc, self.best_model_file))
-                best_val_acc, best_val_acc_epoch = val_acc, epoch
-            elif epoch - best_val_acc_epoch >= self.params['patience']:
+                print("  (Best epoch so far, cum. val. acc decreased to %.5f from %.5f. Saving to '%s')" % (score, best, self.best_model_file))
+                best, best_epoch = score, epoch
+            elif epoch - best_epoch >= self.params['patience']:
                 print("Stopping training after %i epochs without improvement on validation accuracy." % self.params['patience'])
                 break
 
@@ -300,12 +299,13 @@ class ChemModel(object):
     def restore_progress(self, model_path: str):
         import torch
         print("Restoring weights from file %s." % model_path)
-        with open(model_path, 'rb') as in_file:
-            data_to_load = pickle.load(in_file)
-        assert len(self.params) == len(data_to_load['params'])
-        for par, par_value in self.params.items():
-            if par not in ['task_ids', 'num_epochs']:
-                assert par_value == data_to_load['params'][par]
+        with open(model_path, 'rb') as fh:
+            data_to_load = pickle.load(fh)
+        # same model configuration required, except for the task list and the epoch budget (chem_tensorflow.py:335-340)
+        theirs = data_to_load['params']
+        assert len(theirs) == len(self.params), "checkpoint was written with a different parameter set"
+        mismatched = [k for k, v in self.params.items() if k not in ('task_ids', 'num_epochs') and theirs[k] != v]
+        assert not mismatched, "checkpoint parameters differ: %s" % mismatched
         used = set()
         saved = data_to_load['weights']
         for n, v in self.trainable_variables():
