@@ -44,49 +44,47 @@ def import_reference():
     return ref_sparse, ref_dense, ref_utils
 
 
-def base_placeholders(m):
-    for k, dt in (("target_values", tf_shim.float32), ("target_mask", tf_shim.float32), ("num_graphs", tf_shim.int32),
-                  ("out_layer_dropout_keep_prob", tf_shim.float32)):
-        m.placeholders[k] = tf_shim.placeholder(dt, None, name=k)      # chem_tensorflow.py:134-139
+def build_model(m):
+    """The reference's make_model (chem_tensorflow.py:133-170), unmodified: placeholders, the two hooks inside variable_scope
+    "graph_model", the per-task readout MLPs, gated_regression, masked loss and accuracy."""
+    m.placeholders, m.weights, m.ops = {}, {}, {}
+    m.make_model()
+    gate, trans = m.weights["regression_gate_task0"], m.weights["regression_transform_task0"]
+    return {"w_gate": gate.params["weights"][0], "b_gate": gate.params["biases"][0],
+            "w_trans": trans.params["weights"][0], "b_trans": trans.params["biases"][0]}
 
 
-def readout(m, ref_utils, final, h):
-    np.random.seed(77)
-    gate = ref_utils.MLP(2 * h, 1, [], m.placeholders["out_layer_dropout_keep_prob"])     # chem_tensorflow.py:153-157
-    trans = ref_utils.MLP(h, 1, [], m.placeholders["out_layer_dropout_keep_prob"])
-    out = m.gated_regression(final, gate, trans)
-    w = {"w_gate": gate.params["weights"][0].value, "b_gate": gate.params["biases"][0].value,
-         "w_trans": trans.params["weights"][0].value, "b_trans": trans.params["biases"][0].value}
-    return out, w
+def evaluate_model(m, feed):
+    feed[m.placeholders["out_layer_dropout_keep_prob"]] = 1.0
+    final, loss, acc = tf_shim.evaluate([m.ops["final_node_representations"], m.ops["loss"], m.ops["accuracy_task0"]], feed)
+    ro = tf_shim.evaluate(m.output, feed)                         # gated_regression stores its result in self.output
+    return final, ro, float(loss), float(acc)
 
 
 def sparse_case(ref_sparse, ref_utils, name, cfg, mols):
     m = object.__new__(ref_sparse.SparseGGNNChemModel)
     m.params = {"task_ids": [0], "tie_fwd_bkwd": True, "task_sample_ratios": {}, "batch_size": 100000, "out_layer_dropout_keep_prob": 1.0,
-                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0, "use_propagation_attention": False}
+                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0, "use_propagation_attention": False, "use_graph": True}
     m.params.update(cfg)
     m.num_edge_types, m.annotation_size = 4, len(mols[0]["node_features"][0])
-    m.placeholders, m.weights = {}, {}
-    base_placeholders(m)
     np.random.seed(11)
     tf_shim.CELL_RNG.seed(4242)
-    m.prepare_specific_graph_model()                              # sparse:63-115, unmodified
+    ro_w = build_model(m)                                         # make_model -> sparse:63-115, 117-218, 220-231, unmodified
     L, T, D = len(cfg["layer_timesteps"]), 4, cfg["hidden_size"]
     rng = np.random.RandomState(5)
     for b in m.gnn_weights.edge_biases:                           # the reference initialises zeros / ones: perturb so the paths are exercised
         b.value = rng.uniform(-0.1, 0.1, b.value.shape)
     for a in m.gnn_weights.edge_type_attention_weights:
         a.value = 1.0 + 0.5 * rng.uniform(-1, 1, a.value.shape)
-    final = m.compute_final_node_representations()                # sparse:117-218, unmodified
-    ro, ro_w = readout(m, ref_utils, final, D)                    # sparse:220-231, unmodified
     data = m.process_raw_graphs(mols, is_training_data=False)     # sparse:234-252
     feed = next(iter(m.make_minibatch_iterator(data, is_training=False)))   # sparse:278-350: keyed by the placeholder objects
     h0 = np.asarray(feed[m.placeholders["initial_node_representation"]], dtype=np.float64)
     h0 = h0 * 1.5 + np.random.RandomState(3).normal(0, 0.3, h0.shape)      # every column live, attention scores of order 1
     feed[m.placeholders["initial_node_representation"]] = h0
-    feed[m.placeholders["out_layer_dropout_keep_prob"]] = 1.0
-    out_final, out_ro = tf_shim.evaluate([final, ro], feed)
-    out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0, "final": out_final, "readout": out_ro,
+    out_final, out_ro, loss, acc = evaluate_model(m, feed)
+    out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0, "final": out_final, "readout": out_ro, "loss": np.float64(loss),
+           "accuracy": np.float64(acc), "target_values": np.asarray(feed[m.placeholders["target_values"]], np.float64),
+           "target_mask": np.asarray(feed[m.placeholders["target_mask"]], np.float64),
            "indeg": np.asarray(feed[m.placeholders["num_incoming_edges_per_type"]], np.float64),
            "graph_nodes_list": np.asarray(feed[m.placeholders["graph_nodes_list"]], np.int32),
            "num_graphs": np.int64(feed[m.placeholders["num_graphs"]])}
@@ -101,41 +99,38 @@ def sparse_case(ref_sparse, ref_utils, name, cfg, mols):
         for k, v in (m.gnn_weights.rnn_cells[l].vars or {}).items():
             out["w%d_%s" % (l, k)] = v
     for k, v in ro_w.items():
-        out["ro_" + k] = v
+        out["ro_" + k] = v.value
     np.savez_compressed(os.path.join(HERE, "refgraph_sparse_%s.npz" % name), **out)
-    print(name, "V=%d final max %.3f readout[:3] %s" % (h0.shape[0], np.abs(out_final).max(), np.round(out_ro[:3], 4)))
+    print(name, "V=%d final max %.3f readout[:3] %s loss %.5f mae %.5f" % (h0.shape[0], np.abs(out_final).max(), np.round(out_ro[:3], 4), loss, acc))
 
 
 def dense_case(ref_dense, ref_utils, mols):
     cfg = {"hidden_size": 12, "num_timesteps": 3, "use_edge_bias": True}
     m = object.__new__(ref_dense.DenseGGNNChemModel)
     m.params = {"task_ids": [0], "tie_fwd_bkwd": True, "task_sample_ratios": {}, "batch_size": 4, "out_layer_dropout_keep_prob": 1.0,
-                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0}
+                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0, "use_graph": True}
     m.params.update(cfg)
     m.num_edge_types, m.annotation_size = 4, len(mols[0]["node_features"][0])
-    m.placeholders, m.weights = {}, {}
-    base_placeholders(m)
     np.random.seed(12)
     tf_shim.CELL_RNG.seed(777)
-    m.prepare_specific_graph_model()                              # dense:68-91
+    ro_w = build_model(m)                                         # make_model -> dense:68-91, 93-117, 119-129, unmodified
     m.weights["edge_biases"].value = np.random.RandomState(6).uniform(-0.1, 0.1, m.weights["edge_biases"].value.shape)
-    final = m.compute_final_node_representations()                # dense:93-117
-    ro, ro_w = readout(m, ref_utils, final, cfg["hidden_size"])   # dense:119-129
     data = m.process_raw_graphs(mols, is_training_data=False)     # dense:132-164 (buckets)
     feed = next(iter(m.make_minibatch_iterator(data, is_training=False)))
     h0 = np.asarray(feed[m.placeholders["initial_node_representation"]], dtype=np.float64)
     h0 = h0 + np.random.RandomState(4).normal(0, 0.1, h0.shape)
     feed[m.placeholders["initial_node_representation"]] = h0
-    feed[m.placeholders["out_layer_dropout_keep_prob"]] = 1.0
-    out_final, out_ro = tf_shim.evaluate([final, ro], feed)
-    out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0, "final": out_final, "readout": out_ro,
+    out_final, out_ro, loss, acc = evaluate_model(m, feed)
+    out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0, "final": out_final, "readout": out_ro, "loss": np.float64(loss),
+           "accuracy": np.float64(acc), "target_values": np.asarray(feed[m.placeholders["target_values"]], np.float64),
+           "target_mask": np.asarray(feed[m.placeholders["target_mask"]], np.float64),
            "adj": np.asarray(feed[m.placeholders["adjacency_matrix"]], np.float64),
            "node_mask": np.asarray(feed[m.placeholders["node_mask"]], np.float64),
            "w_edge_weights": m.weights["edge_weights"].value, "w_edge_biases": m.weights["edge_biases"].value}
     for k, v in m.weights["node_gru"].vars.items():
         out["w_" + k] = v
     for k, v in ro_w.items():
-        out["ro_" + k] = v
+        out["ro_" + k] = v.value
     np.savez_compressed(os.path.join(HERE, "refgraph_dense.npz"), **out)
     print("dense b,v =", h0.shape[:2], "final max %.3f readout[:3] %s" % (np.abs(out_final).max(), np.round(out_ro[:3], 4)))
 
@@ -143,6 +138,7 @@ def dense_case(ref_dense, ref_utils, mols):
 def main():
     ref_sparse, ref_dense, ref_utils = import_reference()
     mols = synthetic.make_molecules(12, seed=321)
+    mols[4]["targets"][0][0] = None                              # one unlabeled graph: the loss mask is exercised
     cases = {
         "true_default_shape": {"hidden_size": 12, "layer_timesteps": [2, 2, 1, 2, 1], "residual_connections": {"2": [0], "4": [0, 2]},
                                "use_edge_bias": False, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU",

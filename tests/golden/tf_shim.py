@@ -84,6 +84,8 @@ def concat(values, axis): return Node(lambda *vs: np.concatenate(vs, axis=axis),
 def matmul(a, b): return Node(np.matmul, a, b)
 def einsum(eq, *xs): return Node(lambda *vs: np.einsum(eq, *vs), *xs)
 def exp(x): return Node(np.exp, x)
+def abs(x): return Node(np.abs, x)          # noqa: A001 (mirrors tf.abs)
+def square(x): return Node(np.square, x)
 def expand_dims(x, axis): return Node(lambda v: np.expand_dims(v, axis), x)
 def squeeze(x): return Node(np.squeeze, x)
 def gather(params, indices): return Node(lambda p, i: p[i], params, indices)

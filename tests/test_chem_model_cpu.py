@@ -102,3 +102,47 @@ def test_the_real_engine_still_refuses_the_cpu(tmp_path):
         pytest.skip("CUDA present")
     with pytest.raises(Exception, match="CUDA"):
         chem_sparse.SparseGGNNChemModel(_args(tmp_path, synthetic.make_molecules(64, seed=1)))
+
+
+@pytest.mark.parametrize("name", ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg"])
+def test_forward_batch_loss_matches_the_reference_make_model(tmp_path, stand_in, name):
+    """refgraph_sparse_*.npz hold loss and MAE computed by the reference's OWN make_model (chem_tensorflow.py:133-170: hooks, readout
+    MLPs, gated_regression, masked loss), run unmodified over tests/golden/tf_shim.py.  With the fixture's weights loaded, the mirror's
+    forward_batch on the fixture's feed returns the same numbers (propagation answered by the stand-in engine = the oracle, fp32)."""
+    import json
+    import os
+    import torch
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "refgraph_sparse_%s.npz" % name))
+    cfg = json.loads(str(z["params_json"]))
+    mols = synthetic.make_molecules(8, seed=1)                    # only sets num_edge_types / annotation size; the feed comes from the fixture
+    args = {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:4], "--valid_data": mols[4:],
+            "--config": dict(cfg, batch_size=100000, edge_weight_dropout_keep_prob=1.0)}
+    m = chem_sparse.SparseGGNNChemModel(args)
+    T, D = 4, cfg["hidden_size"]
+    ren = {"rnn_kernel": "cand_kernel", "rnn_bias": "cand_bias"}
+    with torch.no_grad():
+        for l in range(len(cfg["layer_timesteps"])):
+            m.gnn_weights.edge_weights[l].copy_(torch.from_numpy(z["w%d_edge_weights" % l].reshape(T * D, D).astype(np.float32)))
+            if cfg["use_edge_bias"]:
+                m.gnn_weights.edge_biases[l].copy_(torch.from_numpy(z["w%d_edge_biases" % l].astype(np.float32)))
+            if cfg.get("use_propagation_attention"):
+                m.gnn_weights.edge_type_attention_weights[l].copy_(torch.from_numpy(z["w%d_edge_type_attention_weights" % l].astype(np.float32)))
+            for k in ("gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "rnn_kernel", "rnn_bias"):
+                if "w%d_%s" % (l, k) in z.files:
+                    m.gnn_weights.rnn_cells[l][ren.get(k, k)].copy_(torch.from_numpy(z["w%d_%s" % (l, k)].astype(np.float32)))
+        gate, trans = m.weights["regression_gate_task0"], m.weights["regression_transform_task0"]
+        gate.weights[0].copy_(torch.from_numpy(z["ro_w_gate"].astype(np.float32))); gate.biases[0].copy_(torch.from_numpy(z["ro_b_gate"].astype(np.float32)))
+        trans.weights[0].copy_(torch.from_numpy(z["ro_w_trans"].astype(np.float32))); trans.biases[0].copy_(torch.from_numpy(z["ro_b_trans"].astype(np.float32)))
+    feed = {"initial_node_representation": z["h0"].astype(np.float32), "num_incoming_edges_per_type": z["indeg"].astype(np.float32),
+            "graph_nodes_list": z["graph_nodes_list"], "num_graphs": int(z["num_graphs"]), "target_values": z["target_values"],
+            "target_mask": z["target_mask"], "graph_state_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0,
+            "out_layer_dropout_keep_prob": 1.0}
+    for e in range(T):
+        feed["adjacency_e%d" % e] = z["adj%d" % e]
+    assert float(z["target_mask"].sum()) == z["target_mask"].size - 1            # one unlabeled graph in the fixture batch
+    with torch.no_grad():
+        loss, accs = m.forward_batch(feed)
+    np.testing.assert_allclose(m.ops["final_node_representations"].numpy(), z["final"], rtol=1e-4, atol=1e-5 * float(np.abs(z["final"]).max()))
+    np.testing.assert_allclose(m.output.numpy(), z["readout"], rtol=1e-4, atol=1e-5 * float(np.abs(z["readout"]).max()))
+    assert abs(float(loss) - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    assert abs(float(accs[0]) - float(z["accuracy"])) < 1e-4 * abs(float(z["accuracy"]))
