@@ -9,8 +9,11 @@ Default workload = BASELINE.json configs[1] ("cfg2": sparse GGNN, hidden=100, 4 
 
 * ``value``      : node-state updates / s with graph + states + weights already resident in HBM, timed with
                    CUDA events around every step (L2 flushed before each step, flush not timed), max over ranks.
-* ``e2e``        : the same metric through the public host-buffer API (``set_graph_sparse`` + ``forward_host``):
-                   graph arrays and node states start in (pinned) HOST memory every step, result read back.
+* ``e2e``        : the same metric through the public one-call host-buffer API (``run_sparse_host`` / ``run_dense_host``):
+                   graph arrays and node states start in (pinned) HOST memory every step, result read back, serial.
+* ``e2e_pipelined``: the same calls with two batches in flight (two engines, two streams) -- reported beside ``e2e``, not instead.
+* ``train_propagation``: forward with saved states + backward of the propagation, device-resident (SURVEY 8d secondary metric).
+* ``readout``    : the fused gated-regression readout against the same op sequence as torch kernels.
 * ``roofline``   : algorithmic bytes of the dominant kernel / its CUDA-event duration vs the measured HBM peak.
 * ``cpu_baseline``: the fp32 PyTorch-CPU restatement of the TF1 graph (oracle/; TF 1.3 is not installable)
                    on this box's host cores, bounded sample.
