@@ -16,7 +16,13 @@ def glorot_init(shape):
 
 
 class ThreadedIterator:
-    """utils.py:16-36: one producer thread fills a bounded queue; ``None`` is the end sentinel."""
+    """utils.py:16-36: one producer thread fills a bounded queue; ``None`` is the end sentinel.  Unlike the reference, an
+    exception in the producer (e.g. a graph that does not fit the node budget) is handed to the consumer and re-raised there
+    instead of leaving it blocked on the queue forever."""
+
+    class _Failure:
+        def __init__(self, exc):
+            self.exc = exc
 
     def __init__(self, original_iterator, max_queue_size: int = 2):
         self._queue = queue.Queue(maxsize=max_queue_size)
@@ -24,14 +30,21 @@ class ThreadedIterator:
         self._thread.start()
 
     def _worker(self, it):
-        for element in it:
-            assert element is not None, "By convention, iterator elements must not be None"
-            self._queue.put(element, block=True)
+        try:
+            for element in it:
+                assert element is not None, "By convention, iterator elements must not be None"
+                self._queue.put(element, block=True)
+        except BaseException as exc:   # noqa: BLE001 -- delivered to the consumer
+            self._queue.put(self._Failure(exc), block=True)
+            return
         self._queue.put(None, block=True)
 
     def __iter__(self):
         item = self._queue.get(block=True)
         while item is not None:
+            if isinstance(item, self._Failure):
+                self._thread.join()
+                raise item.exc
             yield item
             item = self._queue.get(block=True)
         self._thread.join()

@@ -146,3 +146,26 @@ def test_forward_batch_loss_matches_the_reference_make_model(tmp_path, stand_in,
     np.testing.assert_allclose(m.output.numpy(), z["readout"], rtol=1e-4, atol=1e-5 * float(np.abs(z["readout"]).max()))
     assert abs(float(loss) - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
     assert abs(float(accs[0]) - float(z["accuracy"])) < 1e-4 * abs(float(z["accuracy"]))
+
+
+def test_threaded_iterator_delivers_items_and_re_raises_producer_errors():
+    from gated_graph_neural_network_samples_b200.utils import ThreadedIterator
+    assert list(ThreadedIterator(iter(range(7)), max_queue_size=2)) == list(range(7))
+
+    def failing():
+        yield 1
+        yield 2
+        raise ValueError("graph does not fit")
+
+    got = []
+    with pytest.raises(ValueError, match="does not fit"):
+        for x in ThreadedIterator(failing(), max_queue_size=5):
+            got.append(x)
+    assert got == [1, 2]
+
+
+def test_a_graph_larger_than_the_node_budget_raises_instead_of_hanging(tmp_path, stand_in):
+    mols = synthetic.make_molecules(64, seed=1)
+    m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, batch_size=5))   # every molecule has more than 5 nodes (sparse:297 loops forever)
+    with pytest.raises(Exception, match="does not fit"):
+        m.run_epoch("valid", m.valid_data, False)
