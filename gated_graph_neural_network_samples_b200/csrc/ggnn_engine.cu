@@ -609,6 +609,41 @@ static void fill_target_csr(int V, int T, const int32_t* const* adj, const int32
     }
 }
 
+// The tile plan ggnn_set_graph_sparse would make for this batch, without an engine or a GPU: the cut points (node boundaries no edge
+// crosses, from a difference array over the edge spans) and build_plan() on a scratch engine object that never touches CUDA.
+int ggnn_host_tile_plan(int32_t hidden_size, int32_t num_edge_types, int32_t precision, int32_t num_sms, int32_t V, const int32_t* const* adj,
+                        const int32_t* num_edges, int32_t* tile_start, int32_t tile_capacity, int32_t* num_tiles, char* plan_text,
+                        int32_t plan_text_capacity) {
+    if (hidden_size <= 0 || num_edge_types <= 0 || V < 0 || !adj || !num_edges || !tile_start || !num_tiles || num_sms <= 0) return GGNN_EINVAL;
+    std::vector<int> diff((size_t)V + 2, 0);
+    for (int t = 0; t < num_edge_types; ++t)
+        for (int i = 0; i < num_edges[t]; ++i) {
+            const int s = adj[t][2 * i], d = adj[t][2 * i + 1];
+            if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) return GGNN_ERANGE;
+            const int lo = std::min(s, d), hi = std::max(s, d);
+            if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
+        }
+    std::vector<int> cuts(1, 0);
+    int cover = 0;
+    for (int i = 1; i < V; ++i) {
+        cover += diff[i];
+        if (cover == 0) cuts.push_back(i);
+    }
+    if (V > 0) cuts.push_back(V);
+    ggnn_engine scratch;
+    scratch.D = hidden_size; scratch.T = num_edge_types; scratch.precision = precision; scratch.num_sms = num_sms;
+    scratch.max_smem = 227 * 1024; scratch.V = V;
+    if (precision != GGNN_PREC_FP32) scratch.DP = (hidden_size + 15) / 16 * 16;
+    std::vector<int> ts;
+    int rc = build_plan(&scratch, cuts, ts);
+    if (rc) return rc;
+    *num_tiles = scratch.ntiles;
+    if ((int)ts.size() > tile_capacity) return GGNN_EINVAL;
+    for (size_t i = 0; i < ts.size(); ++i) tile_start[i] = ts[i];
+    if (plan_text && plan_text_capacity > 0) snprintf(plan_text, (size_t)plan_text_capacity, "%s", scratch.plan_text.c_str());
+    return GGNN_OK;
+}
+
 // The same CSR build without an engine or a GPU (host arithmetic only): lets the CPU test-suite pin the integer path bit for bit.
 int ggnn_host_target_csr(int32_t V, int32_t T, const int32_t* const* adj, const int32_t* num_edges, int32_t* row_ptr, int32_t* src,
                          int32_t* msg) {

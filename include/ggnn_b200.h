@@ -167,6 +167,13 @@ int ggnn_backward(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* 
 int ggnn_host_target_csr(int32_t num_nodes, int32_t num_edge_types, const int32_t* const* adjacency_lists, const int32_t* num_edges,
                          int32_t* row_ptr, int32_t* src, int32_t* msg);
 
+/* The tile plan ggnn_set_graph_sparse would make for this batch on a GPU with `num_sms` SMs -- host arithmetic only: tile_start
+ * [num_tiles + 1] (first node of every tile; tile_capacity entries available) and the plan description.  Tiles are unions of whole
+ * connected components whenever the largest component fits a tile (LOCAL plan); used by the CPU test-suite. */
+int ggnn_host_tile_plan(int32_t hidden_size, int32_t num_edge_types, int32_t precision, int32_t num_sms, int32_t num_nodes,
+                        const int32_t* const* adjacency_lists, const int32_t* num_edges, int32_t* tile_start, int32_t tile_capacity,
+                        int32_t* num_tiles, char* plan_text, int32_t plan_text_capacity);
+
 /* Introspection used by the parity tests and the benchmark. */
 int ggnn_num_messages(const ggnn_engine* e, int64_t* out);
 /* Copies the engine's device CSR back: row_ptr [V*T+1] (rows keyed target*T+type), src [M], msg [M]. */

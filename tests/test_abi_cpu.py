@@ -107,3 +107,53 @@ def test_host_csr_build_is_numpys_stable_sort_bit_for_bit():
         np.testing.assert_array_equal(typ, ref_typ)
     rc, *_ = host_csr([np.array([[0, 3]], np.int32)], 3)
     assert rc == -5                                            # GGNN_ERANGE
+
+
+def test_host_tile_plan_keeps_components_whole_and_fills_the_sms():
+    """The tiling logic of ggnn_set_graph_sparse without a GPU (ggnn_host_tile_plan): tiles partition [0, V) in order, no edge crosses
+    a tile in a LOCAL plan, no tile exceeds its row budget, a batch that cannot fill the chip is cut into <= num_sms smaller tiles (and
+    <= 64-row tiles select the compact operand layout), a component larger than a tile switches to the GLOBAL plan."""
+    import ctypes as C
+    from gated_graph_neural_network_samples_b200 import _lib, packing, synthetic
+    lib = _lib.load()
+
+    def plan(adjs, V, D=100, precision=1, sms=148):
+        T = len(adjs)
+        adjs = [np.ascontiguousarray(np.asarray(a, np.int32).reshape(-1, 2)) for a in adjs]
+        ptrs = (C.c_void_p * T)(*[a.ctypes.data for a in adjs])
+        counts = (C.c_int32 * T)(*[a.shape[0] for a in adjs])
+        ts = np.empty(V + 2, np.int32)
+        n = C.c_int32()
+        text = C.create_string_buffer(512)
+        rc = lib.ggnn_host_tile_plan(D, T, precision, sms, V, ptrs, counts, ts.ctypes.data, V + 2, C.byref(n), text, 512)
+        assert rc == 0
+        return ts[:n.value + 1].copy(), text.value.decode()
+
+    def check_partition(ts, V, adjs, local):
+        assert ts[0] == 0 and ts[-1] == V and np.all(np.diff(ts) > 0)
+        if local:
+            tile_of = np.searchsorted(ts, np.arange(V), side="right") - 1
+            for a in adjs:
+                a = np.asarray(a).reshape(-1, 2)
+                assert np.array_equal(tile_of[a[:, 0]], tile_of[a[:, 1]])       # every edge stays inside one tile
+
+    for n_mols, expect_compact in [(256, True), (5500, False)]:
+        mols = synthetic.make_molecules(n_mols, seed=0)
+        b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), 8, 4)
+        V = b["initial_node_representation"].shape[0]
+        for precision in (1, 0):                                               # bf16x3 (tcgen05 plan), fp32 (FFMA plan)
+            ts, text = plan(b["adjacency_lists"], V, precision=precision)
+            assert "LOCAL" in text, text
+            check_partition(ts, V, b["adjacency_lists"], True)
+            budget = int(text.split("rows/tile<=")[1].split()[0])
+            assert np.max(np.diff(ts)) <= budget <= 128
+            if precision == 1:
+                assert ("compact" in text) == expect_compact, text
+                if expect_compact:
+                    assert len(ts) - 1 <= 148 and budget <= 64                 # cut small enough to use (almost) every SM
+    # one 300-node ring: larger than any tile -> one launch per step over 128-row tiles
+    ring = np.stack([np.arange(300), (np.arange(300) + 1) % 300], 1).astype(np.int32)
+    ts, text = plan([ring], 300)
+    assert "GLOBAL" in text and list(ts) == [0, 128, 256, 300]
+    ts, text = plan([np.zeros((0, 2), np.int32)], 0)
+    assert list(ts) == [0]
