@@ -1,0 +1,89 @@
+"""CPU property tests (hypothesis) of the integer/host paths: random multigraphs with self-loops, duplicate edges, empty edge types and
+isolated nodes through the CSR build the engine uses, the tile plan, and the flattened packer."""
+import ctypes as C
+
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from gated_graph_neural_network_samples_b200 import _lib, packing
+from oracle import ggnn_oracle as O
+
+
+@st.composite
+def multigraphs(draw):
+    V = draw(st.integers(1, 60))
+    T = draw(st.integers(1, 5))
+    adjs = []
+    for _ in range(T):
+        n = draw(st.integers(0, 80))
+        e = draw(st.lists(st.tuples(st.integers(0, V - 1), st.integers(0, V - 1)), min_size=n, max_size=n))
+        adjs.append(np.asarray(e, np.int32).reshape(-1, 2))
+    return V, adjs
+
+
+def _ptrs(adjs):
+    adjs = [np.ascontiguousarray(a) for a in adjs]
+    T = len(adjs)
+    return adjs, (C.c_void_p * T)(*[a.ctypes.data for a in adjs]), (C.c_int32 * T)(*[a.shape[0] for a in adjs])
+
+
+@settings(max_examples=150, deadline=None)
+@given(multigraphs())
+def test_host_csr_equals_numpy_stable_sort(g):
+    V, adjs = g
+    lib = _lib.load()
+    adjs, ptrs, counts = _ptrs(adjs)
+    T, M = len(adjs), sum(a.shape[0] for a in adjs)
+    row_ptr, src, msg = np.empty(V * T + 1, np.int32), np.empty(max(M, 1), np.int32), np.empty(max(M, 1), np.int32)
+    assert lib.ggnn_host_target_csr(V, T, ptrs, counts, row_ptr.ctypes.data, src.ctypes.data, msg.ctypes.data) == 0
+    ref_ptr, ref_src, ref_typ, ref_order = O.stable_target_csr(adjs, V)
+    assert np.array_equal(row_ptr[::T], ref_ptr) and np.array_equal(src[:M], ref_src) and np.array_equal(msg[:M], ref_order)
+    assert np.array_equal(np.repeat(np.tile(np.arange(T, dtype=np.int32), V), np.diff(row_ptr)), ref_typ)
+
+
+@settings(max_examples=100, deadline=None)
+@given(multigraphs(), st.sampled_from([0, 1]), st.sampled_from([8, 100, 128]))
+def test_tile_plan_is_a_partition_that_respects_components(g, precision, D):
+    V, adjs = g
+    lib = _lib.load()
+    adjs, ptrs, counts = _ptrs(adjs)
+    ts, n, text = np.empty(V + 2, np.int32), C.c_int32(), C.create_string_buffer(512)
+    assert lib.ggnn_host_tile_plan(D, len(adjs), precision, 148, V, ptrs, counts, ts.ctypes.data, V + 2, C.byref(n), text, 512) == 0
+    ts = ts[:n.value + 1]
+    assert ts[0] == 0 and ts[-1] == V and np.all(np.diff(ts) > 0)
+    plan = text.value.decode()
+    budget = int(plan.split("rows/tile<=")[1].split()[0])
+    assert np.max(np.diff(ts)) <= budget
+    if "LOCAL" in plan:
+        tile_of = np.searchsorted(ts, np.arange(V), side="right") - 1
+        for a in adjs:
+            assert np.array_equal(tile_of[a[:, 0]], tile_of[a[:, 1]])
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 25))
+def test_flat_packer_equals_per_graph_packer_on_random_subsets(seed, k):
+    from gated_graph_neural_network_samples_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    proc = test_flat_packer_equals_per_graph_packer_on_random_subsets.proc
+    flat = test_flat_packer_equals_per_graph_packer_on_random_subsets.flat
+    idx = rng.integers(0, len(proc), size=k)                 # with repetition: the same graph may appear twice in a batch
+    a = packing.pack_sparse_batch([proc[i] for i in idx], 16, 4)
+    b = flat.pack(idx, 16)
+    for key in a:
+        if key == "adjacency_lists":
+            assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a[key], b[key]))
+        elif key == "num_graphs":
+            assert a[key] == b[key]
+        else:
+            assert a[key].dtype == b[key].dtype and np.array_equal(a[key], b[key]), key
+
+
+def _init_flat():
+    from gated_graph_neural_network_samples_b200 import synthetic
+    proc = packing.process_raw_graphs_sparse(synthetic.make_molecules(60, seed=17))
+    test_flat_packer_equals_per_graph_packer_on_random_subsets.proc = proc
+    test_flat_packer_equals_per_graph_packer_on_random_subsets.flat = packing.FlatSparseGraphs(proc, 4)
+
+
+_init_flat()
