@@ -21,6 +21,7 @@
 #include "ggnn_readout.cuh"
 #include "ggnn_fwd_ffma.cuh"
 #include "ggnn_fwd_tc.cuh"
+#include "ggnn_fwd_stream.cuh"
 
 using namespace ggnn;
 
@@ -117,6 +118,12 @@ struct ggnn_engine {
     float* last_out = nullptr;
     bool save = false;
     bool saved_valid = false;
+    // streaming tensor-core plan (ggnn_fwd_stream.cuh): D > 128, or forced with GGNN_TC_STREAM=1
+    bool stream = false;
+    DevBuf ts_weights, ts_images, ts_u;
+    size_t ts_off_edge[MAX_LAYERS] = {0}, ts_off_gate[MAX_LAYERS] = {0}, ts_off_cand[MAX_LAYERS] = {0};
+    int ts_nc[2] = {0, 0}, ts_nblk[2] = {0, 0};      // [0]: DP-wide outputs (agg, candidate)  [1]: the 2*DP-wide gate output
+    int ts_tiled_nc[2] = {-1, -1};                   // the N-block widths the tiled weights were made for
     int tc_row_budget = 128, tc_kgs = 2048;   // tensor-core plan: no tile has more rows than the budget; <= 64 selects compact operand tiles
     int use_att = 0;                 // use_propagation_attention (sparse:170-196): fp32 path only
     DevBuf att_buf;                  // attention probabilities per target-CSR slot ([steps][M] when saving for backward, else [M])
@@ -197,7 +204,33 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
     int max_span = 0;
     for (size_t i = 1; i < cuts.size(); ++i) max_span = std::max(max_span, cuts[i] - cuts[i - 1]);
     e->max_span = max_span;
+    e->stream = false;
     if (e->precision != GGNN_PREC_FP32) {
+        const char* fs = getenv("GGNN_TC_STREAM");
+        if (e->DP > 128 || (fs && fs[0] == '1' && e->gather_mode == GATHER_SPARSE)) {
+            // streaming plan: fixed 128-row tiles (the gather reads the previous state from L2, so tiles need not respect components),
+            // one launch per GEMM of a timestep; N blocks sized so that small batches still spread over the chip
+            if (e->gather_mode != GATHER_SPARSE)
+                return e->fail(GGNN_EUNSUPPORTED, "hidden_size > 128 on the tensor-core path needs the CSR graph format (a weighted dense adjacency runs on GGNN_PREC_FP32)");
+            e->stream = true; e->variant = 3; e->nb1 = 0; e->local = false;
+            tile_start.clear(); tile_start.push_back(0);
+            for (int r = ts::TILE_M; r < V; r += ts::TILE_M) tile_start.push_back(r);
+            if (V > 0) tile_start.push_back(V);
+            e->ntiles = (int)tile_start.size() - 1;
+            for (int i = 0; i < 2; ++i) {
+                const int width = (i + 1) * e->DP;
+                int nblk = (width + 255) / 256;
+                // a tcgen05.mma costs the same for every N <= 128, so never go below 128 columns per CTA
+                while (e->ntiles * nblk <= e->num_sms / 2 && width / (nblk + 1) >= 128) ++nblk;
+                e->ts_nblk[i] = nblk;
+                e->ts_nc[i] = ((width + nblk - 1) / nblk + 15) / 16 * 16;
+            }
+            char buf[256];
+            snprintf(buf, sizeof buf, "tcgen05-%s STREAM(3 launches per step: gather-GEMM, gate GEMM, candidate GEMM) tiles=%d DP=%d N-blocks agg/cand=%dx%d gate=%dx%d max_component=%d",
+                     e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->ntiles, e->DP, e->ts_nblk[0], e->ts_nc[0], e->ts_nblk[1], e->ts_nc[1], max_span);
+            e->plan_text = buf;
+            return GGNN_OK;
+        }
         e->variant = 2;
         e->nb1 = 0;
         e->local = max_span <= tc::TILE_M;
@@ -490,10 +523,6 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     if (cfg->cell != GGNN_CELL_GRU && cfg->cell != GGNN_CELL_RNN) return bad("Unknown RNN cell type");              // sparse:112
     if (cfg->activation != GGNN_ACT_TANH && cfg->activation != GGNN_ACT_RELU) return bad("Unknown activation function type");  // sparse:81
     if (cfg->precision != GGNN_PREC_FP32 && cfg->precision != GGNN_PREC_BF16X3 && cfg->precision != GGNN_PREC_BF16) return bad("unknown precision");
-    if (cfg->precision != GGNN_PREC_FP32 && cfg->hidden_size > 128) {
-        g_create_error = "the tensor-core path (bf16x3/bf16) supports hidden_size <= 128 in this revision; use GGNN_PREC_FP32";
-        return GGNN_EUNSUPPORTED;
-    }
     ggnn_engine* e = new ggnn_engine();
     e->D = cfg->hidden_size; e->T = cfg->num_edge_types; e->L = cfg->num_layers;
     e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
@@ -546,7 +575,7 @@ int ggnn_destroy(ggnn_engine* e) {
     if (!e) return GGNN_OK;
     cudaSetDevice(e->device);
     e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
-    e->tc_weights.release(); e->tc_respre.release(); e->err_flag.release(); e->dbg_buf.release();
+    e->tc_weights.release(); e->tc_respre.release(); e->ts_weights.release(); e->ts_images.release(); e->ts_u.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
     if (e->stage_done) cudaEventDestroy(e->stage_done);
     if (e->ro_stage_done) cudaEventDestroy(e->ro_stage_done);
@@ -1078,6 +1107,162 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     return GGNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------ streaming tensor-core path (host)
+static int ts_prepare_weights(ggnn_engine* e, cudaStream_t st) {
+    const int D = e->D, DP = e->DP, T = e->T, NKS = DP / 16;
+    const int nc0 = e->ts_nc[0], nb0 = e->ts_nblk[0], nc1 = e->ts_nc[1], nb1 = e->ts_nblk[1];
+    size_t off = 0;
+    for (int l = 0; l < e->L; ++l) {
+        const int nseg = e->nres[l] + 2;
+        e->ts_off_edge[l] = off; off += (size_t)nb0 * T * NKS * 64 * nc0;
+        e->ts_off_gate[l] = off; off += (size_t)nb1 * nseg * NKS * 64 * nc1;
+        e->ts_off_cand[l] = off; off += (size_t)nb0 * nseg * NKS * 64 * nc0;
+    }
+    if (off > e->ts_weights.cap || e->ts_tiled_nc[0] != nc0 || e->ts_tiled_nc[1] != nc1) e->weights_dirty = true;
+    CU_TRY(e, e->ts_weights.reserve(off));
+    if (!e->weights_dirty) return GGNN_OK;
+    uint8_t* base = (uint8_t*)e->ts_weights.ptr;
+    for (int l = 0; l < e->L; ++l) {
+        const int nseg = e->nres[l] + 2;
+        auto launch = [&](const float* W, uint8_t* out, int segs, int ncolblk, int src_ld, int NC, int nblk) {
+            const long long total = (long long)nblk * segs * NKS * 2 * NC;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, 2048);
+            ts::ggnn_tile_weights_stream_kernel<<<blocks, 256, 0, st>>>(W, out, D, DP, segs, ncolblk, src_ld, NC, nblk);
+            ++e->last_launches;
+        };
+        launch(e->w[l].edge_weights, base + e->ts_off_edge[l], T, 1, D, nc0, nb0);
+        if (e->cell == CELL_GRU) launch(e->w[l].gate_kernel, base + e->ts_off_gate[l], nseg, 2, 2 * D, nc1, nb1);
+        launch(e->w[l].cand_kernel, base + e->ts_off_cand[l], nseg, 1, D, nc0, nb0);
+    }
+    CU_TRY(e, cudaGetLastError());
+    e->weights_dirty = false;
+    e->ts_tiled_nc[0] = nc0; e->ts_tiled_nc[1] = nc1;
+    return GGNN_OK;
+}
+
+static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStream_t st) {
+    const int D = e->D, DP = e->DP, T = e->T, L = e->L, V = e->V, NKS = DP / 16;
+    const int ntiles = e->ntiles;
+    int rc = ts_prepare_weights(e, st);
+    if (rc) return rc;
+    const size_t img_b = (size_t)ntiles * NKS * ts::A_STAGE_B;
+    const int n_img = L + 1 + 4;    // node_states_per_layer images, two step temporaries, agg, r*h
+    CU_TRY(e, e->ts_images.reserve(img_b * n_img));
+    uint8_t* ib = (uint8_t*)e->ts_images.ptr;
+    auto img_state = [&](int l) { return ib + (size_t)l * img_b; };
+    uint8_t* img_tmp[2] = {ib + (size_t)(L + 1) * img_b, ib + (size_t)(L + 2) * img_b};
+    uint8_t* img_agg = ib + (size_t)(L + 3) * img_b;
+    uint8_t* img_rh = ib + (size_t)(L + 4) * img_b;
+    const size_t vd = (size_t)std::max(V, 1) * D;
+    const size_t vd_bytes = (size_t)V * D * sizeof(float);
+    float* sb = (float*)e->state_buf.ptr;
+    std::vector<float*> state(L + 1);
+    state[0] = const_cast<float*>(h0);
+    for (int l = 1; l <= L; ++l) state[l] = (l == L) ? h_out : sb + (size_t)(l - 1) * vd;
+    float* tmp[2] = {sb + (size_t)(L - 1 > 0 ? L - 1 : 0) * vd, nullptr};
+    tmp[1] = tmp[0] + vd;
+    const bool gru = e->cell == CELL_GRU;
+    if (gru && !e->save) CU_TRY(e, e->ts_u.reserve(vd * sizeof(float)));
+    float* sv = (float*)e->save_bufs.ptr;
+    const size_t per = vd * (size_t)std::max(e->total_steps, 1);
+    char* g = (char*)e->graph_buf.ptr;
+
+    // shared-memory budgets
+    const size_t avail = (e->max_smem > 2048 ? e->max_smem - 2048 : 0);
+    const int csr_cap = std::min((e->max_tile_msgs + 3) / 4 * 4, 8192);
+    const size_t csr_b = (size_t)((ts::TILE_M * T + 1 + 3) & ~3) * 4 + (size_t)csr_cap * 4;
+    auto stages_for = [&](int NC, size_t budget) {
+        const size_t stage = (size_t)ts::A_STAGE_B + 64 * (size_t)NC;
+        return (int)std::min<size_t>(ts::MAX_NS, budget / stage);
+    };
+    ts::StreamParams base;
+    memset(&base, 0, sizeof base);
+    base.V = V; base.D = D; base.DP = DP; base.T = T;
+    base.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
+    base.cell = e->cell; base.act = e->act; base.use_bias = e->use_bias; base.use_avg = e->use_avg;
+    base.row_ptr = (const int*)(g + e->off_row_ptr); base.csr_src = (const int*)(g + e->off_src);
+    base.tile_mask = (const unsigned*)(g + e->off_mask);
+    base.indeg = (const float*)(g + e->off_indeg); base.denom = (const float*)(g + e->off_denom);
+    base.csr_cap = csr_cap;
+    base.drop_keep = e->drop_keep; base.drop_seed = e->drop_seed;
+    base.error_flag = (int*)e->err_flag.ptr;
+    auto tmem_cols = [](int NC) { int c = 32; while (c < NC) c *= 2; return c; };
+    const int nc0 = e->ts_nc[0], nb0 = e->ts_nblk[0], nc1 = e->ts_nc[1], nb1 = e->ts_nblk[1];
+    // edge kernel: one CTA per SM, deep ring; TMA-fed kernels: two CTAs per SM when the grid is larger than the chip
+    const int ns_edge = stages_for(nc0, avail > csr_b ? avail - csr_b : 0);
+    auto fed_budget = [&](int nblk) { return ((long long)ntiles * nblk > e->num_sms) ? (avail + 2048) / 2 - 2048 : avail; };
+    const int ns_gate = stages_for(nc1, fed_budget(nb1)), ns_cand = stages_for(nc0, fed_budget(nb0));
+    if (ns_edge < 2 || ns_gate < 2 || ns_cand < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the streaming ring (DP=%d)", DP);
+    auto smem_of = [&](int NC, int ns, bool gather) { return (size_t)1024 + (size_t)ns * (ts::A_STAGE_B + 64 * (size_t)NC) + (gather ? csr_b : 0); };
+    auto k_edge = ts::ggnn_stream_kernel<16, true>;
+    auto k_fed = ts::ggnn_stream_kernel<8, false>;
+    const size_t sm_edge = smem_of(nc0, ns_edge, true);
+    const size_t sm_fed = std::max(smem_of(nc1, ns_gate, false), smem_of(nc0, ns_cand, false));
+    CU_TRY(e, cudaFuncSetAttribute(k_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_edge));
+    CU_TRY(e, cudaFuncSetAttribute(k_fed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fed));
+
+    {   // node_states_per_layer[0] -> operand image
+        const long long total = (long long)ntiles * ts::TILE_M * (DP / 8);
+        ts::ggnn_image_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(h0, img_state(0), V, D, DP, ntiles);
+        ++e->last_launches;
+    }
+    const uint8_t* wb = (const uint8_t*)e->ts_weights.ptr;
+    for (int l = 0; l < L; ++l) {
+        const float* in = state[l];
+        const uint8_t* img_in = img_state(l);
+        if (e->steps[l] == 0) {   // a layer without timesteps aliases the previous state (sparse:152)
+            CU_TRY(e, cudaMemcpyAsync(state[l + 1], in, vd_bytes, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(e, cudaMemcpyAsync(img_state(l + 1), img_in, img_b, cudaMemcpyDeviceToDevice, st));
+            continue;
+        }
+        const int R = e->nres[l], nseg = R + 2;
+        for (int s = 0; s < e->steps[l]; ++s) {
+            const bool last = s == e->steps[l] - 1;
+            float* out = last ? state[l + 1] : tmp[s & 1];
+            uint8_t* img_out = last ? img_state(l + 1) : img_tmp[s & 1];
+            const int gs = e->step_base[l] + s;
+            const size_t so = (size_t)gs * vd;
+            float* u_buf = gru ? (e->save ? sv + 3 * per + so : (float*)e->ts_u.ptr) : nullptr;
+            // ---- aggregated messages
+            ts::StreamParams p = base;
+            p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.tmem_cols = tmem_cols(nc0);
+            p.g_src = in; p.w = wb + e->ts_off_edge[l]; p.kt_all = T * NKS;
+            p.bias = e->use_bias ? e->w[l].edge_biases : nullptr;
+            p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs;
+            k_edge<<<dim3(ntiles, nb0), 18 * 32, sm_edge, st>>>(p);
+            ++e->last_launches;
+            auto set_segs = [&](ts::StreamParams& q, const uint8_t* last_img) {
+                q.nseg = nseg;
+                for (int i = 0; i < R; ++i) q.seg[i] = img_state(e->res[l][i]);
+                q.seg[R] = img_agg; q.seg[R + 1] = last_img;
+                q.kt_all = nseg * NKS;
+            };
+            if (gru) {
+                ts::StreamParams q = base;
+                q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.tmem_cols = tmem_cols(nc1);
+                set_segs(q, img_in);
+                q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_in = in; q.u_buf = u_buf; q.img_out = img_rh;
+                if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; }
+                q.gstep = gs;
+                k_fed<<<dim3(ntiles, nb1), 10 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
+                ++e->last_launches;
+            }
+            ts::StreamParams c = base;
+            c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.tmem_cols = tmem_cols(nc0);
+            set_segs(c, gru ? img_rh : img_in);
+            c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_in = in; c.u_buf = u_buf; c.h_out = out; c.img_out = img_out;
+            if (e->save) { if (gru) c.sv_c = sv + 4 * per + so; else c.sv_h = sv + so; }
+            c.gstep = gs;
+            k_fed<<<dim3(ntiles, nb0), 10 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
+            ++e->last_launches;
+            in = out; img_in = img_out;
+        }
+    }
+    CU_TRY(e, cudaGetLastError());
+    if (e->save) { e->saved_valid = true; e->saved_drop_keep = e->drop_keep; e->saved_drop_seed = e->drop_seed; }
+    return GGNN_OK;
+}
+
 int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
     if (!e->weights_set) return e->fail(GGNN_ESTATE, "ggnn_set_weights has not been called");
@@ -1095,7 +1280,7 @@ int ggnn_forward(ggnn_engine* e, const float* h0, float* h_out, ggnn_stream_t st
         if (h_out != h0) CU_TRY(e, cudaMemcpyAsync(h_out, h0, vd_bytes, cudaMemcpyDeviceToDevice, st));
         return GGNN_OK;
     }
-    if (e->precision != GGNN_PREC_FP32) return forward_tc(e, h0, h_out, st);
+    if (e->precision != GGNN_PREC_FP32) return e->stream ? forward_stream(e, h0, h_out, st) : forward_tc(e, h0, h_out, st);
     if (e->use_att) {
         if (e->gather_mode != GATHER_SPARSE) return e->fail(GGNN_EUNSUPPORTED, "propagation attention needs the sparse graph format");
         CU_TRY(e, e->att_buf.reserve(sizeof(float) * (size_t)std::max<int64_t>(e->M, 1) * (size_t)(e->save ? std::max(e->total_steps, 1) : 1)));

@@ -116,7 +116,13 @@ def test_fast_single_bf16_mode_is_close_but_outside_the_bar():
     assert err < 3e-2
 
 
-def test_hidden_256_is_refused_not_silently_rerouted():
-    from gated_graph_neural_network_samples_b200.engine import GgnnError, PropagationEngine
-    with pytest.raises(GgnnError, match="hidden_size <= 128"):
-        PropagationEngine(dict(CFG2, hidden_size=256), 4, precision=PREC)
+def test_hidden_256_takes_the_streaming_tensor_core_plan():
+    """D > 128 does not fit the tile-local fused kernel: the engine plans the streaming tcgen05 path (tests/test_gpu_stream.py)."""
+    _, b = U.molecule_batch(8, 256, seed=5)
+    p = dict(CFG2, hidden_size=256, layer_timesteps=[1])
+    w = O.init_sparse_weights(p, 4, np.random.default_rng(1))
+    ref = O.sparse_propagation_np(b["initial_node_representation"], b["adjacency_lists"], b["num_incoming_edges_per_type"], w, p, dtype=np.float64)
+    got, eng = U.engine_sparse(p, 4, w, b["adjacency_lists"], b["num_incoming_edges_per_type"], b["initial_node_representation"],
+                               precision=PREC, return_engine=True)
+    assert "STREAM" in eng.plan
+    _check(got, ref, "D=256")

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Streaming tcgen05 path: its tests, then bench lines of the configs it serves.
+TAG=${1:-st}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+timeout 900 python -m pytest ${NEW_TESTS:-tests/test_gpu_stream.py} -m gpu -x -q -s > $OUT/pytest_new.log 2>&1; rc=$?
+grep -E "max\|err\||passed|failed|Error|error|assert" $OUT/pytest_new.log | tail -60
+[ $rc -ne 0 ] && { echo "new tests failed ($rc)"; tail -40 $OUT/pytest_new.log; }
+for cfg in ${BENCH_CFGS:-cfg4}; do
+  timeout 600 python bench.py --config $cfg --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_$cfg.json 2> $OUT/bench_$cfg.err; echo "$cfg exit $?"
+  python -c "import json; d=json.loads(open('$OUT/bench_$cfg.json').read().strip().splitlines()[-1]); print('  ms', round(d['ms_per_step'],4), 'hot', round(d['ms_per_step_hot_l2'],4), 'e2e_ms', round(d['e2e']['ms_per_step'],3), 'train_ms', round(d['train_propagation']['ms_per_step'],3), 'frac', round(d['roofline']['frac'],4), d['config']['plan'])" || tail -15 $OUT/bench_$cfg.err
+done
