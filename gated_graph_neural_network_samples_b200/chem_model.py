@@ -102,6 +102,13 @@ class ChemModel(object):
         self.max_num_vertices = max(self.max_num_vertices, largest_id)
         self.num_edge_types = max(self.num_edge_types, largest_type * (1 if self.params['tie_fwd_bkwd'] else 2))
         self.annotation_size = max(self.annotation_size, len(graphs[0]["node_features"][0]))
+        if is_training_data:
+            # data parallelism: ranks own contiguous, node-balanced ranges of the TRAINING graphs; the shape facts above
+            # come from the whole set, so every rank builds the same model.  Validation runs on every rank (replicas are identical).
+            from . import parallel
+            rank, ws = parallel.world()
+            if ws > 1:
+                graphs = parallel.shard_graphs(graphs, rank, ws)
         return self.process_raw_graphs(graphs, is_training_data)
 
     # ------------------------------------------------------------------ the five hooks (chem_tensorflow.py:130-131,202-212)
@@ -142,15 +149,17 @@ class ChemModel(object):
         tv = torch.as_tensor(np.asarray(feed[self.placeholders['target_values']], dtype=np.float32), device=self.device)
         tm = torch.as_tensor(np.asarray(feed[self.placeholders['target_mask']], dtype=np.float32), device=self.device)
         losses, accs = [], []
+        self._task_sums = []      # per task: (ratio * sum of masked 0.5*diff^2 [graph attached], mask sum) -- what data parallelism exchanges
         for internal_id, task_id in enumerate(self.params['task_ids']):
             gate, trans = self.weights['regression_gate_task%i' % task_id], self.weights['regression_transform_task%i' % task_id]
             computed = self.gated_regression(final, gate.bind(keep), trans.bind(keep))
             diff = (computed - tv[internal_id, :]) * tm[internal_id, :]                         # :161-164
             num = tm[internal_id, :].sum() + SMALL_NUMBER
             accs.append(diff.abs().sum() / num)                                                 # :165
-            task_loss = (0.5 * diff * diff).sum() / num                                         # :166
-            task_loss = task_loss * (1.0 / (self.params.get('task_sample_ratios', {}).get(task_id) or 1.0))   # :168
-            losses.append(task_loss)
+            ratio = 1.0 / (self.params.get('task_sample_ratios', {}).get(task_id) or 1.0)           # :168
+            numer = (0.5 * diff * diff).sum() * ratio
+            self._task_sums.append((numer, float(tm[internal_id, :].sum())))
+            losses.append(numer / num)                                                          # :166
         return torch.stack(losses).sum(), accs                                                  # :170
 
     # ------------------------------------------------------------------ training step (chem_tensorflow.py:172-193)
@@ -182,10 +191,20 @@ class ChemModel(object):
         self.optimizer = torch.optim.Adam([v for _, v in named], lr=self.params['learning_rate'], eps=1e-8)   # tf.train.AdamOptimizer defaults
 
     def train_step(self, loss):
-        import torch
-        self.optimizer.zero_grad(set_to_none=True)
-        loss.backward()
-        self.reduce_gradients()
+        """Adam step with per-variable clip_by_norm (chem_tensorflow.py:183-191).  Under torch.distributed the gradient is the one of
+        the UNION of all ranks' batches: exactly one all-reduce over one persistent flat buffer (parallel.FlatGradients), the clip after
+        it.  ``loss`` may be None on a rank whose shard ran out of batches (it still takes part in the collective and the update).
+        Returns the number of ranks that had a batch."""
+        from . import parallel
+        _, ws = parallel.world()
+        active = 1
+        if ws == 1:
+            self.optimizer.zero_grad(set_to_none=True)
+            loss.backward()
+        else:
+            active = self.reduce_gradients(loss is not None)
+            if active == 0:
+                return 0
         clamp = self.params['clamp_gradient_norm']
         for _, v in self._train_vars:                                    # tf.clip_by_norm PER VARIABLE, :186-190
             if v.grad is not None:
@@ -194,11 +213,27 @@ class ChemModel(object):
                     v.grad.mul_(clamp / n)
         self.optimizer.step()
         self.after_weight_update()
+        return active
 
-    def reduce_gradients(self):
-        """Data-parallel hook: ONE all-reduce of all trainable gradients per step (parallel.py); no-op on 1 GPU."""
+    def reduce_gradients(self, have_batch: bool = True) -> int:
+        """Data-parallel exchange of one step: back-propagate every task's un-normalised masked loss sum into its segment of the flat
+        buffer, ONE all-reduce, divide by the all-rank mask sums (the reference normalises per task by the batch's mask sum,
+        chem_tensorflow.py:163-166 -- neither the graph count nor a per-rank mean reproduces the union batch)."""
         from . import parallel
-        parallel.allreduce_gradients([v for _, v in self._train_vars])
+        n_tasks = len(self.params['task_ids'])
+        if getattr(self, '_flat_grads', None) is None:
+            self._flat_grads = parallel.FlatGradients([v for _, v in self._train_vars], n_tasks)
+        fg = self._flat_grads
+        fg.zero()
+        dens = [0.0] * n_tasks
+        if have_batch:
+            for t, (numer, den) in enumerate(self._task_sums):
+                fg.bind(t)
+                numer.backward(retain_graph=t + 1 < n_tasks)
+                dens[t] = den
+        fg.set_masses(dens, have_batch)
+        fg.allreduce()
+        return fg.finish(SMALL_NUMBER)
 
     def after_weight_update(self):
         pass
@@ -220,7 +255,15 @@ class ChemModel(object):
         graphs_seen, steps = 0, 0
         loss_sum, acc_sum = 0.0, np.zeros(len(self.params['task_ids']))
         batches = ThreadedIterator(self.make_minibatch_iterator(data, is_training), max_queue_size=5)   # packing overlaps the GPU work
-        for feed in batches:
+        from . import parallel
+        lockstep = is_training and parallel.world()[1] > 1     # every rank must take part in every step's all-reduce
+        batches = iter(batches)
+        while True:
+            feed = next(batches, None)
+            if feed is None:
+                if lockstep and self.train_step(None) > 0:       # this shard is exhausted, another rank still has a batch
+                    continue
+                break
             n = feed[self.placeholders['num_graphs']]
             feed[self.placeholders['out_layer_dropout_keep_prob']] = self.params['out_layer_dropout_keep_prob'] if is_training else 1.0
             if is_training:
@@ -234,6 +277,7 @@ class ChemModel(object):
             loss_sum += float(batch_loss.detach()) * n
             acc_sum += np.array([float(a.detach()) for a in batch_accs]) * n
             print("Running %s, batch %i (has %i graphs). Loss so far: %.4f" % (epoch_name, steps - 1, n, loss_sum / graphs_seen), end='\r')
+        graphs_seen = max(graphs_seen, 1)
         accuracies = acc_sum / graphs_seen
         return (loss_sum / graphs_seen, accuracies, accuracies / self.CHEMICAL_ACCURACIES[self.params["task_ids"]],
                 graphs_seen / (time.time() - t_begin), steps)
@@ -289,9 +333,23 @@ class ChemModel(object):
             b1, b2 = opt.param_groups[0]['betas']
             weights_to_save['beta1_power:0'] = np.float32(b1 ** (step + 1))   # tf.train.AdamOptimizer keeps beta^(t+1) after t updates
             weights_to_save['beta2_power:0'] = np.float32(b2 ** (step + 1))
+            weights_to_save['adam_step'] = np.int64(step)   # beta1^(t+1) underflows float32 after ~1000 updates: the count is kept explicitly
         with open(model_path, 'wb') as out_file:
             pickle.dump({"params": self.params, "weights": weights_to_save, "train_step": train_step, "valid_step": valid_step},
                         out_file, pickle.HIGHEST_PROTOCOL)
+
+    @staticmethod
+    def _adam_step_from_checkpoint(saved: dict, betas, fallback: int) -> int:
+        """Number of Adam updates a checkpoint was written after.  Our own pickles carry it as 'adam_step'; a TensorFlow pickle only has
+        beta1_power = beta1^(t+1) and beta2_power, float32 -- beta1_power underflows to 0 after ~1000 updates (log -> -inf), beta2_power
+        (0.999^t) lasts ~100 k updates; beyond that the pickle's train_step (batches seen) is the best available count."""
+        if 'adam_step' in saved:
+            return max(int(saved['adam_step']), 0)
+        for key, beta in (('beta1_power:0', betas[0]), ('beta2_power:0', betas[1])):
+            val = float(saved.get(key, 0.0))
+            if np.isfinite(val) and 0.0 < val < 1.0 and 0.0 < beta < 1.0:
+                return max(int(round(np.log(val) / np.log(beta))) - 1, 0)
+        return max(int(fallback), 0)
 
     def initialize_model(self) -> None:
         pass  # variables are initialised where they are created
@@ -318,9 +376,8 @@ class ChemModel(object):
         # Adam slots (TF names "<variable>/Adam:0", "<variable>/Adam_1:0", "beta1_power:0"): restored when present
         opt = getattr(self, 'optimizer', None)
         if opt is not None and 'beta1_power:0' in saved:
-            b1 = opt.param_groups[0]['betas'][0]
-            step = max(int(round(np.log(float(saved['beta1_power:0'])) / np.log(b1))) - 1, 0)
-            used.update(('beta1_power:0', 'beta2_power:0'))
+            step = self._adam_step_from_checkpoint(saved, opt.param_groups[0]['betas'], data_to_load.get('train_step', 0))
+            used.update(('beta1_power:0', 'beta2_power:0', 'adam_step'))
             for n, v in self._train_vars:
                 m, s2 = n[:-2] + '/Adam:0', n[:-2] + '/Adam_1:0'
                 if m in saved and s2 in saved:

@@ -1145,24 +1145,26 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
     const int ntiles = e->ntiles;
     int rc = ts_prepare_weights(e, st);
     if (rc) return rc;
-    const size_t img_b = (size_t)ntiles * NKS * ts::A_STAGE_B;
-    const int n_img = L + 1 + 4;    // node_states_per_layer images, two step temporaries, agg, r*h
-    CU_TRY(e, e->ts_images.reserve(img_b * n_img));
+    const size_t img_b = (size_t)ntiles * NKS * ts::A_STAGE_B;   // one operand image == one chunk-major fp32 copy, in bytes
+    const int n_img = L + 1 + 4;    // images: node_states_per_layer, two step temporaries, agg, r*h
+    const int n_chk = L + 1 + 3;    // chunk-major fp32: node_states_per_layer, two step temporaries, u
+    CU_TRY(e, e->ts_images.reserve(img_b * (n_img + n_chk)));
     uint8_t* ib = (uint8_t*)e->ts_images.ptr;
     auto img_state = [&](int l) { return ib + (size_t)l * img_b; };
     uint8_t* img_tmp[2] = {ib + (size_t)(L + 1) * img_b, ib + (size_t)(L + 2) * img_b};
     uint8_t* img_agg = ib + (size_t)(L + 3) * img_b;
     uint8_t* img_rh = ib + (size_t)(L + 4) * img_b;
+    uint8_t* cb = ib + (size_t)n_img * img_b;
+    auto chk_state = [&](int l) { return (float*)(cb + (size_t)l * img_b); };
+    float* chk_tmp[2] = {(float*)(cb + (size_t)(L + 1) * img_b), (float*)(cb + (size_t)(L + 2) * img_b)};
+    float* u_chk = (float*)(cb + (size_t)(L + 3) * img_b);
     const size_t vd = (size_t)std::max(V, 1) * D;
     const size_t vd_bytes = (size_t)V * D * sizeof(float);
     float* sb = (float*)e->state_buf.ptr;
     std::vector<float*> state(L + 1);
     state[0] = const_cast<float*>(h0);
     for (int l = 1; l <= L; ++l) state[l] = (l == L) ? h_out : sb + (size_t)(l - 1) * vd;
-    float* tmp[2] = {sb + (size_t)(L - 1 > 0 ? L - 1 : 0) * vd, nullptr};
-    tmp[1] = tmp[0] + vd;
     const bool gru = e->cell == CELL_GRU;
-    if (gru && !e->save) CU_TRY(e, e->ts_u.reserve(vd * sizeof(float)));
     float* sv = (float*)e->save_bufs.ptr;
     const size_t per = vd * (size_t)std::max(e->total_steps, 1);
     char* g = (char*)e->graph_buf.ptr;
@@ -1170,7 +1172,7 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
     // shared-memory budgets
     const size_t avail = (e->max_smem > 2048 ? e->max_smem - 2048 : 0);
     const int csr_cap = std::min((e->max_tile_msgs + 3) / 4 * 4, 8192);
-    const size_t csr_b = (size_t)((ts::TILE_M * T + 1 + 3) & ~3) * 4 + (size_t)csr_cap * 4;
+    const size_t csr_b = (size_t)((ts::TILE_M * T + 1 + 3) & ~3) * 4 + (size_t)csr_cap * 4 + (size_t)T * ts::TILE_M;
     auto stages_for = [&](int NC, size_t budget) {
         const size_t stage = (size_t)ts::A_STAGE_B + 64 * (size_t)NC;
         return (int)std::min<size_t>(ts::MAX_NS, budget / stage);
@@ -1186,6 +1188,17 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
     base.csr_cap = csr_cap;
     base.drop_keep = e->drop_keep; base.drop_seed = e->drop_seed;
     base.error_flag = (int*)e->err_flag.ptr;
+    // optional per-CTA phase stamps, one slice per launch (tools/stream_trace.py)
+    long long* dbg = nullptr;
+    const size_t dbg_slice = (size_t)ntiles * std::max(e->ts_nblk[0], e->ts_nblk[1]) * 16;
+    if (getenv("GGNN_TS_DEBUG")) {
+        const size_t n = dbg_slice * (size_t)(3 * std::max(e->total_steps, 1));
+        CU_TRY(e, e->dbg_buf.reserve(n * sizeof(long long)));
+        CU_TRY(e, cudaMemsetAsync(e->dbg_buf.ptr, 0, n * sizeof(long long), st));
+        dbg = (long long*)e->dbg_buf.ptr;
+    }
+    int dbg_launch = 0;
+    auto next_dbg = [&]() -> long long* { return dbg ? dbg + dbg_slice * (size_t)(dbg_launch++) : nullptr; };
     auto tmem_cols = [](int NC) { int c = 32; while (c < NC) c *= 2; return c; };
     const int nc0 = e->ts_nc[0], nb0 = e->ts_nblk[0], nc1 = e->ts_nc[1], nb1 = e->ts_nblk[1];
     // edge kernel: one CTA per SM, deep ring; TMA-fed kernels: two CTAs per SM when the grid is larger than the chip
@@ -1203,32 +1216,33 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
 
     {   // node_states_per_layer[0] -> operand image
         const long long total = (long long)ntiles * ts::TILE_M * (DP / 8);
-        ts::ggnn_image_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(h0, img_state(0), V, D, DP, ntiles);
+        ts::ggnn_image_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(h0, img_state(0), chk_state(0), V, D, DP, ntiles);
         ++e->last_launches;
     }
     const uint8_t* wb = (const uint8_t*)e->ts_weights.ptr;
     for (int l = 0; l < L; ++l) {
-        const float* in = state[l];
         const uint8_t* img_in = img_state(l);
+        const float* chk_in = chk_state(l);
         if (e->steps[l] == 0) {   // a layer without timesteps aliases the previous state (sparse:152)
-            CU_TRY(e, cudaMemcpyAsync(state[l + 1], in, vd_bytes, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(e, cudaMemcpyAsync(state[l + 1], state[l], vd_bytes, cudaMemcpyDeviceToDevice, st));
             CU_TRY(e, cudaMemcpyAsync(img_state(l + 1), img_in, img_b, cudaMemcpyDeviceToDevice, st));
+            CU_TRY(e, cudaMemcpyAsync(chk_state(l + 1), chk_in, img_b, cudaMemcpyDeviceToDevice, st));
             continue;
         }
         const int R = e->nres[l], nseg = R + 2;
         for (int s = 0; s < e->steps[l]; ++s) {
             const bool last = s == e->steps[l] - 1;
-            float* out = last ? state[l + 1] : tmp[s & 1];
+            float* out = last ? state[l + 1] : nullptr;   // the row-major copy exists only for node_states_per_layer entries
             uint8_t* img_out = last ? img_state(l + 1) : img_tmp[s & 1];
+            float* chk_out = last ? chk_state(l + 1) : chk_tmp[s & 1];
             const int gs = e->step_base[l] + s;
             const size_t so = (size_t)gs * vd;
-            float* u_buf = gru ? (e->save ? sv + 3 * per + so : (float*)e->ts_u.ptr) : nullptr;
             // ---- aggregated messages
             ts::StreamParams p = base;
             p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.tmem_cols = tmem_cols(nc0);
-            p.g_src = in; p.w = wb + e->ts_off_edge[l]; p.kt_all = T * NKS;
+            p.g_img = img_in; p.w = wb + e->ts_off_edge[l]; p.kt_all = T * NKS;
             p.bias = e->use_bias ? e->w[l].edge_biases : nullptr;
-            p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs;
+            p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs; p.dbg = next_dbg();
             k_edge<<<dim3(ntiles, nb0), 18 * 32, sm_edge, st>>>(p);
             ++e->last_launches;
             auto set_segs = [&](ts::StreamParams& q, const uint8_t* last_img) {
@@ -1241,21 +1255,21 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
                 ts::StreamParams q = base;
                 q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.tmem_cols = tmem_cols(nc1);
                 set_segs(q, img_in);
-                q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_in = in; q.u_buf = u_buf; q.img_out = img_rh;
-                if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; }
-                q.gstep = gs;
+                q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_chk = chk_in; q.u_buf = u_chk; q.img_out = img_rh;
+                if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; q.sv_u = sv + 3 * per + so; }
+                q.gstep = gs; q.dbg = next_dbg();
                 k_fed<<<dim3(ntiles, nb1), 10 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
                 ++e->last_launches;
             }
             ts::StreamParams c = base;
             c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.tmem_cols = tmem_cols(nc0);
             set_segs(c, gru ? img_rh : img_in);
-            c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_in = in; c.u_buf = u_buf; c.h_out = out; c.img_out = img_out;
+            c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_chk = chk_in; c.u_buf = u_chk; c.h_chk_out = chk_out; c.h_out = out; c.img_out = img_out;
             if (e->save) { if (gru) c.sv_c = sv + 4 * per + so; else c.sv_h = sv + so; }
-            c.gstep = gs;
+            c.gstep = gs; c.dbg = next_dbg();
             k_fed<<<dim3(ntiles, nb0), 10 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
             ++e->last_launches;
-            in = out; img_in = img_out;
+            img_in = img_out; chk_in = chk_out;
         }
     }
     CU_TRY(e, cudaGetLastError());
@@ -1510,7 +1524,7 @@ int ggnn_debug_trace(ggnn_engine* e, int64_t* out, int32_t capacity) {
     if (!e->dbg_buf.ptr) return e->fail(GGNN_ESTATE, "no debug trace recorded (set GGNN_TC_DEBUG_TIMING=1)");
     CU_TRY(e, cudaSetDevice(e->device));
     CU_TRY(e, cudaDeviceSynchronize());
-    CU_TRY(e, cudaMemcpy(out, e->dbg_buf.ptr, sizeof(long long) * (size_t)std::min(capacity, 512), cudaMemcpyDeviceToHost));
+    CU_TRY(e, cudaMemcpy(out, e->dbg_buf.ptr, sizeof(long long) * std::min((size_t)capacity, e->dbg_buf.cap / sizeof(long long)), cudaMemcpyDeviceToHost));
     return GGNN_OK;
 }
 

@@ -15,6 +15,12 @@
 // pre-split and pre-tiled per (N block, K-step) into contiguous 64*NC-byte stages (ggnn_tile_weights_stream_kernel).
 // fp32 accuracy on bf16 tensor cores as in ggnn_fwd_tc.cuh: x = hi + lo, product = Ah.Bh + Ah.Bl + Al.Bh (3 MMAs).
 //
+// The fp32 master copy of every state (and the update gate u) is kept in a second, chunk-major layout
+//   float(tile, chunk = col/8, row, j) = ((tile*NKC + chunk)*128 + row)*8 + j
+// so that an epilogue warp (32 rows x 8 columns) reads and writes 1 KB contiguous instead of 32 scattered sectors (the row-per-thread
+// pattern on a row-major [V, D] array costs one L1TEX tag cycle per row and instruction and made the epilogues longer than the GEMMs);
+// the user-visible row-major [V, D] arrays are written only for node_states_per_layer entries and for the backward pass.
+//
 // Roles: warp 0 = producer (one thread: bulk copies), warp 1 = MMA issuer (+ TMEM allocator), warps 2.. = workers
 // (gather groups of 4 warps in the edge kernel; epilogue: TMEM lane quarter = warp % 4, column group = worker / 4).
 // The TMA-fed variants use <= ~100 KB of shared memory and <= 256 TMEM columns so that two CTAs share an SM: one
@@ -45,7 +51,7 @@ struct StreamParams {
     int nseg;
     const uint8_t* seg[MAX_SEG];
     // ---- A operand, gathered (EPI_AGG): per present edge type a DP-wide segment of per-type source sums
-    const float* g_src;          // fp32 state the messages are gathered from [V][D]
+    const uint8_t* g_img;        // image of the state the messages are gathered from (a row with one type-t message is a 64-byte copy)
     const int* row_ptr;          // [V*T+1] target-keyed CSR
     const int* csr_src;          // [M]
     const unsigned* tile_mask;   // [ntiles] bit t: some row of the tile receives a type-t message
@@ -57,16 +63,36 @@ struct StreamParams {
     const float* bias;           // AGG: edge_biases [T][D] or null; GATE: gate_bias [2D]; CAND: cand_bias [D]
     const float* indeg;          // [V][T]
     const float* denom;          // [V]
-    const float* h_in;           // fp32 state entering the step [V][D]   (GATE: r*h, save; CAND: blend)
-    float* u_buf;                // [V][D] update gate: written by GATE, read by CAND
-    float* h_out;                // CAND: new state fp32 [V][D]
+    const float* h_chk;          // fp32 state entering the step, chunk-major   (GATE: r*h, save; CAND: blend)
+    float* u_buf;                // update gate, chunk-major: written by GATE, read by CAND
+    float* h_chk_out;            // CAND: new state fp32, chunk-major
+    float* h_out;                // CAND: new state fp32 row-major [V][D], or null (only node_states_per_layer entries need it)
+    float* sv_u;                 // GATE: row-major copy of u for the backward pass, or null
     uint8_t* img_out;            // AGG: agg image; GATE: r*h image; CAND: image of the new state
     float* sv_h; float* sv_agg; float* sv_r; float* sv_c;   // this step's save-for-backward slots or null
     float drop_keep; unsigned long long drop_seed; int gstep;
     int* error_flag;
+    long long* dbg;   // optional per-CTA phase stamps [grid.y][grid.x][16] (GGNN_TS_DEBUG=1), or nullptr
 };
 
-__device__ __forceinline__ size_t img_tile_bytes(int NKS) { return (size_t)NKS * A_STAGE_B; }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ size_t chunk_off(int NKC, int tile, int c, int row) { return (((size_t)tile * NKC + c) * TILE_M + row) * 8; }
+__device__ __forceinline__ void chunk_load(const float* base, int NKC, int tile, int c, int row, float (&v)[8]) {
+    const float4* q = reinterpret_cast<const float4*>(base + chunk_off(NKC, tile, c, row));
+    const float4 a = __ldcg(q), b = __ldcg(q + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void chunk_store(float* base, int NKC, int tile, int c, int row, const float (&v)[8]) {
+    float4* q = reinterpret_cast<float4*>(base + chunk_off(NKC, tile, c, row));
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void unpack8(const uint4& a, float (&x)[8]) {
+    const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { x[2 * j] = __uint_as_float(w[j] << 16); x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+}
 
 // one [row, 8 columns] chunk of an image (both parts); col0 % 8 == 0
 __device__ __forceinline__ void img_store_chunk(uint8_t* img, int NKS, int tile, int row, int col0, const float (&x)[8]) {
@@ -100,6 +126,8 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     int* sPtr = reinterpret_cast<int*>(smem + (size_t)NS * STAGE_B);    // [128*T + 1] tile-relative CSR row offsets (GATHER)
     int* sSrc = sPtr + ((TILE_M * T + 1 + 3) & ~3);                     // [csr_cap] global source ids
+    uint8_t* sPerm = reinterpret_cast<uint8_t*>(sSrc + p.csr_cap);       // [T][128] rows of the tile ordered: >= 2 type-t messages | exactly 1 | none
+    __shared__ int s_n0[32], s_n1[32];                                   // per present type: rows with >= 2 messages, rows with exactly 1
 
     if (tid == 0) {
         s_abort = 0;
@@ -129,9 +157,14 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
         if (lane == 0) {
             bool ok = true;
             const uint8_t* wb = p.w + (size_t)nb * p.kt_all * B_STAGE_B;
+            long long waited = 0;
             for (int k = 0; k < nk && ok; ++k) {
                 const int s = k % NS, it = k / NS;
-                if (it > 0 && !tc::mbar_wait(&bar_empty[s], (uint32_t)(it - 1) & 1u, abortp)) { ok = false; break; }
+                if (it > 0) {
+                    const long long w0 = p.dbg ? clock64() : 0;
+                    if (!tc::mbar_wait(&bar_empty[s], (uint32_t)(it - 1) & 1u, abortp)) { ok = false; break; }
+                    if (p.dbg) waited += clock64() - w0;
+                }
                 uint8_t* st = smem + (size_t)s * STAGE_B;
                 if (GATHER) {
                     const int kk = s_types[k / NKS] * NKS + (k % NKS);
@@ -145,6 +178,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
                 }
             }
             if (!ok) atomicExch(p.error_flag, 13);
+            if (p.dbg) p.dbg[((size_t)nb * gridDim.x + tile) * 16 + 4] = waited;
         }
     } else if (warp == 1) {
         // =============================================================================== MMA ISSUER
@@ -156,11 +190,15 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
         const uint32_t b_lo16 = (32u * (uint32_t)NC) >> 4;
         const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = STAGE_B >> 4;
         const uint32_t tm_d = __shfl_sync(0xffffffffu, tmem, 0);
+        long long waited_b = 0, waited_a = 0;
         for (int k = 0; k < nk && ok; ++k) {
             const int s = k % NS;
             const uint32_t par = (uint32_t)(k / NS) & 1u;
+            const long long w0 = p.dbg ? clock64() : 0;
             if (!tc::mbar_wait(&bar_full[s], par, abortp)) ok = false;
+            const long long w1 = p.dbg ? clock64() : 0;
             if (GATHER && ok && !tc::mbar_wait(&bar_afull[s], par, abortp)) ok = false;
+            if (p.dbg) { waited_b += w1 - w0; waited_a += clock64() - w1; }
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
             tc::tc_fence_after();
@@ -179,6 +217,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
             __syncwarp();
         }
         if (!ok && lane == 0) atomicExch(p.error_flag, 12);
+        if (p.dbg && lane == 0) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[5] = waited_b; d[6] = waited_a; }
     } else {
         // =============================================================================== WORKERS
         const int wi = warp - 2;
@@ -186,10 +225,19 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
         const int row = q * 32 + lane;                // tile row == TMEM lane
         const bool row_ok = row < rows;
         const int grow = row0 + (row_ok ? row : 0);
+        constexpr int NCG = NWORK / 4;                // epilogue column groups
+        const int cgp = wi >> 2;
+        const int nchunks = NC >> 3;
+        const int colb = nb * NC;                     // first (padded) output column of this CTA
         bool ok = true;
+        const bool stamp = p.dbg && wi == 0 && lane == 0;
+        long long t0 = 0, t_gather = 0, t_acc = 0, g_load = 0, g_wait = 0, g_tail = 0, t_setup = 0;
+        if (stamp) t0 = clock64();
+        const int NKC = DP >> 3;
         if (GATHER) {
             constexpr int NG = NWORK / 4;             // gather groups (4 warps = 128 rows each)
             const int grp = wi >> 2;
+            const int gi = (wi & 3) * 32 + lane;      // index within the group: which entry of the per-type row order this thread serves
             // ---- the tile's CSR slice -> shared memory
             const int base = p.row_ptr[(size_t)row0 * T];
             const int nptr = rows * T + 1;
@@ -199,61 +247,130 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
             const bool cached = mt <= p.csr_cap;
             if (cached) for (int i = wt; i < mt; i += NWORK * 32) sSrc[i] = p.csr_src[base + i];
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
-            const int* srcs = cached ? sSrc : p.csr_src + base;
-            for (int k = grp; k < nk && ok; k += NG) {
-                const int s = k % NS, it = k / NS;
-                const int t = s_types[k / NKS], col0 = (k % NKS) * 16;
-                int beg = 0, end = 0;
-                if (row_ok) { beg = sPtr[row * T + t]; end = sPtr[row * T + t + 1]; }
-                float a[16];
+            // ---- per present type: order the rows by message count class so that whole warps take the same path.  Only ~1/4 of the
+            // (row, type) pairs of a molecule batch have a message at all, and most of those exactly one.
+            for (int ti = wi; ti < s_ntypes; ti += NWORK) {
+                const int t = s_types[ti];
+                int cls[4], n0 = 0, n1 = 0;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) a[j] = 0.0f;
-                for (int m = beg; m < end; m += 2) {   // two source rows in flight
-                    const bool two = m + 1 < end;
-                    const float* s0 = p.g_src + (size_t)srcs[m] * D;
-                    const float* s1 = p.g_src + (size_t)srcs[two ? m + 1 : m] * D;
-                    float v0[16], v1[16];
-                    tc::load8_guarded_cg(s0, col0, D, *reinterpret_cast<float(*)[8]>(&v0[0]));
-                    tc::load8_guarded_cg(s0, col0 + 8, D, *reinterpret_cast<float(*)[8]>(&v0[8]));
-                    tc::load8_guarded_cg(s1, col0, two ? D : 0, *reinterpret_cast<float(*)[8]>(&v1[0]));
-                    tc::load8_guarded_cg(s1, col0 + 8, two ? D : 0, *reinterpret_cast<float(*)[8]>(&v1[8]));
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) a[j] += v0[j];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) a[j] += v1[j];
+                for (int i = 0; i < 4; ++i) {
+                    const int r = i * 32 + lane;
+                    const int cnt = r < rows ? sPtr[r * T + t + 1] - sPtr[r * T + t] : 0;
+                    cls[i] = cnt >= 2 ? 0 : (cnt == 1 ? 1 : 2);
+                    n0 += __popc(__ballot_sync(0xffffffffu, cls[i] == 0));
+                    n1 += __popc(__ballot_sync(0xffffffffu, cls[i] == 1));
                 }
-                uint4 h0, l0, h1, l1;
-                tc::split8(*reinterpret_cast<float(*)[8]>(&a[0]), h0, l0);
-                tc::split8(*reinterpret_cast<float(*)[8]>(&a[8]), h1, l1);
+                int run[3] = {0, n0, n0 + n1};
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned m = __ballot_sync(0xffffffffu, cls[i] == c);
+                        if (cls[i] == c) sPerm[ti * TILE_M + run[c] + __popc(m & lt)] = (uint8_t)(i * 32 + lane);
+                        run[c] += __popc(m);
+                    }
+                }
+                if (lane == 0) { s_n0[ti] = n0; s_n1[ti] = n1; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
+            const int* srcs = cached ? sSrc : p.csr_src + base;
+            if (stamp) t_setup = clock64();
+            for (int k = grp; k < nk && ok; k += NG) {
+                const long long c0 = stamp ? clock64() : 0;
+                const int s = k % NS, it = k / NS;
+                const int ti = k / NKS, ks = k - ti * NKS;
+                const int t = s_types[ti];
+                const int prow = sPerm[ti * TILE_M + gi];
+                const int n0 = s_n0[ti], n01 = n0 + s_n1[ti];
+                uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0, o2 = o0, o3 = o0;   // hi k-group 0 | hi k-group 1 | lo k-group 0 | lo k-group 1
+                if (gi < n01) {
+                    const int beg = sPtr[prow * T + t];
+                    {
+                        const int src = srcs[beg];
+                        const uint8_t* sp = p.g_img + ((size_t)(src >> 7) * NKS + ks) * A_STAGE_B + (size_t)(src & 127) * 16;
+                        o0 = __ldcg(reinterpret_cast<const uint4*>(sp));
+                        o1 = __ldcg(reinterpret_cast<const uint4*>(sp + 2048));
+                        o2 = __ldcg(reinterpret_cast<const uint4*>(sp + 4096));
+                        o3 = __ldcg(reinterpret_cast<const uint4*>(sp + 6144));
+                    }
+                    if (gi < n0) {   // two or more messages: fp32 sum in message order, then re-split (two source rows in flight)
+                        const int end = sPtr[prow * T + t + 1];
+                        auto img_row = [&](int m) {
+                            const int src = srcs[m];
+                            return p.g_img + ((size_t)(src >> 7) * NKS + ks) * A_STAGE_B + (size_t)(src & 127) * 16;
+                        };
+                        const uint8_t* sp1 = img_row(beg + 1);
+                        uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(sp1)), q1 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 2048));
+                        uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 4096)), q3 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 6144));
+                        float a0[8], a1[8];
+                        unpack8(o0, a0); unpack8(o1, a1);
+                        tc::unpack8_add(o2, a0, 1.0f); tc::unpack8_add(o3, a1, 1.0f);
+                        for (int m = beg + 2; ; ++m) {
+                            const uint4 c0 = q0, c1 = q1, c2 = q2, c3 = q3;
+                            if (m < end) {
+                                const uint8_t* sp = img_row(m);
+                                q0 = __ldcg(reinterpret_cast<const uint4*>(sp)); q1 = __ldcg(reinterpret_cast<const uint4*>(sp + 2048));
+                                q2 = __ldcg(reinterpret_cast<const uint4*>(sp + 4096)); q3 = __ldcg(reinterpret_cast<const uint4*>(sp + 6144));
+                            }
+                            tc::unpack8_add(c0, a0, 1.0f); tc::unpack8_add(c2, a0, 1.0f);
+                            tc::unpack8_add(c1, a1, 1.0f); tc::unpack8_add(c3, a1, 1.0f);
+                            if (m >= end) break;
+                        }
+                        tc::split8(a0, o0, o2);
+                        tc::split8(a1, o1, o3);
+                    }
+                }
+                const long long c1 = stamp ? clock64() : 0;
                 if (it > 0 && !tc::mbar_wait(&bar_empty[s], (uint32_t)(it - 1) & 1u, abortp)) { ok = false; }
                 ok = __all_sync(0xffffffffu, ok);
                 if (!ok) break;
-                uint8_t* ap = smem + (size_t)s * STAGE_B + (size_t)row * 16;
-                *reinterpret_cast<uint4*>(ap) = h0;
-                *reinterpret_cast<uint4*>(ap + 2048) = h1;
-                *reinterpret_cast<uint4*>(ap + 4096) = l0;
-                *reinterpret_cast<uint4*>(ap + 6144) = l1;
+                const long long c2 = stamp ? clock64() : 0;
+                uint8_t* ap = smem + (size_t)s * STAGE_B + (size_t)prow * 16;
+                *reinterpret_cast<uint4*>(ap) = o0;
+                *reinterpret_cast<uint4*>(ap + 2048) = o1;
+                *reinterpret_cast<uint4*>(ap + 4096) = o2;
+                *reinterpret_cast<uint4*>(ap + 6144) = o3;
                 tc::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
+                if (stamp) { const long long c3 = clock64(); g_load += c1 - c0; g_wait += c2 - c1; g_tail += c3 - c2; }
             }
+            if (stamp) t_gather = clock64();
         }
-        // ---- epilogue: accumulator -> registers -> outputs
+        // ---- epilogue: accumulator -> registers -> outputs.  The global operands of the first chunk are requested BEFORE the wait for the
+        // accumulator, those of chunk c+1 before the math of chunk c (the loads are L2 hits after the prefetch above).
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const bool have_acc = nk > 0;
+        const bool gru = p.cell == CELL_GRU;
+        // the global operands of this thread's next chunk are requested before the math of the current one
+        float hA[8], uA[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { hA[j] = 0.0f; uA[j] = 0.0f; }
+        const bool cand_h = p.epi == EPI_CAND && (gru || p.sv_h);
+        auto load_ops = [&](int c, float (&hb)[8], float (&ub)[8]) {   // operands of chunk c (if it exists)
+            const int colp = colb + c * 8;
+            if (c >= nchunks) return;
+            if (p.epi == EPI_CAND) {
+                if (colp >= DP) return;
+                if (cand_h) chunk_load(p.h_chk, NKC, tile, colp >> 3, row, hb);
+                if (gru) chunk_load(p.u_buf, NKC, tile, colp >> 3, row, ub);
+            } else if (p.epi == EPI_GATE) {
+                if (colp < DP) chunk_load(p.h_chk, NKC, tile, colp >> 3, row, hb);
+            }
+        };
+        if (!GATHER) load_ops(cgp, hA, uA);
         if (ok && nk > 0) {
             if (!tc::mbar_wait(&bar_acc, 0, abortp)) ok = false;
             ok = __all_sync(0xffffffffu, ok);
             tc::tc_fence_after();
         }
+        if (stamp) t_acc = clock64();
         if (ok) {
-            constexpr int NCG = NWORK / 4;            // column groups
-            const int cgp = wi >> 2;
-            const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-            const bool have_acc = nk > 0;
-            const int nchunks = NC >> 3;
             if (p.epi == EPI_AGG) {
                 const float den = (p.use_avg && row_ok) ? p.denom[grow] : 1.0f;
                 for (int c = cgp; c < nchunks; c += NCG) {
-                    const int col = nb * NC + c * 8;
+                    const int col = colb + c * 8;
                     if (col >= DP) break;
                     float v[8];
                     if (have_acc) tc::tmem_ld8(tmem + lane_addr + c * 8, v);
@@ -276,42 +393,47 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
                     img_store_chunk(p.img_out, NKS, tile, row, col, v);
                 }
             } else if (p.epi == EPI_GATE) {
-                for (int c = cgp; c < nchunks; c += NCG) {
-                    const int colp = nb * NC + c * 8;
-                    if (colp >= 2 * DP) break;
+                auto gate_chunk = [&](int c, float (&hb)[8], float (&ub)[8]) -> bool {
+                    const int colp = colb + c * 8;
+                    if (c >= nchunks || colp >= 2 * DP) return false;
                     const bool is_r = colp < DP;
                     const int col = is_r ? colp : colp - DP;
-                    float g[8], b[8];
+                    float g[8], b[8], h[8];
                     tc::tmem_ld8_nowait(tmem + lane_addr + c * 8, g);
-                    tc::load8_guarded(p.bias + (is_r ? 0 : D), col, D, b);
-                    if (is_r) {
-                        float h[8], rh[8];
-                        tc::load8_guarded_cg(p.h_in + (size_t)grow * D, col, row_ok ? D : 0, h);
-                        tc::tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { g[j] = tc::sigmoid_fast(g[j] + b[j]); rh[j] = g[j] * h[j]; }
+                    for (int j = 0; j < 8; ++j) h[j] = hb[j];
+                    load_ops(c + NCG, hb, ub);
+                    tc::load8_guarded(p.bias + (is_r ? 0 : D), col, D, b);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] = tc::sigmoid_fast(g[j] + b[j]);
+                    if (is_r) {
+                        float rh[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rh[j] = g[j] * h[j];
                         if (p.sv_r && row_ok) {
                             tc::store8_guarded(p.sv_r + (size_t)grow * D, col, D, g);
                             tc::store8_guarded(p.sv_h + (size_t)grow * D, col, D, h);
                         }
                         img_store_chunk(p.img_out, NKS, tile, row, col, rh);
                     } else {
-                        tc::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] = tc::sigmoid_fast(g[j] + b[j]);
-                        if (row_ok) tc::store8_guarded(p.u_buf + (size_t)grow * D, col, D, g);
+                        chunk_store(p.u_buf, NKC, tile, col >> 3, row, g);
+                        if (p.sv_u && row_ok) tc::store8_guarded(p.sv_u + (size_t)grow * D, col, D, g);
                     }
-                }
+                    return true;
+                };
+                for (int c = cgp; c < nchunks; c += NCG)
+                    if (!gate_chunk(c, hA, uA)) break;
             } else {
-                const bool gru = p.cell == CELL_GRU;
-                for (int c = cgp; c < nchunks; c += NCG) {
-                    const int col = nb * NC + c * 8;
-                    if (col >= DP) break;
+                auto cand_chunk = [&](int c, float (&hb)[8], float (&ub)[8]) -> bool {
+                    const int col = colb + c * 8;
+                    if (c >= nchunks || col >= DP) return false;
                     float cv[8], b[8], h[8], u[8], hn[8];
                     tc::tmem_ld8_nowait(tmem + lane_addr + c * 8, cv);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { h[j] = hb[j]; u[j] = ub[j]; }
+                    load_ops(c + NCG, hb, ub);
                     tc::load8_guarded(p.bias, col, D, b);
-                    if (gru || p.sv_h) tc::load8_guarded_cg(p.h_in + (size_t)grow * D, col, row_ok ? D : 0, h);
-                    if (gru) tc::load8_guarded_cg(p.u_buf + (size_t)grow * D, col, row_ok ? D : 0, u);
                     tc::tmem_ld_wait();
                     if (gru) {
 #pragma unroll
@@ -331,12 +453,21 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) hn[j] = (row_ok && col + j < D) ? hn[j] : 0.0f;
-                    if (row_ok) tc::store8_guarded(p.h_out + (size_t)grow * D, col, D, hn);
+                    chunk_store(p.h_chk_out, NKC, tile, col >> 3, row, hn);
+                    if (p.h_out && row_ok) tc::store8_guarded(p.h_out + (size_t)grow * D, col, D, hn);
                     img_store_chunk(p.img_out, NKS, tile, row, col, hn);
-                }
+                    return true;
+                };
+                for (int c = cgp; c < nchunks; c += NCG)
+                    if (!cand_chunk(c, hA, uA)) break;
             }
         }
         if (!ok && lane == 0) atomicExch(p.error_flag, 11);
+        if (stamp) {
+            long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16;
+            d[0] = t0; d[1] = t_gather - t0; d[2] = t_acc - t0; d[3] = clock64() - t0; d[7] = nk;
+            d[8] = g_load; d[9] = g_wait; d[10] = g_tail; d[11] = t_setup - t0;
+        }
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -345,8 +476,8 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
     }
 }
 
-// fp32 [V][D] row-major -> tile-major bf16 hi/lo image ([ntiles*128][DP], zero padded)
-__global__ void ggnn_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, int V, int D, int DP, int ntiles) {
+// fp32 [V][D] row-major -> tile-major bf16 hi/lo image + chunk-major fp32 copy ([ntiles*128][DP], zero padded)
+__global__ void ggnn_image_kernel(const float* __restrict__ x, uint8_t* __restrict__ img, float* __restrict__ chk, int V, int D, int DP, int ntiles) {
     const int NKC = DP >> 3, NKS = DP >> 4;
     const long long total = (long long)ntiles * TILE_M * NKC;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -358,6 +489,7 @@ __global__ void ggnn_image_kernel(const float* __restrict__ x, uint8_t* __restri
         float v[8];
         tc::load8_guarded(x + (size_t)(grow < V ? grow : 0) * D, kc * 8, grow < V ? D : 0, v);
         img_store_chunk(img, NKS, tile, row, kc * 8, v);
+        chunk_store(chk, NKC, tile, kc, row, v);
     }
 }
 
