@@ -207,7 +207,11 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
     e->stream = false;
     if (e->precision != GGNN_PREC_FP32) {
         const char* fs = getenv("GGNN_TC_STREAM");
-        if (e->DP > 128 || (fs && fs[0] == '1' && e->gather_mode == GATHER_SPARSE)) {
+        const char* fgl = getenv("GGNN_FORCE_GLOBAL");
+        // a component larger than a tile cannot use the tile-local fused kernel: the streaming plan beats one-launch-per-step of that
+        // kernel (cfg5: 0.41 vs 0.57 ms), so it is the default there; GGNN_TC_STREAM=0/1 and GGNN_FORCE_GLOBAL=1 override
+        const bool big_component = max_span > tc::TILE_M && e->gather_mode == GATHER_SPARSE && !(fgl && fgl[0] == '1') && !(fs && fs[0] == '0');
+        if (e->DP > 128 || big_component || (fs && fs[0] == '1' && e->gather_mode == GATHER_SPARSE)) {
             // streaming plan: fixed 128-row tiles (the gather reads the previous state from L2, so tiles need not respect components),
             // one launch per GEMM of a timestep; N blocks sized so that small batches still spread over the chip
             if (e->gather_mode != GATHER_SPARSE)

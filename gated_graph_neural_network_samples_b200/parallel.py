@@ -125,10 +125,18 @@ class FlatGradients:
         if ws > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)      # the single collective of the step
 
-    def finish(self, eps: float) -> int:
-        """Combine the reduced numerators into the union-batch gradient (in task 0's segment); returns the number of active ranks."""
-        tail = self.flat[self.num_tasks * self.P:].tolist()
+    def finish(self, eps: float, sync: bool = True):
+        """Combine the reduced numerators into the union-batch gradient (in task 0's segment); returns the number of active ranks.
+        ``sync=False`` does the division with device-side scalars and returns None: no host round trip in the step."""
         seg0 = self.flat[:self.P]
+        if not sync:
+            base = self.num_tasks * self.P
+            seg0.div_(self.flat[base] + eps)
+            for t in range(1, self.num_tasks):
+                seg0.addcdiv_(self.flat[t * self.P:(t + 1) * self.P], (self.flat[base + t] + eps).expand(self.P))
+            self.bind(0)
+            return None
+        tail = self.flat[self.num_tasks * self.P:].tolist()
         seg0.div_(tail[0] + eps)
         for t in range(1, self.num_tasks):
             seg0.add_(self.flat[t * self.P:(t + 1) * self.P], alpha=1.0 / (tail[t] + eps))

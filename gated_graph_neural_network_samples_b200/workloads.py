@@ -70,8 +70,9 @@ def dense_engine_params(params: dict) -> dict:
             "use_edge_msg_avg_aggregation": False, "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh"}
 
 
-def build(name: str, seed: int = 0, scale: float = 1.0) -> dict:
-    """Materialise a workload.  ``scale`` multiplies the number of molecules (sharding / sampling)."""
+def build(name: str, seed: int = 0, scale: float = 1.0, shard=None) -> dict:
+    """Materialise a workload.  ``scale`` multiplies the number of molecules (sampling); ``shard=(rank, world)`` keeps this rank's
+    contiguous, node-balanced range of the molecule list (parallel.shard_bounds: strong scaling of one fixed batch)."""
     cfg = CONFIGS[name]
     T = cfg["edge_types"]
     params = dict(cfg["params"])
@@ -81,7 +82,13 @@ def build(name: str, seed: int = 0, scale: float = 1.0) -> dict:
     if cfg["kind"] == "sparse":
         n = max(1, int(round(cfg["molecules"] * scale)))
         mols = synthetic.make_molecules(n, seed=seed, num_bond_types=T)
+        if shard is not None:
+            from . import parallel
+            mols = parallel.shard_graphs(mols, int(shard[0]), int(shard[1]))
+            n = len(mols)
+        out["molecules"] = mols
         b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), D, T)
+        out["target_values"] = np.asarray([m["targets"][0][0] for m in mols], np.float32)
         out.update(engine_params=params, num_graphs=n, adjacency_lists=b["adjacency_lists"],
                    num_incoming_edges_per_type=b["num_incoming_edges_per_type"],
                    h0=b["initial_node_representation"], graph_nodes_list=b["graph_nodes_list"])
@@ -101,6 +108,27 @@ def build(name: str, seed: int = 0, scale: float = 1.0) -> dict:
     out["M"] = int(sum(a.shape[0] for a in out.get("adjacency_lists", [])))
     out["timesteps"] = int(sum(out["engine_params"]["layer_timesteps"]))
     out["node_updates"] = out["V"] * out["timesteps"]
+    return out
+
+
+def union_of(name: str, seeds) -> dict:
+    """ONE batch holding the molecules of ``build(name, seed=s)`` for every s in ``seeds``, in that order: the union batch a
+    data-parallel step over those shards must reproduce."""
+    cfg = CONFIGS[name]
+    assert cfg["kind"] == "sparse"
+    T, params = cfg["edge_types"], dict(cfg["params"])
+    D = int(params["hidden_size"])
+    mols = []
+    for s in seeds:
+        mols += synthetic.make_molecules(cfg["molecules"], seed=s, num_bond_types=T)
+    b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), D, T)
+    out = {"name": name, "kind": "sparse", "num_edge_types": T, "params": params, "engine_params": params, "num_graphs": len(mols),
+           "adjacency_lists": b["adjacency_lists"], "num_incoming_edges_per_type": b["num_incoming_edges_per_type"],
+           "h0": b["initial_node_representation"], "graph_nodes_list": b["graph_nodes_list"],
+           "target_values": np.asarray([m["targets"][0][0] for m in mols], np.float32)}
+    out["weights"] = init_weights(params, T, seed=1)
+    out["V"] = int(out["h0"].shape[0])
+    out["M"] = int(sum(a.shape[0] for a in out["adjacency_lists"]))
     return out
 
 

@@ -67,14 +67,18 @@ def test_global_mode_matches_local_mode(monkeypatch):
         _check(got, ref, "force_global=%s" % fg)
 
 
-def test_single_large_graph_rgcn_global_mode():
+def test_single_large_graph_rgcn_global_mode(monkeypatch):
     adj, indeg = synthetic.random_sparse_graph(10000, 40000, 4, seed=2)
     h0 = np.random.default_rng(4).normal(0, 0.1, (10000, 100)).astype(np.float32)
     w = O.init_sparse_weights(CFG5, 4, np.random.default_rng(1))
     ref = O.sparse_propagation_np(h0, adj, indeg, w, CFG5, dtype=np.float64)
     got, eng = U.engine_sparse(CFG5, 4, w, adj, indeg, h0, precision=PREC, return_engine=True)
-    assert "GLOBAL" in eng.plan
+    assert "STREAM" in eng.plan            # a 10 000-node component does not fit a tile: streaming plan (tests/test_gpu_stream.py)
     _check(got, ref, "cfg5")
+    monkeypatch.setenv("GGNN_TC_STREAM", "0")   # ... and the one-launch-per-step form of the tile kernel still serves it
+    got, eng = U.engine_sparse(CFG5, 4, w, adj, indeg, h0, precision=PREC, return_engine=True)
+    assert "GLOBAL" in eng.plan
+    _check(got, ref, "cfg5 global")
 
 
 def test_dense_cfg3_shape():
