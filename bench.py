@@ -472,7 +472,8 @@ def main():
 
     # ---- workload: every rank owns one full configs[1]-sized shard of independent graphs (weak scaling,
     # no data-path collective: forward propagation never crosses graphs)
-    w = workloads.build(args.config, seed=rank)
+    shard = os.environ.get("GGNN_BENCH_SHARD")   # "r,n": time ONE GPU on rank r's shard of an n-way split of the batch (profiling aid)
+    w = workloads.build(args.config, seed=rank, shard=tuple(int(x) for x in shard.split(",")) if shard else None)
     P = w["engine_params"]
     eng, dev_w = B.make_engine(w)
     dense = w["kind"] == "dense"

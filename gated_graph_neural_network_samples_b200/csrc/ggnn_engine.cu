@@ -124,6 +124,9 @@ struct ggnn_engine {
     size_t ts_off_edge[MAX_LAYERS] = {0}, ts_off_gate[MAX_LAYERS] = {0}, ts_off_cand[MAX_LAYERS] = {0};
     int ts_nc[2] = {0, 0}, ts_nblk[2] = {0, 0};      // [0]: DP-wide outputs (agg, candidate)  [1]: the 2*DP-wide gate output
     int ts_tiled_nc[2] = {-1, -1};                   // the N-block widths the tiled weights were made for
+    size_t off_pair = 0, off_vptr = 0, off_vsrc = 0, off_tvp = 0, off_vinfo = 0;   // streaming plan: (target,type) -> source table, virtual rows (pairs with several messages)
+    int ts_nv = 0;                                   // number of virtual rows of the current batch
+    DevBuf ts_virt;                                  // their operand image
     int tc_row_budget = 128, tc_kgs = 2048;   // tensor-core plan: no tile has more rows than the budget; <= 64 selects compact operand tiles
     int use_att = 0;                 // use_propagation_attention (sparse:170-196): fp32 path only
     DevBuf att_buf;                  // attention probabilities per target-CSR slot ([steps][M] when saving for backward, else [M])
@@ -579,7 +582,7 @@ int ggnn_destroy(ggnn_engine* e) {
     if (!e) return GGNN_OK;
     cudaSetDevice(e->device);
     e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
-    e->tc_weights.release(); e->tc_respre.release(); e->ts_weights.release(); e->ts_images.release(); e->ts_u.release(); e->err_flag.release(); e->dbg_buf.release();
+    e->tc_weights.release(); e->tc_respre.release(); e->ts_weights.release(); e->ts_images.release(); e->ts_u.release(); e->ts_virt.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
     if (e->stage_done) cudaEventDestroy(e->stage_done);
     if (e->ro_stage_done) cudaEventDestroy(e->ro_stage_done);
@@ -758,6 +761,18 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
         e->off_tslot = off;
         if (e->use_att) off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
     }
+    // streaming plan: per (target, type) pair the ONE node to copy from (or none / a virtual row), see ggnn_fwd_stream.cuh
+    int nv = 0; int64_t nvm = 0;
+    if (e->stream) {
+        for (size_t k = 0; k < (size_t)V * T; ++k)
+            if (counts[k + 1] >= 2) { ++nv; nvm += counts[k + 1]; }
+        e->off_pair = off; off = align_up(off + sizeof(int) * (size_t)std::max(ntiles, 1) * ts::TILE_M * T, 16);
+        e->off_vptr = off; off = align_up(off + sizeof(int) * (size_t)(nv + 1), 16);
+        e->off_vsrc = off; off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(nvm, 1), 16);
+        e->off_tvp = off;  off = align_up(off + sizeof(int) * (size_t)(ntiles + 1), 16);
+        e->off_vinfo = off; off = align_up(off + sizeof(int) * 8 * (size_t)std::max(nv, 1), 16);
+    }
+    e->ts_nv = nv;
     for (int t = 0; t < T; ++t) e->edges_of_type[t] = num_edges[t];
     if (e->stage_done) CU_TRY(e, cudaEventSynchronize(e->stage_done));   // previous upload may still be reading the stage
     CU_TRY(e, e->graph_stage.reserve(off));
@@ -772,6 +787,33 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
 
     // ---- pass 2: exclusive scan + stable fill (iteration in message order keeps the reference's order per row)
     fill_target_csr(V, T, adj, num_edges, counts, row_ptr, csr_src, csr_msg);
+    if (e->stream) {
+        int* pair = (int*)(base + e->off_pair);
+        int* vptr = (int*)(base + e->off_vptr);
+        int* vsrc = (int*)(base + e->off_vsrc);
+        int* tvp = (int*)(base + e->off_tvp);
+        int* vinfo = (int*)(base + e->off_vinfo);
+        int vid = 0, vm = 0, next_tile = 0;
+        vptr[0] = 0;
+        for (int v = 0; v < V; ++v) {
+            while (next_tile <= ntiles && v == next_tile * ts::TILE_M) tvp[next_tile++] = vid;
+            for (int t = 0; t < T; ++t) {
+                const size_t k = (size_t)v * T + t;
+                const int b = row_ptr[k], cnt = row_ptr[k + 1] - b;
+                if (cnt == 0) pair[k] = -1;
+                else if (cnt == 1) pair[k] = csr_src[b];
+                else {
+                    pair[k] = -(2 + vid);
+                    vinfo[8 * vid] = cnt;
+                    for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
+                    for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
+                    vptr[++vid] = vm;
+                }
+            }
+        }
+        while (next_tile <= ntiles) tvp[next_tile++] = vid;
+        for (size_t k = (size_t)V * T; k < (size_t)std::max(ntiles, 1) * ts::TILE_M * T; ++k) pair[k] = -1;
+    }
     if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
         int* trow = (int*)(base + e->off_trow);
         int* ttgt = (int*)(base + e->off_ttgt);
@@ -1175,42 +1217,56 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
 
     // shared-memory budgets
     const size_t avail = (e->max_smem > 2048 ? e->max_smem - 2048 : 0);
-    const int csr_cap = std::min((e->max_tile_msgs + 3) / 4 * 4, 8192);
-    const size_t csr_b = (size_t)((ts::TILE_M * T + 1 + 3) & ~3) * 4 + (size_t)csr_cap * 4 + (size_t)T * ts::TILE_M;
-    auto stages_for = [&](int NC, size_t budget) {
-        const size_t stage = (size_t)ts::A_STAGE_B + 64 * (size_t)NC;
-        return (int)std::min<size_t>(ts::MAX_NS, budget / stage);
-    };
+    const size_t csr_b = (size_t)ts::TILE_M * T * 4;   // the tile's (target, type) -> source table
+    CU_TRY(e, e->ts_virt.reserve((size_t)((e->ts_nv + ts::TILE_M - 1) / ts::TILE_M + 1) * NKS * ts::A_STAGE_B));
+    // a ring stage carries KS = 4 K-steps (the producer thread pays several hundred cycles per bulk copy whatever its size; measured on
+    // cfg4 / its 1/8 shard / cfg5: KS = 4 beats 2 beats 1 even where only two 96 KB stages fit)
+    const char* env_ks = getenv("GGNN_TS_KSTEPS");
+    const char* env_ns = getenv("GGNN_TS_STAGES");
+    auto ksteps_for = [&](int NC) { return std::max(1, std::min(env_ks ? atoi(env_ks) : 4, NKS)); };
+    auto stage_bytes = [&](int NC) { return (size_t)ksteps_for(NC) * ((size_t)ts::A_STAGE_B + 64 * (size_t)NC); };
+    auto stages_for = [&](int NC, size_t budget) { return (int)std::min<size_t>(env_ns ? (size_t)atoi(env_ns) : (size_t)ts::MAX_NS, budget / stage_bytes(NC)); };
     ts::StreamParams base;
     memset(&base, 0, sizeof base);
     base.V = V; base.D = D; base.DP = DP; base.T = T;
     base.nparts = e->precision == GGNN_PREC_BF16X3 ? 3 : 1;
     base.cell = e->cell; base.act = e->act; base.use_bias = e->use_bias; base.use_avg = e->use_avg;
-    base.row_ptr = (const int*)(g + e->off_row_ptr); base.csr_src = (const int*)(g + e->off_src);
     base.tile_mask = (const unsigned*)(g + e->off_mask);
+    base.pair_src = (const int*)(g + e->off_pair); base.vrow_ptr = (const int*)(g + e->off_vptr);
+    base.vsrc = (const int*)(g + e->off_vsrc); base.tile_vptr = (const int*)(g + e->off_tvp);
+    base.vinfo = (const int4*)(g + e->off_vinfo);
+    base.virt_img = (uint8_t*)e->ts_virt.ptr;
+    // pairs with several messages are pre-summed into virtual rows by the prologue of every gather launch (GGNN_TS_VIRT=0: summed inside
+    // the gather loop instead -- measured slower even on cfg5, where most pairs have two messages: 0.57 vs 0.50 ms)
+    base.virt_rows = 1;
+    if (const char* vr = getenv("GGNN_TS_VIRT")) base.virt_rows = vr[0] == '1';
     base.indeg = (const float*)(g + e->off_indeg); base.denom = (const float*)(g + e->off_denom);
-    base.csr_cap = csr_cap;
     base.drop_keep = e->drop_keep; base.drop_seed = e->drop_seed;
     base.error_flag = (int*)e->err_flag.ptr;
     // optional per-CTA phase stamps, one slice per launch (tools/stream_trace.py)
     long long* dbg = nullptr;
     const size_t dbg_slice = (size_t)ntiles * std::max(e->ts_nblk[0], e->ts_nblk[1]) * 16;
     if (getenv("GGNN_TS_DEBUG")) {
-        const size_t n = dbg_slice * (size_t)(3 * std::max(e->total_steps, 1));
+        const size_t n = (dbg_slice + 2048) * (size_t)(3 * std::max(e->total_steps, 1));
         CU_TRY(e, e->dbg_buf.reserve(n * sizeof(long long)));
         CU_TRY(e, cudaMemsetAsync(e->dbg_buf.ptr, 0, n * sizeof(long long), st));
         dbg = (long long*)e->dbg_buf.ptr;
     }
     int dbg_launch = 0;
-    auto next_dbg = [&]() -> long long* { return dbg ? dbg + dbg_slice * (size_t)(dbg_launch++) : nullptr; };
+    long long* dbg2_cur = nullptr;   // per launch: [grid][16] phase stamps, then [256][8] K-step timeline of CTA (0,0)
+    auto next_dbg = [&]() -> long long* {
+        if (!dbg) return nullptr;
+        long long* q = dbg + (dbg_slice + 2048) * (size_t)(dbg_launch++);
+        dbg2_cur = q + dbg_slice;
+        return q;
+    };
     auto tmem_cols = [](int NC) { int c = 32; while (c < NC) c *= 2; return c; };
     const int nc0 = e->ts_nc[0], nb0 = e->ts_nblk[0], nc1 = e->ts_nc[1], nb1 = e->ts_nblk[1];
-    // edge kernel: one CTA per SM, deep ring; TMA-fed kernels: two CTAs per SM when the grid is larger than the chip
+    // one CTA per SM for all three kernels: the whole shared memory is the ring
     const int ns_edge = stages_for(nc0, avail > csr_b ? avail - csr_b : 0);
-    auto fed_budget = [&](int nblk) { return ((long long)ntiles * nblk > e->num_sms) ? (avail + 2048) / 2 - 2048 : avail; };
-    const int ns_gate = stages_for(nc1, fed_budget(nb1)), ns_cand = stages_for(nc0, fed_budget(nb0));
+    const int ns_gate = stages_for(nc1, avail), ns_cand = stages_for(nc0, avail);
     if (ns_edge < 2 || ns_gate < 2 || ns_cand < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the streaming ring (DP=%d)", DP);
-    auto smem_of = [&](int NC, int ns, bool gather) { return (size_t)1024 + (size_t)ns * (ts::A_STAGE_B + 64 * (size_t)NC) + (gather ? csr_b : 0); };
+    auto smem_of = [&](int NC, int ns, bool gather) { return (size_t)1024 + (size_t)ns * stage_bytes(NC) + (gather ? csr_b : 0); };
     auto k_edge = ts::ggnn_stream_kernel<16, true>;
     auto k_fed = ts::ggnn_stream_kernel<8, false>;
     const size_t sm_edge = smem_of(nc0, ns_edge, true);
@@ -1243,10 +1299,10 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
             const size_t so = (size_t)gs * vd;
             // ---- aggregated messages
             ts::StreamParams p = base;
-            p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.tmem_cols = tmem_cols(nc0);
+            p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.ksteps = ksteps_for(nc0); p.tmem_cols = tmem_cols(nc0);
             p.g_img = img_in; p.w = wb + e->ts_off_edge[l]; p.kt_all = T * NKS;
             p.bias = e->use_bias ? e->w[l].edge_biases : nullptr;
-            p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs; p.dbg = next_dbg();
+            p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs; p.dbg = next_dbg(); p.dbg2 = dbg2_cur;
             k_edge<<<dim3(ntiles, nb0), 18 * 32, sm_edge, st>>>(p);
             ++e->last_launches;
             auto set_segs = [&](ts::StreamParams& q, const uint8_t* last_img) {
@@ -1257,20 +1313,20 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
             };
             if (gru) {
                 ts::StreamParams q = base;
-                q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.tmem_cols = tmem_cols(nc1);
+                q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.ksteps = ksteps_for(nc1); q.tmem_cols = tmem_cols(nc1);
                 set_segs(q, img_in);
                 q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_chk = chk_in; q.u_buf = u_chk; q.img_out = img_rh;
                 if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; q.sv_u = sv + 3 * per + so; }
-                q.gstep = gs; q.dbg = next_dbg();
+                q.gstep = gs; q.dbg = next_dbg(); q.dbg2 = dbg2_cur;
                 k_fed<<<dim3(ntiles, nb1), 10 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
                 ++e->last_launches;
             }
             ts::StreamParams c = base;
-            c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.tmem_cols = tmem_cols(nc0);
+            c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.ksteps = ksteps_for(nc0); c.tmem_cols = tmem_cols(nc0);
             set_segs(c, gru ? img_rh : img_in);
             c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_chk = chk_in; c.u_buf = u_chk; c.h_chk_out = chk_out; c.h_out = out; c.img_out = img_out;
             if (e->save) { if (gru) c.sv_c = sv + 4 * per + so; else c.sv_h = sv + so; }
-            c.gstep = gs; c.dbg = next_dbg();
+            c.gstep = gs; c.dbg = next_dbg(); c.dbg2 = dbg2_cur;
             k_fed<<<dim3(ntiles, nb0), 10 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
             ++e->last_launches;
             img_in = img_out; chk_in = chk_out;

@@ -5,7 +5,11 @@
 // One timestep (sparse:153-216) = three launches of ONE kernel template, each a 128-row x NC-column output tile
 // per CTA whose K dimension is streamed through a shared-memory ring, one UMMA K-step (16 columns) per stage:
 //   EPI_AGG   agg       = [A_0 | .. | A_{T-1}] . [W_0; ..; W_{T-1}]      A_t[v] = sum of h[src] over the type-t messages into v,
-//                         + indeg.B, / (deg + 1e-7)                       gathered by the worker warps straight into the ring (GATHER)
+//                         + indeg.B, / (deg + 1e-7)                       gathered by the worker warps straight into the ring (GATHER):
+//                         a (target, type) pair with ONE message is a 64-byte asynchronous copy (cp.async, completion on the stage's
+//                         mbarrier) of the source row's image chunks, a pair with none is zeros, and the few pairs with several
+//                         messages are summed once per launch into "virtual rows" (prologue) and then copied like the others --
+//                         no load latency sits between two K-steps of a gather warp
 //   EPI_GATE  [r | u]   = sigmoid([res.. | agg | h] . K_g + b_g)          writes r*h (operand image) and u
 //   EPI_CAND  h'        = u*h + (1-u)*act([res.. | agg | r*h] . K_c + b_c) (RNN: act([res.. | agg | h] . K + b))
 // Node-state operands live in HBM/L2 as bf16 hi/lo "images" in the canonical K-major no-swizzle UMMA layout, tile-major:
@@ -43,6 +47,7 @@ struct StreamParams {
     int V, D, DP, T;
     int NC;                // output columns per CTA (multiple of 16, <= 256); grid.y = number of N blocks
     int nstages;           // ring depth
+    int ksteps;            // K-steps (16 columns) per ring stage (4 unless the hidden size has fewer)
     int nparts;            // 3: bf16x3, 1: single bf16 MMA
     int tmem_cols;         // power of two >= max(32, NC)
     int epi;               // EPI_*
@@ -52,10 +57,14 @@ struct StreamParams {
     const uint8_t* seg[MAX_SEG];
     // ---- A operand, gathered (EPI_AGG): per present edge type a DP-wide segment of per-type source sums
     const uint8_t* g_img;        // image of the state the messages are gathered from (a row with one type-t message is a 64-byte copy)
-    const int* row_ptr;          // [V*T+1] target-keyed CSR
-    const int* csr_src;          // [M]
     const unsigned* tile_mask;   // [ntiles] bit t: some row of the tile receives a type-t message
-    int csr_cap;                 // capacity (ints) of the shared copy of the tile's source list; larger tiles read it from L2
+    const int* pair_src;         // [ntiles*128*T] per (target, type): -1 no message | source node (exactly one message) | -(2 + vid) several
+    const int* vrow_ptr;         // [NV+1] messages of the pairs with several messages (their "virtual rows"), CSR over vid ...
+    const int* vsrc;             // ... source nodes in message order
+    const int4* vinfo;           // [NV][2]: {count, src0, src1, src2 | src3 .. src6}: the first sources inline, one 32-byte load per virtual row
+    const int* tile_vptr;        // [ntiles+1] vid range of each tile
+    uint8_t* virt_img;           // image rows of the virtual rows (written in the prologue of every launch, row index = vid)
+    int virt_rows;               // 1: pairs with several messages are pre-summed into virtual rows (molecule batches); 0: summed in the gather loop
     // ---- B operand
     const uint8_t* w;            // [nblk][kt_all] stages of 64*NC bytes: [hi: 2 k-groups x NC x 16 B | lo: same]
     int kt_all;                  // K-steps per N block in `w`
@@ -73,6 +82,7 @@ struct StreamParams {
     float drop_keep; unsigned long long drop_seed; int gstep;
     int* error_flag;
     long long* dbg;   // optional per-CTA phase stamps [grid.y][grid.x][16] (GGNN_TS_DEBUG=1), or nullptr
+    long long* dbg2;  // optional per-K-step timeline of CTA (0,0): [256][8] clocks (issuer: B landed, A landed, issued | gather: start, stage free, issued | producer: stage free, issued)
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -103,8 +113,45 @@ __device__ __forceinline__ void img_store_chunk(uint8_t* img, int NKS, int tile,
     *reinterpret_cast<uint4*>(p + 4096) = lo;
 }
 
+// Sum of the image rows of one (target, type) pair with several messages, one K-step (16 columns), fp32 in message order, re-split:
+// (hi k-group 0, hi k-group 1, lo k-group 0, lo k-group 1).  `info` = vinfo[2*vid..]: {count, src0..src6}; longer lists continue in vsrc.
+__device__ __forceinline__ void sum_pair_sources(const uint8_t* __restrict__ g_img, int NKS, int ks, const int4& i0, const int4& i1,
+                                                 const int* __restrict__ vsrc_tail, uint4& h0, uint4& h1, uint4& l0, uint4& l1) {
+    auto img_row = [&](int src) { return g_img + ((size_t)(src >> 7) * NKS + ks) * A_STAGE_B + (size_t)(src & 127) * 16; };
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+    auto add_row = [&](const uint8_t* sp) {
+        const uint4 y0 = __ldcg(reinterpret_cast<const uint4*>(sp)), y1 = __ldcg(reinterpret_cast<const uint4*>(sp + 2048));
+        const uint4 y2 = __ldcg(reinterpret_cast<const uint4*>(sp + 4096)), y3 = __ldcg(reinterpret_cast<const uint4*>(sp + 6144));
+        tc::unpack8_add(y0, a0, 1.0f); tc::unpack8_add(y2, a0, 1.0f);
+        tc::unpack8_add(y1, a1, 1.0f); tc::unpack8_add(y3, a1, 1.0f);
+    };
+    const int cnt = i0.x;
+    {   // the first two sources are always there: request both before the first add
+        const uint8_t* s0 = img_row(i0.y);
+        const uint8_t* s1 = img_row(i0.z);
+        const uint4 x0 = __ldcg(reinterpret_cast<const uint4*>(s0)), x1 = __ldcg(reinterpret_cast<const uint4*>(s0 + 2048));
+        const uint4 x2 = __ldcg(reinterpret_cast<const uint4*>(s0 + 4096)), x3 = __ldcg(reinterpret_cast<const uint4*>(s0 + 6144));
+        const uint4 y0 = __ldcg(reinterpret_cast<const uint4*>(s1)), y1 = __ldcg(reinterpret_cast<const uint4*>(s1 + 2048));
+        const uint4 y2 = __ldcg(reinterpret_cast<const uint4*>(s1 + 4096)), y3 = __ldcg(reinterpret_cast<const uint4*>(s1 + 6144));
+        tc::unpack8_add(x0, a0, 1.0f); tc::unpack8_add(x2, a0, 1.0f);
+        tc::unpack8_add(x1, a1, 1.0f); tc::unpack8_add(x3, a1, 1.0f);
+        tc::unpack8_add(y0, a0, 1.0f); tc::unpack8_add(y2, a0, 1.0f);
+        tc::unpack8_add(y1, a1, 1.0f); tc::unpack8_add(y3, a1, 1.0f);
+    }
+    if (cnt > 2) add_row(img_row(i0.w));
+    if (cnt > 3) add_row(img_row(i1.x));
+    if (cnt > 4) add_row(img_row(i1.y));
+    if (cnt > 5) add_row(img_row(i1.z));
+    if (cnt > 6) add_row(img_row(i1.w));
+    for (int m = 7; m < cnt; ++m) add_row(img_row(vsrc_tail[m]));   // rare tail, in message order
+    tc::split8(a0, h0, l0);
+    tc::split8(a1, h1, l1);
+}
+
 template <int NWORK, bool GATHER>
-__global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_kernel(const __grid_constant__ StreamParams p) {
+__global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[MAX_NS];    // B (and TMA-fed A) bytes landed
     __shared__ __align__(8) uint64_t bar_afull[MAX_NS];   // gathered A written (GATHER)
@@ -117,21 +164,20 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, nb = blockIdx.y;
-    const int D = p.D, DP = p.DP, T = p.T, NC = p.NC, NS = p.nstages;
+    const int D = p.D, DP = p.DP, T = p.T, NC = p.NC, NS = p.nstages, KS = p.ksteps;
     const int NKS = DP >> 4;
+    const int GPS = (NKS + KS - 1) / KS;              // stages ("K groups") per K segment; the last one of a segment may be partial
     const int row0 = tile * TILE_M;
     const int rows = min(TILE_M, p.V - row0);
-    const uint32_t B_STAGE_B = 64u * (uint32_t)NC;
-    const uint32_t STAGE_B = (uint32_t)A_STAGE_B + B_STAGE_B;
+    const uint32_t B_STEP_B = 64u * (uint32_t)NC;    // one K-step of the B operand: [hi: 2 k-groups x NC x 16 B | lo: same]
+    const uint32_t A_REGION_B = (uint32_t)KS * A_STAGE_B;
+    const uint32_t STAGE_B = A_REGION_B + (uint32_t)KS * B_STEP_B;   // a stage = KS K-steps of A, then KS K-steps of B
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    int* sPtr = reinterpret_cast<int*>(smem + (size_t)NS * STAGE_B);    // [128*T + 1] tile-relative CSR row offsets (GATHER)
-    int* sSrc = sPtr + ((TILE_M * T + 1 + 3) & ~3);                     // [csr_cap] global source ids
-    uint8_t* sPerm = reinterpret_cast<uint8_t*>(sSrc + p.csr_cap);       // [T][128] rows of the tile ordered: >= 2 type-t messages | exactly 1 | none
-    __shared__ int s_n0[32], s_n1[32];                                   // per present type: rows with >= 2 messages, rows with exactly 1
+    int* sPair = reinterpret_cast<int*>(smem + (size_t)NS * STAGE_B);   // [128*T] the tile's slice of pair_src (GATHER)
 
     if (tid == 0) {
         s_abort = 0;
-        for (int i = 0; i < MAX_NS; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_afull[i], 4); tc::mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < MAX_NS; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_afull[i], TILE_M); tc::mbar_init(&bar_empty[i], 1); }
         tc::mbar_init(&bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         int n = 0;
@@ -150,32 +196,40 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
     tc::tc_fence_after();
     const uint32_t tmem = s_tmem;
     volatile int* abortp = &s_abort;
-    const int nk = GATHER ? s_ntypes * NKS : p.nseg * NKS;   // K-steps of this tile
+    const int nsegs = GATHER ? s_ntypes : p.nseg;    // K segments of this tile (present edge types / operand images)
+    const int ng = nsegs * GPS;                        // stages to stream
+    const int nk = nsegs * NKS;                        // K-steps in total
 
     if (warp == 0) {
         // =============================================================================== PRODUCER (one thread)
+        // Issuing a bulk copy costs this thread several hundred cycles whatever its size, so a stage carries KS K-steps: the A operand of
+        // those K-steps is ONE contiguous piece of the image, their B operand ONE contiguous piece of the pre-tiled weights.
         if (lane == 0) {
             bool ok = true;
-            const uint8_t* wb = p.w + (size_t)nb * p.kt_all * B_STAGE_B;
+            const uint8_t* wb = p.w + (size_t)nb * p.kt_all * B_STEP_B;
             long long waited = 0;
-            for (int k = 0; k < nk && ok; ++k) {
-                const int s = k % NS, it = k / NS;
-                if (it > 0) {
+            int sg = 0, j = 0, s = 0, round = 0;
+            for (int g = 0; g < ng && ok; ++g) {
+                if (round > 0) {
                     const long long w0 = p.dbg ? clock64() : 0;
-                    if (!tc::mbar_wait(&bar_empty[s], (uint32_t)(it - 1) & 1u, abortp)) { ok = false; break; }
+                    if (!tc::mbar_wait(&bar_empty[s], (uint32_t)(round - 1) & 1u, abortp)) { ok = false; break; }
                     if (p.dbg) waited += clock64() - w0;
                 }
+                long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256) ? p.dbg2 + g * 8 : nullptr;
+                if (d2) d2[6] = clock64();
+                const int ks0 = j * KS, nks = min(KS, NKS - ks0);
                 uint8_t* st = smem + (size_t)s * STAGE_B;
+                const int seg_k0 = (GATHER ? s_types[sg] : sg) * NKS + ks0;   // first K-step of the stage in the weight stream
                 if (GATHER) {
-                    const int kk = s_types[k / NKS] * NKS + (k % NKS);
-                    tc::mbar_arrive_expect_tx(&bar_full[s], B_STAGE_B);
-                    tc::bulk_copy_g2s(st + A_STAGE_B, wb + (size_t)kk * B_STAGE_B, B_STAGE_B, &bar_full[s]);
+                    tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)nks * B_STEP_B);
                 } else {
-                    const int sg = k / NKS, ks = k - sg * NKS;
-                    tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)A_STAGE_B + B_STAGE_B);
-                    tc::bulk_copy_g2s(st, p.seg[sg] + ((size_t)tile * NKS + ks) * A_STAGE_B, A_STAGE_B, &bar_full[s]);
-                    tc::bulk_copy_g2s(st + A_STAGE_B, wb + (size_t)k * B_STAGE_B, B_STAGE_B, &bar_full[s]);
+                    tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)nks * ((uint32_t)A_STAGE_B + B_STEP_B));
+                    tc::bulk_copy_g2s(st, p.seg[sg] + ((size_t)tile * NKS + ks0) * A_STAGE_B, (uint32_t)nks * A_STAGE_B, &bar_full[s]);
                 }
+                tc::bulk_copy_g2s(st + A_REGION_B, wb + (size_t)seg_k0 * B_STEP_B, (uint32_t)nks * B_STEP_B, &bar_full[s]);
+                if (d2) d2[7] = clock64();
+                if (++j == GPS) { j = 0; ++sg; }
+                if (++s == NS) { s = 0; ++round; }
             }
             if (!ok) atomicExch(p.error_flag, 13);
             if (p.dbg) p.dbg[((size_t)nb * gridDim.x + tile) * 16 + 4] = waited;
@@ -188,33 +242,42 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
         const uint64_t descB = tc::make_desc(0, 16u * (uint32_t)NC, 128);
         const uint32_t idesc = tc::make_idesc_bf16(NC);
         const uint32_t b_lo16 = (32u * (uint32_t)NC) >> 4;
-        const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = STAGE_B >> 4;
+        const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = STAGE_B >> 4, aregion16 = A_REGION_B >> 4, bstep16 = B_STEP_B >> 4;
         const uint32_t tm_d = __shfl_sync(0xffffffffu, tmem, 0);
         long long waited_b = 0, waited_a = 0;
-        for (int k = 0; k < nk && ok; ++k) {
-            const int s = k % NS;
-            const uint32_t par = (uint32_t)(k / NS) & 1u;
+        int j = 0, s = 0;
+        uint32_t par = 0;
+        for (int g = 0; g < ng && ok; ++g) {
             const long long w0 = p.dbg ? clock64() : 0;
             if (!tc::mbar_wait(&bar_full[s], par, abortp)) ok = false;
             const long long w1 = p.dbg ? clock64() : 0;
             if (GATHER && ok && !tc::mbar_wait(&bar_afull[s], par, abortp)) ok = false;
             if (p.dbg) { waited_b += w1 - w0; waited_a += clock64() - w1; }
+            long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256 && lane == 0) ? p.dbg2 + g * 8 : nullptr;
+            if (d2) { d2[0] = w1; d2[1] = clock64(); }
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
+            if (GATHER) tc::fence_async_smem();   // the gathered A stage was written through the generic proxy (cp.async / st.shared): order it before the MMA's reads
             tc::tc_fence_after();
+            const int nks = min(KS, NKS - j * KS);
             if (tc::elect_one()) {
-                const uint32_t a16 = smem16 + (uint32_t)s * stage16, b16 = a16 + (A_STAGE_B >> 4);
-                const uint64_t ah = descA | (uint64_t)a16, al = descA | (uint64_t)(a16 + (4096u >> 4));
-                const uint64_t bh = descB | (uint64_t)b16, bl = descB | (uint64_t)(b16 + b_lo16);
-                tc::umma_bf16(tm_d, ah, bh, idesc, k > 0 ? 1u : 0u);
-                if (x3) {
-                    tc::umma_bf16(tm_d, ah, bl, idesc, 1u);
-                    tc::umma_bf16(tm_d, al, bh, idesc, 1u);
+                const uint32_t a16 = smem16 + (uint32_t)s * stage16, b16 = a16 + aregion16;
+                for (int i = 0; i < nks; ++i) {
+                    const uint64_t ah = descA | (uint64_t)(a16 + (uint32_t)i * (A_STAGE_B >> 4)), al = ah + (4096u >> 4);
+                    const uint64_t bh = descB | (uint64_t)(b16 + (uint32_t)i * bstep16), bl = bh + b_lo16;
+                    tc::umma_bf16(tm_d, ah, bh, idesc, (g > 0 || i > 0) ? 1u : 0u);
+                    if (x3) {
+                        tc::umma_bf16(tm_d, ah, bl, idesc, 1u);
+                        tc::umma_bf16(tm_d, al, bh, idesc, 1u);
+                    }
                 }
                 tc::umma_commit(&bar_empty[s]);
-                if (k == nk - 1) tc::umma_commit(&bar_acc);
+                if (g == ng - 1) tc::umma_commit(&bar_acc);
             }
             __syncwarp();
+            if (d2) d2[2] = clock64();
+            if (++j == GPS) j = 0;
+            if (++s == NS) { s = 0; par ^= 1u; }
         }
         if (!ok && lane == 0) atomicExch(p.error_flag, 12);
         if (p.dbg && lane == 0) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[5] = waited_b; d[6] = waited_a; }
@@ -237,104 +300,92 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
         if (GATHER) {
             constexpr int NG = NWORK / 4;             // gather groups (4 warps = 128 rows each)
             const int grp = wi >> 2;
-            const int gi = (wi & 3) * 32 + lane;      // index within the group: which entry of the per-type row order this thread serves
-            // ---- the tile's CSR slice -> shared memory
-            const int base = p.row_ptr[(size_t)row0 * T];
-            const int nptr = rows * T + 1;
+            const int gi = (wi & 3) * 32 + lane;      // the tile row this thread gathers
             const int wt = tid - 64;
-            for (int i = wt; i < TILE_M * T + 1; i += NWORK * 32) sPtr[i] = p.row_ptr[(size_t)row0 * T + min(i, nptr - 1)] - base;
-            const int mt = p.row_ptr[(size_t)(row0 + rows) * T] - base;
-            const bool cached = mt <= p.csr_cap;
-            if (cached) for (int i = wt; i < mt; i += NWORK * 32) sSrc[i] = p.csr_src[base + i];
-            asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
-            // ---- per present type: order the rows by message count class so that whole warps take the same path.  Only ~1/4 of the
-            // (row, type) pairs of a molecule batch have a message at all, and most of those exactly one.
-            for (int ti = wi; ti < s_ntypes; ti += NWORK) {
-                const int t = s_types[ti];
-                int cls[4], n0 = 0, n1 = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = i * 32 + lane;
-                    const int cnt = r < rows ? sPtr[r * T + t + 1] - sPtr[r * T + t] : 0;
-                    cls[i] = cnt >= 2 ? 0 : (cnt == 1 ? 1 : 2);
-                    n0 += __popc(__ballot_sync(0xffffffffu, cls[i] == 0));
-                    n1 += __popc(__ballot_sync(0xffffffffu, cls[i] == 1));
+            // ---- the tile's (target, type) -> source table
+            for (int i = wt; i < TILE_M * T; i += NWORK * 32) sPair[i] = p.pair_src[(size_t)row0 * T + i];
+            // ---- virtual rows: the pairs of this tile with several messages, summed in message order (fp32), re-split, stored as image rows.
+            // (Batches where most pairs have several messages -- dense graphs -- sum them in the gather loop instead: p.virt_rows == 0.)
+            if (p.virt_rows) {
+                const int v0 = p.tile_vptr[tile], nv = p.tile_vptr[tile + 1] - v0;
+                for (int task = wt; task < nv * NKS; task += NWORK * 32) {
+                    const int vid = v0 + task / NKS, ks = task % NKS;
+                    const int4 i0 = __ldg(p.vinfo + 2 * (size_t)vid), i1 = __ldg(p.vinfo + 2 * (size_t)vid + 1);
+                    uint4 h0, l0, h1, l1;
+                    sum_pair_sources(p.g_img, NKS, ks, i0, i1, p.vsrc + p.vrow_ptr[i0.x > 7 ? vid : 0], h0, h1, l0, l1);
+                    uint8_t* vp = p.virt_img + ((size_t)(vid >> 7) * NKS + ks) * A_STAGE_B + (size_t)(vid & 127) * 16;
+                    *reinterpret_cast<uint4*>(vp) = h0;
+                    *reinterpret_cast<uint4*>(vp + 2048) = h1;
+                    *reinterpret_cast<uint4*>(vp + 4096) = l0;
+                    *reinterpret_cast<uint4*>(vp + 6144) = l1;
                 }
-                int run[3] = {0, n0, n0 + n1};
-                const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned m = __ballot_sync(0xffffffffu, cls[i] == c);
-                        if (cls[i] == c) sPerm[ti * TILE_M + run[c] + __popc(m & lt)] = (uint8_t)(i * 32 + lane);
-                        run[c] += __popc(m);
-                    }
-                }
-                if (lane == 0) { s_n0[ti] = n0; s_n1[ti] = n1; }
+                __threadfence();   // the copies below read these rows back through L2 (cp.async.cg)
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
-            const int* srcs = cached ? sSrc : p.csr_src + base;
             if (stamp) t_setup = clock64();
-            for (int k = grp; k < nk && ok; k += NG) {
+            // group `grp` fills stages grp, grp + NGE, ...: every row is an asynchronous 64-byte copy per K-step (or zeros).
+            // No more groups than ring stages: a parity wait on a stage's barrier is only sound if the waiter cannot be two phases ahead
+            // of it, and group X waiting for round r of a stage has (through its previous stage, NGE K-groups back) only seen round r-2
+            // complete when NS >= NGE.  Surplus groups idle (deep K-step stages leave room for 2-3 ring slots only).
+            const int NGE = min(NG, NS);
+            int sg = 0, j = grp;
+            while (j >= GPS) { j -= GPS; ++sg; }
+            for (int g = grp < NGE ? grp : ng; g < ng && ok; g += NGE) {
                 const long long c0 = stamp ? clock64() : 0;
-                const int s = k % NS, it = k / NS;
-                const int ti = k / NKS, ks = k - ti * NKS;
-                const int t = s_types[ti];
-                const int prow = sPerm[ti * TILE_M + gi];
-                const int n0 = s_n0[ti], n01 = n0 + s_n1[ti];
-                uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0, o2 = o0, o3 = o0;   // hi k-group 0 | hi k-group 1 | lo k-group 0 | lo k-group 1
-                if (gi < n01) {
-                    const int beg = sPtr[prow * T + t];
-                    {
-                        const int src = srcs[beg];
-                        const uint8_t* sp = p.g_img + ((size_t)(src >> 7) * NKS + ks) * A_STAGE_B + (size_t)(src & 127) * 16;
-                        o0 = __ldcg(reinterpret_cast<const uint4*>(sp));
-                        o1 = __ldcg(reinterpret_cast<const uint4*>(sp + 2048));
-                        o2 = __ldcg(reinterpret_cast<const uint4*>(sp + 4096));
-                        o3 = __ldcg(reinterpret_cast<const uint4*>(sp + 6144));
-                    }
-                    if (gi < n0) {   // two or more messages: fp32 sum in message order, then re-split (two source rows in flight)
-                        const int end = sPtr[prow * T + t + 1];
-                        auto img_row = [&](int m) {
-                            const int src = srcs[m];
-                            return p.g_img + ((size_t)(src >> 7) * NKS + ks) * A_STAGE_B + (size_t)(src & 127) * 16;
-                        };
-                        const uint8_t* sp1 = img_row(beg + 1);
-                        uint4 q0 = __ldcg(reinterpret_cast<const uint4*>(sp1)), q1 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 2048));
-                        uint4 q2 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 4096)), q3 = __ldcg(reinterpret_cast<const uint4*>(sp1 + 6144));
-                        float a0[8], a1[8];
-                        unpack8(o0, a0); unpack8(o1, a1);
-                        tc::unpack8_add(o2, a0, 1.0f); tc::unpack8_add(o3, a1, 1.0f);
-                        for (int m = beg + 2; ; ++m) {
-                            const uint4 c0 = q0, c1 = q1, c2 = q2, c3 = q3;
-                            if (m < end) {
-                                const uint8_t* sp = img_row(m);
-                                q0 = __ldcg(reinterpret_cast<const uint4*>(sp)); q1 = __ldcg(reinterpret_cast<const uint4*>(sp + 2048));
-                                q2 = __ldcg(reinterpret_cast<const uint4*>(sp + 4096)); q3 = __ldcg(reinterpret_cast<const uint4*>(sp + 6144));
-                            }
-                            tc::unpack8_add(c0, a0, 1.0f); tc::unpack8_add(c2, a0, 1.0f);
-                            tc::unpack8_add(c1, a1, 1.0f); tc::unpack8_add(c3, a1, 1.0f);
-                            if (m >= end) break;
-                        }
-                        tc::split8(a0, o0, o2);
-                        tc::split8(a1, o1, o3);
-                    }
-                }
+                const int s = g % NS, round = g / NS;
+                long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256 && gi == 0) ? p.dbg2 + g * 8 : nullptr;
+                if (d2) d2[3] = clock64();
+                const int ks0 = j * KS, nks = min(KS, NKS - ks0);
+                const int ps = sPair[gi * T + s_types[sg]];
+                const uint8_t* sp = nullptr;
+                if (ps >= 0) sp = p.g_img + ((size_t)(ps >> 7) * NKS + ks0) * A_STAGE_B + (size_t)(ps & 127) * 16;
+                else if (ps < -1 && p.virt_rows) { const int vid = -(ps + 2); sp = p.virt_img + ((size_t)(vid >> 7) * NKS + ks0) * A_STAGE_B + (size_t)(vid & 127) * 16; }
                 const long long c1 = stamp ? clock64() : 0;
-                if (it > 0 && !tc::mbar_wait(&bar_empty[s], (uint32_t)(it - 1) & 1u, abortp)) { ok = false; }
-                ok = __all_sync(0xffffffffu, ok);
-                if (!ok) break;
+                // one warp of the group polls the stage's barrier, the other three block on a hardware barrier (polling warps cost issue slots)
+                if (round > 0 && (wi & 3) == 0 && !tc::mbar_wait(&bar_empty[s], (uint32_t)(round - 1) & 1u, abortp)) *abortp = 1;
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                if (*abortp) { ok = false; break; }
                 const long long c2 = stamp ? clock64() : 0;
-                uint8_t* ap = smem + (size_t)s * STAGE_B + (size_t)prow * 16;
-                *reinterpret_cast<uint4*>(ap) = o0;
-                *reinterpret_cast<uint4*>(ap + 2048) = o1;
-                *reinterpret_cast<uint4*>(ap + 4096) = o2;
-                *reinterpret_cast<uint4*>(ap + 6144) = o3;
-                tc::fence_async_smem();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bar_afull[s]);
+                if (d2) d2[4] = clock64();
+                uint8_t* ap = smem + (size_t)s * STAGE_B + (size_t)gi * 16;
+                const uint32_t bar = smem_u32(&bar_afull[s]);
+                if (sp) {
+                    uint32_t dst = smem_u32(ap);
+                    for (int i = 0; i < nks; ++i, dst += A_STAGE_B, sp += A_STAGE_B) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(sp) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 2048u), "l"(sp + 2048) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 4096u), "l"(sp + 4096) : "memory");
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 6144u), "l"(sp + 6144) : "memory");
+                    }
+                    // one arrival on the stage's barrier when this thread's copies have landed (the barrier counts 128 threads)
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+                } else if (ps < -1) {   // several messages, summed here (dense graphs): loads -> registers -> stage
+                    const int vid = -(ps + 2);
+                    const int4 i0 = __ldg(p.vinfo + 2 * (size_t)vid), i1 = __ldg(p.vinfo + 2 * (size_t)vid + 1);
+                    const int* tail = p.vsrc + p.vrow_ptr[i0.x > 7 ? vid : 0];
+                    for (int i = 0; i < nks; ++i, ap += A_STAGE_B) {
+                        uint4 h0, l0, h1, l1;
+                        sum_pair_sources(p.g_img, NKS, ks0 + i, i0, i1, tail, h0, h1, l0, l1);
+                        *reinterpret_cast<uint4*>(ap) = h0;
+                        *reinterpret_cast<uint4*>(ap + 2048) = h1;
+                        *reinterpret_cast<uint4*>(ap + 4096) = l0;
+                        *reinterpret_cast<uint4*>(ap + 6144) = l1;
+                    }
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                } else {
+                    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                    for (int i = 0; i < nks; ++i, ap += A_STAGE_B) {
+                        *reinterpret_cast<uint4*>(ap) = z;
+                        *reinterpret_cast<uint4*>(ap + 2048) = z;
+                        *reinterpret_cast<uint4*>(ap + 4096) = z;
+                        *reinterpret_cast<uint4*>(ap + 6144) = z;
+                    }
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+                }
+                if (d2) d2[5] = clock64();
                 if (stamp) { const long long c3 = clock64(); g_load += c1 - c0; g_wait += c2 - c1; g_tail += c3 - c2; }
+                j += NGE;
+                while (j >= GPS) { j -= GPS; ++sg; }
             }
             if (stamp) t_gather = clock64();
         }
@@ -360,9 +411,10 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, GATHER ? 1 : 2) ggnn_stream_
             }
         };
         if (!GATHER) load_ops(cgp, hA, uA);
-        if (ok && nk > 0) {
-            if (!tc::mbar_wait(&bar_acc, 0, abortp)) ok = false;
-            ok = __all_sync(0xffffffffu, ok);
+        if (nk > 0) {   // worker warp 0 polls for the accumulator, the others block on the hardware barrier behind it
+            if (wi == 0 && ok && !tc::mbar_wait(&bar_acc, 0, abortp)) *abortp = 1;
+            asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
+            if (*abortp) ok = false;
             tc::tc_fence_after();
         }
         if (stamp) t_acc = clock64();

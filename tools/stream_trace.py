@@ -13,7 +13,8 @@ from gated_graph_neural_network_samples_b200 import workloads
 from gated_graph_neural_network_samples_b200.engine import PropagationEngine
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
-w = workloads.build(cfg)
+shard = os.environ.get("GGNN_BENCH_SHARD")
+w = workloads.build(cfg, shard=tuple(int(x) for x in shard.split(",")) if shard else None)
 eng = PropagationEngine(w["engine_params"], w["num_edge_types"], precision="bf16x3")
 eng.set_weights([{k: torch.from_numpy(v).cuda() for k, v in lw.items()} for lw in w["weights"]])
 eng.set_graph_sparse(w["adjacency_lists"], w["num_incoming_edges_per_type"])
@@ -29,7 +30,8 @@ slice_ = ntiles * max(nb) * 16
 steps = sum(w["engine_params"]["layer_timesteps"])
 gru = w["engine_params"].get("graph_rnn_cell", "GRU").lower() == "gru"
 per_step = 3 if gru else 2
-n = slice_ * per_step * steps
+stride = slice_ + 2048
+n = stride * per_step * steps
 buf = np.zeros(n, np.int64)
 eng._check(eng.lib.ggnn_debug_trace(eng._h, buf.ctypes.data, n))
 names = ["edge", "gate", "cand"] if gru else ["edge", "cand"]
@@ -38,6 +40,20 @@ print("%-6s %5s %9s %9s %9s %9s | %9s %9s %9s  (median cycles over CTAs; start s
 for li in range(per_step * steps):
     kind = names[li % per_step]
     ctas = ntiles * (nb[1] if kind == "gate" else nb[0])
-    d = buf[li * slice_: li * slice_ + ctas * 16].reshape(ctas, 16)
+    d = buf[li * stride: li * stride + ctas * 16].reshape(ctas, 16)
     med = lambda c: int(np.median(d[:, c]))
     print("%-6s %5d %9d %9d %9d %9d | %9d %9d %9d | setup %6d load %7d wait %7d tail %7d" % (kind, med(7), med(1) if kind == "edge" else 0, med(2), med(3), med(3) - med(2), med(4), med(5), med(6), med(11), med(8), med(9), med(10)))
+
+# K-step timeline of CTA (0,0) for the first launch of each kind (clocks relative to the CTA's first stamp)
+for li in range(per_step):
+    tl = buf[li * stride + slice_: li * stride + slice_ + 2048].reshape(256, 8)
+    nz = tl[tl > 0]
+    if nz.size == 0:
+        continue
+    t0 = nz.min()
+    print("\n%s launch, CTA (0,0): k | issuer: B landed, A landed, issued | gather: start, stage free, copies issued | producer: stage free, TMA issued" % names[li])
+    for k in list(range(0, 24)) + list(range(64, 72)):
+        r = tl[k]
+        if not r.any():
+            continue
+        print("%4d | %7d %7d %7d | %7d %7d %7d | %7d %7d" % tuple([k] + [int(x - t0) if x > 0 else -1 for x in r]))
