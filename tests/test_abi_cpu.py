@@ -151,9 +151,18 @@ def test_host_tile_plan_keeps_components_whole_and_fills_the_sms():
                 assert ("compact" in text) == expect_compact, text
                 if expect_compact:
                     assert len(ts) - 1 <= 148 and budget <= 64                 # cut small enough to use (almost) every SM
-    # one 300-node ring: larger than any tile -> one launch per step over 128-row tiles
+    # one 300-node ring: larger than any tile -> fixed 128-row tiles; tensor precisions take the streaming plan, fp32 one launch per step
     ring = np.stack([np.arange(300), (np.arange(300) + 1) % 300], 1).astype(np.int32)
     ts, text = plan([ring], 300)
-    assert "GLOBAL" in text and list(ts) == [0, 128, 256, 300]
+    assert "STREAM" in text and list(ts) == [0, 128, 256, 300]
+    ts, text = plan([ring], 300, precision=0)
+    assert "GLOBAL" in text
+    # hidden sizes above 128 stream whatever the component sizes, with N blocks of at least 128 columns
+    mols = synthetic.make_molecules(64, seed=1, num_bond_types=8)
+    b = packing.pack_sparse_batch(packing.process_raw_graphs_sparse(mols), 256, 8)
+    V = b["initial_node_representation"].shape[0]
+    ts, text = plan(b["adjacency_lists"], V, D=256)
+    assert "STREAM" in text and list(ts[:-1]) == list(range(0, V, 128)) and ts[-1] == V
+    assert "agg/cand=2x128" in text and "gate=4x128" in text, text          # 10 tiles: N is split so that more SMs get work
     ts, text = plan([np.zeros((0, 2), np.int32)], 0)
     assert list(ts) == [0]
