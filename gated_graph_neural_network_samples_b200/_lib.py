@@ -78,6 +78,8 @@ def load(build_if_missing: bool = True):
         except Exception as ex:  # no nvcc on the box: use the shipped .so if there is one
             if not os.path.exists(path):
                 raise RuntimeError("libggnn_b200.so is missing and could not be built: %s" % ex)
+            import warnings
+            warnings.warn("libggnn_b200.so is OLDER than its sources and could not be rebuilt (%s): running the stale binary" % str(ex)[:200])
     if not os.path.exists(path):
         raise RuntimeError("libggnn_b200.so not found at %s -- run `python -m gated_graph_neural_network_samples_b200._build`"
                            % path)

@@ -65,12 +65,16 @@ class DenseGGNNChemModel(ChemModel):
         self.engine.set_save_for_backward(torch.is_grad_enabled())
         self.engine.set_graph_dense(adj)
         keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
+        edge_weights = self.weights['edge_weights']
         if keep < 1.0:
-            # the dense reference draws a fresh weight-dropout mask per timestep and type (dense:104); not supported
-            raise Exception("edge-weight dropout inside the dense propagation is not supported by the B200 engine")
+            # dense:104 builds a fresh tf.nn.dropout on W[e] per timestep and type.  The engine takes the weights once per sess.run, so the
+            # mask is drawn once per batch (every type its own slice of it) and shared by the timesteps -- the sparse model's behaviour
+            # (sparse:91).  A deliberate deviation: the reference feeds this slot with graph_state_dropout_keep_prob
+            # (dense:222), so refusing it would make state dropout unusable in dense training.
+            edge_weights = torch.nn.functional.dropout(edge_weights, p=1.0 - keep, training=True)
         state_keep = float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0))          # DropoutWrapper, dense:89
         self.engine.set_state_dropout(state_keep, int(torch.randint(0, 2 ** 62, (1,)).item()) if state_keep < 1.0 else 0)
-        flat, lay = [self.weights['edge_weights']], {'edge_weights': 0}
+        flat, lay = [edge_weights], {'edge_weights': 0}
         if 'edge_biases' in self.weights:
             lay['edge_biases'] = len(flat); flat.append(self.weights['edge_biases'].view(T, D))
         for k, t in self.weights['node_gru'].items():
@@ -108,6 +112,14 @@ class DenseGGNNChemModel(ChemModel):
         if is_training_data:
             for _, bucket in bucketed.items():
                 np.random.shuffle(bucket)
+                # dense:153-158: beyond the first len(bucket) * ratio examples of the (shuffled) bucket the task's label is dropped
+                for task_id in self.params['task_ids']:
+                    ratio = self.params.get('task_sample_ratios', {}).get(str(task_id))
+                    if ratio is not None:
+                        for ex_id in range(int(len(bucket) * ratio), len(bucket)):
+                            targets = [list(t) for t in bucket[ex_id]['targets']]
+                            targets[task_id][0] = None
+                            bucket[ex_id] = dict(bucket[ex_id], targets=targets)
         bucket_at_step = [[idx for _ in range(len(b) // self.params['batch_size'])] for idx, b in bucketed.items()]
         bucket_at_step = [x for y in bucket_at_step for x in y]
         return (bucketed, bucket_sizes, bucket_at_step)

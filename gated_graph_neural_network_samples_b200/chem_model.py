@@ -278,6 +278,9 @@ class ChemModel(object):
             acc_sum += np.array([float(a.detach()) for a in batch_accs]) * n
             print("Running %s, batch %i (has %i graphs). Loss so far: %.4f" % (epoch_name, steps - 1, n, loss_sum / graphs_seen), end='\r')
         graphs_seen = max(graphs_seen, 1)
+        eng = getattr(self, 'engine', None)
+        if eng is not None and hasattr(eng, 'sync_check'):
+            eng.sync_check()   # a (bounded) barrier timeout inside a tensor-core kernel is only written to a flag: surface it once per epoch
         accuracies = acc_sum / graphs_seen
         return (loss_sum / graphs_seen, accuracies, accuracies / self.CHEMICAL_ACCURACIES[self.params["task_ids"]],
                 graphs_seen / (time.time() - t_begin), steps)

@@ -29,12 +29,13 @@ def _propagation_function():
         @staticmethod
         def forward(ctx, engine, layout, h0, *flat):
             layers = [{k: flat[i] for k, i in lay.items()} for lay in layout]
-            need = any(t.requires_grad for t in flat) or h0.requires_grad
+            # ctx.needs_input_grad is all False under torch.no_grad() (validation epochs): no activations are saved there
+            need = any(ctx.needs_input_grad[2:])
             engine.set_weights([{k: v.detach().contiguous() for k, v in lw.items()} for lw in layers])
             engine.set_save_for_backward(need)
             out = engine.forward(h0.detach().contiguous())
             ctx.engine, ctx.layout, ctx.shapes = engine, layout, [t.shape for t in flat]
-            ctx.h0_needs = h0.requires_grad
+            ctx.h0_needs = bool(ctx.needs_input_grad[2])
             ctx.keepalive = (h0, out, flat)   # the engine reads these buffers again in ggnn_backward
             return out
 

@@ -30,6 +30,14 @@
 namespace ggnn {
 namespace tc {
 
+// Profiling hooks (phase stamps + per-role event log of tile 0, read by tools/tc_trace.py / tc_phase_timing.py) are compiled in only
+// with -DGGNN_TC_TRACE (GGNN_TC_TRACE=1 python -m ..._build): in the shipped kernel they were 10 % of the issued warp instructions.
+#ifdef GGNN_TC_TRACE
+#define GGNN_TRACE_ON(p) ((p).dbg != nullptr)
+#else
+#define GGNN_TRACE_ON(p) false
+#endif
+
 constexpr int TILE_M = 128;
 constexpr int NUM_WORKERS = 512;          // 16 worker warps: 4 per TMEM lane quarter
 #ifndef GGNN_TC_ISSUERS
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         };
         int* ev_ip = nullptr; int* ev_sp = nullptr;   // set below (the event log of thread 0)
         auto ev_raw = [&](int code) {
-            if (ev_ip && p.dbg && tile == 0 && tid == 0 && *ev_sp == 1 && *ev_ip < 64) { p.dbg[64 + 2 * *ev_ip] = code; p.dbg[65 + 2 * *ev_ip] = clock64(); ++*ev_ip; }
+            if (GGNN_TRACE_ON(p) && ev_ip && tile == 0 && tid == 0 && *ev_sp == 1 && *ev_ip < 64) { p.dbg[64 + 2 * *ev_ip] = code; p.dbg[65 + 2 * *ev_ip] = clock64(); ++*ev_ip; }
         };
         auto wait_on = [&](uint64_t* bar, uint32_t parity) {
             ev_raw(1);
@@ -358,9 +366,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         int ev_i = 0, ev_step = -1;
         ev_ip = &ev_i; ev_sp = &ev_step;
         auto ev = [&](int code) {
-            if (p.dbg && tile == 0 && tid == 0 && ev_step == 1 && ev_i < 64) { p.dbg[64 + 2 * ev_i] = code; p.dbg[65 + 2 * ev_i] = clock64(); ++ev_i; }
+            if (GGNN_TRACE_ON(p) && tile == 0 && tid == 0 && ev_step == 1 && ev_i < 64) { p.dbg[64 + 2 * ev_i] = code; p.dbg[65 + 2 * ev_i] = clock64(); ++ev_i; }
         };
-        auto stamp = [&]() { if (p.dbg && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); ev(9); };
+        auto stamp = [&]() { if (GGNN_TRACE_ON(p) && tile == 0 && tid == 0 && dbg_i < 40) p.dbg[dbg_i++] = clock64(); ev(9); };
         stamp();   // 0: start
 
         // ---- initial state: global fp32 -> TMEM (fp32 master) + opH (bf16 hi/lo)
@@ -698,7 +706,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             const uint32_t full0 = smem_u32(&bar_w_full[0]), empty0 = smem_u32(&bar_w_empty[0]);
             const uint32_t idesc = make_idesc_bf16(DP), idesc2 = make_idesc_bf16(2 * DP);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-            const bool dbg_on = p.dbg && tile == 0 && lane == 0 && iw == 0;
+            const bool dbg_on = GGNN_TRACE_ON(p) && tile == 0 && lane == 0 && iw == 0;
             long long dbg_ready = 0;
             const long long dbg_t0 = clock64();
             int dbg_g = 0;
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
             bool ok = true;
             int pev_i = 0, pev_step = -1;
             auto pev = [&](int code) {
-                if (p.dbg && tile == 0 && pw == 0 && pev_step == 1 && pev_i < 64) { p.dbg[320 + 2 * pev_i] = code; p.dbg[321 + 2 * pev_i] = clock64(); ++pev_i; }
+                if (GGNN_TRACE_ON(p) && tile == 0 && pw == 0 && pev_step == 1 && pev_i < 64) { p.dbg[320 + 2 * pev_i] = code; p.dbg[321 + 2 * pev_i] = clock64(); ++pev_i; }
             };
             auto next_slot = [&](int set) -> uint32_t {
                 const uint32_t n = (set == SET_BASE) ? nstg : nstg + EXT;

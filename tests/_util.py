@@ -84,3 +84,32 @@ def load_golden_sparse(golden_dir, name):
 def max_rel_err(got, ref):
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+def seeded_weight(index, shape):
+    """tests/golden/make_reference_graph_golden.py::seeded_weight -- the weights of the fixtures too large to commit (D = 256)."""
+    r = np.sqrt(6.0 / (shape[-2] + shape[-1]))
+    return np.random.RandomState(9000 + index).uniform(-r, r, size=shape).astype(np.float32).astype(np.float64)
+
+
+def load_refgraph_wide(golden_dir, name):
+    """refgraph_sparse_{cfg2,cfg4}_shape.npz: BASELINE-width fixtures computed by the reference's own graph code.  Returns
+    (npz, params, per-layer weight dicts (float64 values that are exactly representable in fp32), adjacency lists, T)."""
+    from gated_graph_neural_network_samples_b200.engine import residual_inputs_of_layer
+    z = np.load(os.path.join(golden_dir, "refgraph_sparse_%s.npz" % name))
+    p = json.loads(str(z["params_json"]))
+    T, D, L = int(z["num_edge_types"]), int(p["hidden_size"]), len(p["layer_timesteps"])
+    if int(z["weights_stored"]):
+        w = [{k[len("w%d_" % l):]: np.asarray(z[k], np.float64) for k in z.files if k.startswith("w%d_" % l)} for l in range(L)]
+    else:   # the generator's recipe: per layer [edge [T*D, D], cand_bias, cand_kernel, gate_bias, gate_kernel], one index each
+        w, idx = [], 0
+        for l in range(L):
+            din = D * (1 + len(residual_inputs_of_layer(p, l)))
+            lw = {"edge_weights": seeded_weight(idx, (T * D, D)).reshape(T, D, D)}
+            lw["cand_bias"] = np.asarray(z["w%d_cand_bias" % l], np.float64)
+            lw["cand_kernel"] = seeded_weight(idx + 2, (din + D, D))
+            lw["gate_bias"] = np.asarray(z["w%d_gate_bias" % l], np.float64)
+            lw["gate_kernel"] = seeded_weight(idx + 4, (din + D, 2 * D))
+            idx += 5
+            w.append(lw)
+    return z, p, w, [z["adj%d" % e] for e in range(T)], T

@@ -61,6 +61,77 @@ def evaluate_model(m, feed):
     return final, ro, float(loss), float(acc)
 
 
+def seeded_weight(index, shape, scale=None):
+    """Weights of the BASELINE-width fixtures that are too large to commit (D = 256: ~15 MB): value = float32(uniform(-r, r)) from
+    RandomState(9000 + index), r = glorot range of the shape.  tests/_util.py regenerates them from (index, shape) alone."""
+    r = np.sqrt(6.0 / (shape[-2] + shape[-1])) if scale is None else scale
+    return np.random.RandomState(9000 + index).uniform(-r, r, size=shape).astype(np.float32).astype(np.float64)
+
+
+def sparse_case_wide(ref_sparse, name, cfg, mols, T, store_weights):
+    """A BASELINE-width case (cfg2 / cfg4 shape).  ``store_weights``: commit the float32-rounded weights the reference code created
+    (D = 100), or replace them by ``seeded_weight`` values and commit nothing but the recipe (D = 256)."""
+    m = object.__new__(ref_sparse.SparseGGNNChemModel)
+    m.params = {"task_ids": [0], "tie_fwd_bkwd": True, "task_sample_ratios": {}, "batch_size": 100000, "out_layer_dropout_keep_prob": 1.0,
+                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0, "use_propagation_attention": False, "use_graph": True}
+    m.params.update(cfg)
+    m.num_edge_types, m.annotation_size = T, len(mols[0]["node_features"][0])
+    np.random.seed(21)
+    tf_shim.CELL_RNG.seed(5151)
+    n_before = len(tf_shim.VARIABLES)
+    ro_w = build_model(m)                                         # make_model -> sparse:63-115, 117-218, 220-231, unmodified
+    L, D = len(cfg["layer_timesteps"]), cfg["hidden_size"]
+    data = m.process_raw_graphs(mols, is_training_data=False)
+    feed = next(iter(m.make_minibatch_iterator(data, is_training=False)))
+    h0 = np.asarray(feed[m.placeholders["initial_node_representation"]], dtype=np.float64)
+    h0 = (h0 + np.random.RandomState(3).normal(0, 0.1, h0.shape)).astype(np.float32).astype(np.float64)   # exactly representable in fp32
+    feed[m.placeholders["initial_node_representation"]] = h0
+    evaluate_model(m, feed)                                       # first evaluation creates the cells' kernels (their width is only known then)
+    edge_vars = [v for v in tf_shim.VARIABLES[n_before:] if "gnn_edge_weights" in str(getattr(v, "name", ""))]
+    assert len(edge_vars) == L, [getattr(v, "name", None) for v in tf_shim.VARIABLES[n_before:]]
+    idx = 0
+    for l in range(L):
+        cell = m.gnn_weights.rnn_cells[l]
+        cell = getattr(cell, "cell", cell)
+        arrays = [("edge", edge_vars[l], None)] + [(k, cell.vars, k) for k in sorted(cell.vars)]
+        for tag, holder, key in arrays:
+            cur = holder.value if key is None else holder[key]
+            if store_weights:
+                new = np.asarray(cur, np.float64).astype(np.float32).astype(np.float64)
+            elif cur.ndim == 1:
+                new = np.asarray(cur, np.float64)                 # biases keep the reference's initial values (gate 1.0, candidate 0)
+            else:
+                new = seeded_weight(idx, cur.shape)
+            idx += 1
+            if key is None:
+                holder.value = new
+            else:
+                holder[key] = new
+    out_final, out_ro, loss, acc = evaluate_model(m, feed)
+    out = {"params_json": np.asarray(json.dumps(cfg)), "num_edge_types": np.int64(T), "h0": h0.astype(np.float32), "final": out_final,
+           "readout": out_ro, "loss": np.float64(loss), "accuracy": np.float64(acc),
+           "indeg": np.asarray(feed[m.placeholders["num_incoming_edges_per_type"]], np.float32),
+           "graph_nodes_list": np.asarray(feed[m.placeholders["graph_nodes_list"]], np.int32),
+           "num_graphs": np.int64(feed[m.placeholders["num_graphs"]]), "weights_stored": np.int64(1 if store_weights else 0)}
+    for e, ph in enumerate(m.placeholders["adjacency_lists"]):
+        out["adj%d" % e] = np.asarray(feed[ph], np.int32).reshape(-1, 2)
+    for l in range(L):
+        cell = m.gnn_weights.rnn_cells[l]
+        cell = getattr(cell, "cell", cell)
+        if store_weights:
+            out["w%d_edge_weights" % l] = np.asarray(tf_shim.evaluate(m.gnn_weights.edge_weights[l], feed), np.float32)
+            for k, v in cell.vars.items():
+                out["w%d_%s" % (l, k)] = np.asarray(v, np.float32)
+        else:
+            for k, v in cell.vars.items():
+                if v.ndim == 1:
+                    out["w%d_%s" % (l, k)] = np.asarray(v, np.float32)
+    for k, v in ro_w.items():
+        out["ro_" + k] = v.value
+    np.savez_compressed(os.path.join(HERE, "refgraph_sparse_%s.npz" % name), **out)
+    print(name, "V=%d final max %.3f readout[:3] %s" % (h0.shape[0], np.abs(out_final).max(), np.round(out_ro[:3], 4)))
+
+
 def sparse_case(ref_sparse, ref_utils, name, cfg, mols):
     m = object.__new__(ref_sparse.SparseGGNNChemModel)
     m.params = {"task_ids": [0], "tie_fwd_bkwd": True, "task_sample_ratios": {}, "batch_size": 100000, "out_layer_dropout_keep_prob": 1.0,
@@ -153,6 +224,14 @@ def main():
     for name, cfg in cases.items():
         sparse_case(ref_sparse, ref_utils, name, cfg, mols)
     dense_case(ref_dense, ref_utils, synthetic.make_molecules(40, seed=123))   # batch_size 4: several buckets fill (dense:150-164)
+    # BASELINE widths (remove the oracle bridge between the D = 12 fixtures and the D = 100 / 256 checks)
+    sparse_case_wide(ref_sparse, "cfg2_shape", {"hidden_size": 100, "layer_timesteps": [4], "residual_connections": {}, "use_edge_bias": False,
+                                                "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh"},
+                     synthetic.make_molecules(24, seed=77), T=4, store_weights=True)
+    sparse_case_wide(ref_sparse, "cfg4_shape", {"hidden_size": 256, "layer_timesteps": [2, 2, 2, 2], "residual_connections": {"2": [0]},
+                                                "use_edge_bias": False, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU",
+                                                "graph_rnn_activation": "tanh"},
+                     synthetic.make_molecules(12, seed=78, num_bond_types=8), T=8, store_weights=False)
     print("reference-graph fixtures written to", HERE)
 
 

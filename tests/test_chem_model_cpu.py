@@ -96,6 +96,51 @@ def test_dense_model_trains_on_the_host(tmp_path, stand_in):
     assert "graph_model/gru_scope/gru_cell/gates/kernel:0" in dict(m.trainable_variables())
 
 
+def test_dense_task_sample_ratios_and_state_dropout_in_training(tmp_path, stand_in):
+    """dense:153-158 (labels beyond the ratio are dropped per shuffled bucket) and dense:222 (the weight-dropout slot is fed with the
+    state keep probability): a dense training run with both set must run, and the ratio must show up in the target masks."""
+    mols = synthetic.make_molecules(80, seed=5)
+    args = {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:64], "--valid_data": mols[64:],
+            "--config": {"hidden_size": 16, "batch_size": 4, "num_timesteps": 2, "learning_rate": 0.01, "num_epochs": 1,
+                         "task_sample_ratios": {"0": 0.5}, "graph_state_dropout_keep_prob": 0.9}}
+    m = chem_dense.DenseGGNNChemModel(args)
+    labelled = total = 0
+    for feed in m.make_minibatch_iterator(m.train_data, is_training=True):
+        labelled += float(np.sum(feed["target_mask"]))
+        total += feed["num_graphs"]
+        assert feed["edge_weight_dropout_keep_prob"] == 0.9 and feed["graph_state_keep_prob"] == 0.9
+    assert total > 0 and 0.3 * total <= labelled <= 0.7 * total, (labelled, total)
+    for feed in m.make_minibatch_iterator(m.valid_data, is_training=False):
+        assert np.all(feed["target_mask"] == 1.0)               # validation data keeps every label (dense:149: training only)
+    loss = m.run_epoch("train", m.train_data, True)[0]
+    assert np.isfinite(loss)
+
+
+@pytest.mark.parametrize("steps", [3, 2000, 150000])
+def test_adam_step_survives_a_checkpoint_after_many_updates(tmp_path, stand_in, steps):
+    """float32(0.9 ** (t + 1)) underflows to 0 after ~1000 updates (log -> -inf): the count is stored explicitly, and a TensorFlow pickle
+    that only has the beta powers falls back to beta2_power, then to train_step."""
+    mols = synthetic.make_molecules(64, seed=1)
+    m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols))
+    m.run_epoch("train", m.train_data, True)
+    for st in m.optimizer.state.values():
+        st["step"].fill_(float(steps))
+    path = str(tmp_path / "late.pickle")
+    m.save_progress(path, steps, 0)
+    m2 = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols))
+    m2.restore_progress(path)
+    assert all(int(st["step"]) == steps for st in m2.optimizer.state.values())
+    # a pickle written by TensorFlow has no 'adam_step'
+    data = pickle.load(open(path, "rb"))
+    del data["weights"]["adam_step"]
+    pickle.dump(data, open(path, "wb"))
+    m3 = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols))
+    m3.restore_progress(path)
+    got = {int(st["step"]) for st in m3.optimizer.state.values()}
+    assert len(got) == 1
+    assert abs(got.pop() - steps) <= max(1, steps // 50)      # beta2_power = 0.999^(t+1) in float32 resolves t to well under 2 %
+
+
 def test_the_real_engine_still_refuses_the_cpu(tmp_path):
     import torch
     if torch.cuda.is_available():

@@ -47,3 +47,22 @@ def test_dense_propagation_matches_the_reference_graph_code(golden_dir, precisio
     err = U.max_rel_err(got, z["final"])
     print("refgraph dense %-6s max rel err %.2e" % (precision, err))
     assert np.all(np.isfinite(got)) and err < 1e-4
+
+
+@pytest.mark.parametrize("name,precision,plan", [("cfg2_shape", "bf16x3", "LOCAL"), ("cfg2_shape", "fp32", "LOCAL"),
+                                                 ("cfg4_shape", "bf16x3", "STREAM"), ("cfg4_shape", "fp32", "")])
+def test_baseline_width_fixtures_of_the_reference_graph_code(golden_dir, name, precision, plan):
+    """BASELINE configs[1] / configs[3] shapes (hidden 100 / 256) computed by the reference's own graph code: the tile-local fused tcgen05
+    kernel, the streaming tcgen05 kernels and the fp32 kernel against them directly -- no oracle in between."""
+    import torch
+    z, p, w, adj, T = U.load_refgraph_wide(golden_dir, name)
+    got, eng = U.engine_sparse(p, T, w, adj, z["indeg"], z["h0"], precision=precision, return_engine=True)
+    assert plan in eng.plan, eng.plan
+    err = U.max_rel_err(got, z["final"])
+    print("refgraph %-12s %-6s propagation max rel err %.2e  [%s]" % (name, precision, err, eng.plan[:40]))
+    assert np.all(np.isfinite(got)) and err < 1e-4
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    eng.readout_set_graphs(int(z["num_graphs"]), graph_nodes_list=z["graph_nodes_list"])
+    ro = eng.readout_forward(f32(got), f32(z["h0"]), f32(z["ro_w_gate"]), f32(z["ro_b_gate"]), f32(z["ro_w_trans"]), f32(z["ro_b_trans"]))
+    eng.sync_check()
+    assert U.max_rel_err(ro.cpu().numpy(), z["readout"]) < 1e-4

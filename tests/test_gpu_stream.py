@@ -180,3 +180,17 @@ def test_state_dropout_on_the_streaming_path():
                                      dtype=torch.float64, state_dropout=(keep, seed)).numpy()
     _check(got, ref, "state dropout")
     np.testing.assert_array_equal(got != 0.0, eng.state_dropout_mask(1, keep, seed).astype(bool) & (ref != 0.0))
+
+
+@pytest.mark.parametrize("D,T,plan", [(100, 4, "LOCAL"), (256, 8, "STREAM")])
+def test_error_growth_over_32_timesteps_stays_inside_the_bar(D, T, plan):
+    """The epilogues use ex2-based sigmoid / tanh and the operands carry 16 mantissa bits: 32 recurrent timesteps (8x the deepest BASELINE
+    configuration) bound how those errors accumulate on both tensor-core plans."""
+    p = dict(CFG2, hidden_size=D, layer_timesteps=[32])
+    _, b = U.molecule_batch(24, D, T=T, seed=17)
+    w = O.init_sparse_weights(p, T, np.random.default_rng(1))
+    ref = O.sparse_propagation_np(b["initial_node_representation"], b["adjacency_lists"], b["num_incoming_edges_per_type"], w, p, dtype=np.float64)
+    got, eng = U.engine_sparse(p, T, w, b["adjacency_lists"], b["num_incoming_edges_per_type"], b["initial_node_representation"],
+                               precision=PREC, return_engine=True)
+    assert plan in eng.plan
+    _check(got, ref, "32 timesteps D=%d" % D)

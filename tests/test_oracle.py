@@ -225,6 +225,24 @@ def test_oracle_reproduces_the_reference_graph_code_sparse(golden_dir, name):
     np.testing.assert_allclose(ro, z["readout"], rtol=1e-11, atol=1e-12)
 
 
+@pytest.mark.parametrize("name", ["cfg2_shape", "cfg4_shape"])
+def test_oracle_reproduces_the_reference_graph_code_at_baseline_widths(golden_dir, name):
+    """The same at BASELINE widths: hidden 100 / [4] / 4 edge types (configs[1]) and hidden 256 / [2,2,2,2] + residual / 8 edge types
+    (configs[3]), a few dozen molecules each, computed by the reference's unmodified graph code -- no oracle bridge between the D = 12
+    fixtures and the widths the benchmarks run at."""
+    import torch
+    from tests import _util as U
+    z, p, w, adj, T = U.load_refgraph_wide(golden_dir, name)
+    h0, indeg = np.asarray(z["h0"], np.float64), np.asarray(z["indeg"], np.float64)
+    for got in (O.sparse_propagation_np(h0, adj, indeg, w, p, dtype=np.float64),
+                O.sparse_propagation_torch(h0, adj, indeg, w, p, dtype=torch.float64).numpy(),
+                CO.sparse_propagation_c(h0, adj, indeg, w, p)):
+        np.testing.assert_allclose(got, z["final"], rtol=1e-10, atol=1e-12)
+    ro = O.gated_regression_torch(z["final"], h0, z["ro_w_gate"], z["ro_b_gate"], z["ro_w_trans"], z["ro_b_trans"],
+                                  graph_nodes_list=z["graph_nodes_list"], num_graphs=int(z["num_graphs"]), dtype=torch.float64).numpy()
+    np.testing.assert_allclose(ro, z["readout"], rtol=1e-10, atol=1e-12)
+
+
 def test_oracle_reproduces_the_reference_graph_code_dense(golden_dir):
     import torch
     z = np.load(os.path.join(golden_dir, "refgraph_dense.npz"))
