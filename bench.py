@@ -492,6 +492,28 @@ def main():
     # ---- end-to-end through the host-buffer API (pinned host inputs, H2D + D2H inside the timed region)
     e2e_ms_total, h2d, d2h, (h0_host, out_host) = B.time_e2e(eng, w, out, args.steps, args.warmup)
     h0_np = h0_host.numpy()
+    # ---- what the reference's training loop actually fetches: loss + accuracy (chem_tensorflow.py:231-235), not [V, D] states
+    e2e_ro_ms_total, ro_d2h = None, 0
+    if w["kind"] == "sparse":
+        D_ = int(P["hidden_size"])
+        rr_ = np.random.default_rng(3)
+        task = (torch.from_numpy(rr_.normal(0, 0.2, 2 * D_).astype(np.float32)).cuda(), torch.zeros(1, device="cuda"),
+                torch.from_numpy(rr_.normal(0, 0.2, D_).astype(np.float32)).cuda(), torch.zeros(1, device="cuda"))
+        tv_ = w["target_values"].reshape(1, -1); tm_ = np.ones_like(tv_)
+
+        def ro_step():
+            return eng.run_sparse_host_readout(w["adjacency_lists"], w["num_incoming_edges_per_type"], h0_np, w["graph_nodes_list"],
+                                               w["num_graphs"], [task], tv_, tm_)
+
+        for _ in range(max(args.warmup, 3)):
+            ro_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ro_loss, ro_acc = ro_step()
+        e2e_ro_ms_total = (time.perf_counter() - t0) * 1e3
+        ro_d2h = 8
+        assert np.isfinite(ro_loss[0]) and np.isfinite(ro_acc[0])
     # ---- same, two batches in flight (two engines on two streams; the reference overlaps batch preparation with
     # sess.run through ThreadedIterator, chem_tensorflow.py:225): reported beside the serial number, never instead of it
     engs = [eng, PropagationEngine(P, w["num_edge_types"], device=local_rank, precision=args.precision)]
@@ -594,8 +616,8 @@ def main():
             others[name] = B.other_config(name, min(args.steps, 20))
 
     # ---- max over ranks
-    (dev_ms_total, e2e_ms_total, hot_ms, pipe_ms_total, train_ms_total), (total_units_per_step,) = B.reduce(
-        [dev_ms_total, e2e_ms_total, hot_ms, pipe_ms_total, train_ms_total], [float(w["node_updates"])])
+    (dev_ms_total, e2e_ms_total, hot_ms, pipe_ms_total, train_ms_total, e2e_ro_max), (total_units_per_step,) = B.reduce(
+        [dev_ms_total, e2e_ms_total, hot_ms, pipe_ms_total, train_ms_total, e2e_ro_ms_total or 0.0], [float(w["node_updates"])])
 
     if rank == 0:
         ms_per_step = dev_ms_total / args.steps
@@ -620,6 +642,11 @@ def main():
             "e2e": {"value": total_units_per_step / (e2e_ms_total / args.steps * 1e-3), "unit": "node-updates/s",
                     "ms_per_step": e2e_ms_total / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "run_{sparse,dense}_host per step: H2D h0 (pinned) | host CSR build + H2D graph, kernel, D2H result, sync; serial"},
+            "e2e_readout": None if not e2e_ro_max else {
+                "value": total_units_per_step / (e2e_ro_max / args.steps * 1e-3), "unit": "node-updates/s", "ms_per_step": e2e_ro_max / args.steps,
+                "h2d_bytes_per_step": h2d + 4 * w["V"] + 8 * w["num_graphs"], "d2h_bytes_per_step": ro_d2h,
+                "what": "run_sparse_host_readout per step: the fetch of the reference's sess.run([loss, accuracy], feed_dict) -- propagation + "
+                        "fused gated_regression + masked loss/MAE on the device, 2 floats back instead of the [V, D] states; serial"},
             "e2e_pipelined": {"value": total_units_per_step / (pipe_ms_total / args.steps * 1e-3), "unit": "node-updates/s",
                               "ms_per_step": pipe_ms_total / args.steps,
                               "what": "same calls and bytes, two batches in flight (2 engines x 2 streams, forward_host_async); wall clock"},

@@ -1268,7 +1268,7 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
     if (ns_edge < 2 || ns_gate < 2 || ns_cand < 2) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the streaming ring (DP=%d)", DP);
     auto smem_of = [&](int NC, int ns, bool gather) { return (size_t)1024 + (size_t)ns * stage_bytes(NC) + (gather ? csr_b : 0); };
     auto k_edge = ts::ggnn_stream_kernel<16, true>;
-    auto k_fed = ts::ggnn_stream_kernel<8, false>;
+    auto k_fed = ts::ggnn_stream_kernel<16, false>;   // 16 epilogue warps: the epilogue is bound by the latency of its operand loads
     const size_t sm_edge = smem_of(nc0, ns_edge, true);
     const size_t sm_fed = std::max(smem_of(nc1, ns_gate, false), smem_of(nc0, ns_cand, false));
     CU_TRY(e, cudaFuncSetAttribute(k_edge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_edge));
@@ -1318,7 +1318,7 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
                 q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_chk = chk_in; q.u_buf = u_chk; q.img_out = img_rh;
                 if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; q.sv_u = sv + 3 * per + so; }
                 q.gstep = gs; q.dbg = next_dbg(); q.dbg2 = dbg2_cur;
-                k_fed<<<dim3(ntiles, nb1), 10 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
+                k_fed<<<dim3(ntiles, nb1), 18 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
                 ++e->last_launches;
             }
             ts::StreamParams c = base;
@@ -1327,7 +1327,7 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
             c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_chk = chk_in; c.u_buf = u_chk; c.h_chk_out = chk_out; c.h_out = out; c.img_out = img_out;
             if (e->save) { if (gru) c.sv_c = sv + 4 * per + so; else c.sv_h = sv + so; }
             c.gstep = gs; c.dbg = next_dbg(); c.dbg2 = dbg2_cur;
-            k_fed<<<dim3(ntiles, nb0), 10 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
+            k_fed<<<dim3(ntiles, nb0), 18 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
             ++e->last_launches;
             img_in = img_out; chk_in = chk_out;
         }
@@ -1554,6 +1554,50 @@ int ggnn_readout_backward(ggnn_engine* e, const float* h_last, const float* h0, 
     readout::readout_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(h_last, h0, w, (const int*)(g + e->ro_off_graph_of), mask, d_out, d_h_last,
                                                                          d_w_gate, d_b_gate, d_w_trans, d_b_trans, V, e->D);
     CU_TRY(e, cudaGetLastError());
+    return GGNN_OK;
+}
+
+int ggnn_run_sparse_host_readout(ggnn_engine* e, int32_t V, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                                 const float* indeg, const float* h0_host, const int32_t* graph_nodes_list, int32_t G, int32_t num_tasks,
+                                 const ggnn_readout_task* tasks, const float* target_values, const float* target_mask, float* loss_out,
+                                 float* accuracy_out, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    if (V < 0 || G < 0 || num_tasks <= 0 || !tasks || !loss_out || !accuracy_out || (V > 0 && (!h0_host || !graph_nodes_list)) ||
+        (G > 0 && (!target_values || !target_mask)))
+        return e->fail(GGNN_EINVAL, "null / negative argument");
+    CU_TRY(e, cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bytes = (size_t)V * e->D * sizeof(float);
+    const size_t slot = align_up(std::max<size_t>(bytes, 16), 256);
+    const size_t tg = (size_t)num_tasks * std::max(G, 1);
+    // device scratch behind the two state slots: targets | masks | per-task readout [tasks][G] | results [2*tasks]
+    const size_t o_tv = 2 * slot, o_tm = o_tv + align_up(tg * 4, 256), o_ro = o_tm + align_up(tg * 4, 256), o_res = o_ro + align_up(tg * 4, 256);
+    CU_TRY(e, e->io_buf.reserve(o_res + align_up((size_t)2 * num_tasks * 4, 256)));
+    char* io = (char*)e->io_buf.ptr;
+    float *d_in = (float*)io, *d_out = (float*)(io + slot);
+    if (bytes) CU_TRY(e, cudaMemcpyAsync(d_in, h0_host, bytes, cudaMemcpyHostToDevice, st));        // overlaps the host-side CSR build below
+    if (G > 0) {
+        CU_TRY(e, cudaMemcpyAsync(io + o_tv, target_values, tg * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(e, cudaMemcpyAsync(io + o_tm, target_mask, tg * 4, cudaMemcpyHostToDevice, st));
+    }
+    int rc = ggnn_set_graph_sparse(e, V, adjacency_lists, num_edges, indeg, stream);
+    if (rc) return rc;
+    rc = ggnn_readout_set_graphs(e, V, graph_nodes_list, G, 0, nullptr, stream);
+    if (rc) return rc;
+    rc = ggnn_forward(e, d_in, d_out, stream);
+    if (rc) return rc;
+    for (int t = 0; t < num_tasks; ++t) {
+        rc = ggnn_readout_forward(e, d_out, d_in, tasks[t].w_gate, tasks[t].b_gate, tasks[t].w_trans, tasks[t].b_trans,
+                                  (float*)(io + o_ro) + (size_t)t * G, stream);
+        if (rc) return rc;
+    }
+    readout::masked_loss_kernel<<<num_tasks, 256, 0, st>>>((const float*)(io + o_ro), (const float*)(io + o_tv), (const float*)(io + o_tm),
+                                                           (float*)(io + o_res), G, num_tasks);
+    CU_TRY(e, cudaGetLastError());
+    std::vector<float> res((size_t)2 * num_tasks);
+    CU_TRY(e, cudaMemcpyAsync(res.data(), io + o_res, sizeof(float) * 2 * num_tasks, cudaMemcpyDeviceToHost, st));
+    CU_TRY(e, cudaStreamSynchronize(st));
+    for (int t = 0; t < num_tasks; ++t) { loss_out[t] = res[t]; accuracy_out[t] = res[num_tasks + t]; }
     return GGNN_OK;
 }
 

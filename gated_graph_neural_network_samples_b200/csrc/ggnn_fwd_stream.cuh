@@ -420,7 +420,9 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         if (stamp) t_acc = clock64();
         if (ok) {
             if (p.epi == EPI_AGG) {
-                const float den = (p.use_avg && row_ok) ? p.denom[grow] : 1.0f;
+                // sparse:207-209 divides by (sum of in-degrees + 1e-7); one IEEE reciprocal per row, then a multiply per element (differs from
+                // the quotient by at most 1 ulp; tests/test_gpu_stream.py bounds the growth over 32 timesteps)
+                const float inv_den = (p.use_avg && row_ok) ? __frcp_rn(p.denom[grow]) : 1.0f;
                 for (int c = cgp; c < nchunks; c += NCG) {
                     const int col = colb + c * 8;
                     if (col >= DP) break;
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                         }
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = row_ok ? (p.use_avg ? __fdiv_rn(v[j], den) : v[j]) : 0.0f;   // sparse:207-209 divides
+                    for (int j = 0; j < 8; ++j) v[j] = row_ok ? v[j] * inv_den : 0.0f;
                     if (p.sv_agg && row_ok) tc::store8_guarded(p.sv_agg + (size_t)grow * D, col, D, v);
                     img_store_chunk(p.img_out, NKS, tile, row, col, v);
                 }

@@ -131,5 +131,34 @@ __global__ void __launch_bounds__(256) readout_bwd_kernel(const float* __restric
     }
 }
 
+// Masked regression loss of one task (chem_tensorflow.py:161-166): diff = (computed - target) * mask,
+//   loss = sum 0.5*diff^2 / (sum mask + 1e-7),  accuracy (= MAE) = sum |diff| / (sum mask + 1e-7).
+// One block per task; every thread adds a strided slice in index order and the block reduces in a fixed tree: run-to-run identical.
+// out[task] = loss, out[num_tasks + task] = accuracy.
+__global__ void __launch_bounds__(256) masked_loss_kernel(const float* __restrict__ computed, const float* __restrict__ target_values,
+                                                          const float* __restrict__ target_mask, float* __restrict__ out, int G, int num_tasks) {
+    __shared__ float s_sq[256], s_abs[256], s_cnt[256];
+    const int task = blockIdx.x, tid = threadIdx.x;
+    const float* c = computed + (size_t)task * G;
+    const float* tv = target_values + (size_t)task * G;
+    const float* tm = target_mask + (size_t)task * G;
+    float sq = 0.f, ab = 0.f, cnt = 0.f;
+    for (int g = tid; g < G; g += 256) {
+        const float m = tm[g], d = (c[g] - tv[g]) * m;
+        sq += 0.5f * d * d; ab += fabsf(d); cnt += m;
+    }
+    s_sq[tid] = sq; s_abs[tid] = ab; s_cnt[tid] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { s_sq[tid] += s_sq[tid + o]; s_abs[tid] += s_abs[tid + o]; s_cnt[tid] += s_cnt[tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float num = s_cnt[0] + 1e-7f;   // SMALL_NUMBER, utils.py:8
+        out[task] = s_sq[0] / num;
+        out[num_tasks + task] = s_abs[0] / num;
+    }
+}
+
 }  // namespace readout
 }  // namespace ggnn

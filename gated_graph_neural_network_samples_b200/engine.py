@@ -162,6 +162,30 @@ class PropagationEngine:
         self._graph_keepalive = (adjs, indeg)
         return out
 
+    def run_sparse_host_readout(self, adjacency_lists, num_incoming_edges_per_type, h0, graph_nodes_list, num_graphs, readout_tasks,
+                                target_values, target_mask):
+        """The fetches of the reference's ``sess.run([loss, accuracy_task*], feed_dict)`` (chem_tensorflow.py:231-235) in one call: the
+        batch in HOST arrays (reference wire format), per task the readout trainables as CUDA tensors ``(w_gate [2D], b_gate [1],
+        w_trans [D], b_trans [1])``; returns ``(loss [tasks], accuracy [tasks])`` -- 2*tasks floats are all that cross PCIe on the way back."""
+        adjs, indeg, ptrs, counts = self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+        V, nt, G = indeg.shape[0], len(readout_tasks), int(num_graphs)
+        h0 = np.ascontiguousarray(h0, dtype=np.float32)
+        gnl = np.ascontiguousarray(np.asarray(graph_nodes_list, dtype=np.int32).reshape(-1))
+        tv = np.ascontiguousarray(np.asarray(target_values, dtype=np.float32).reshape(nt, G))
+        tm = np.ascontiguousarray(np.asarray(target_mask, dtype=np.float32).reshape(nt, G))
+        if h0.size != V * self.D or gnl.shape[0] != V:
+            raise GgnnError("h0 / graph_nodes_list do not match the %d nodes of the graph" % V)
+        arr = (_lib.GgnnReadoutTask * nt)()
+        for i, (wg, bg, wt, bt) in enumerate(readout_tasks):
+            arr[i].w_gate, arr[i].b_gate = self._f32(wg, 2 * self.D, "w_gate"), self._f32(bg, 1, "b_gate")
+            arr[i].w_trans, arr[i].b_trans = self._f32(wt, self.D, "w_trans"), self._f32(bt, 1, "b_trans")
+        loss, acc = np.empty(nt, np.float32), np.empty(nt, np.float32)
+        self._check(self.lib.ggnn_run_sparse_host_readout(self._h, V, ptrs, counts, indeg.ctypes.data, h0.ctypes.data, gnl.ctypes.data, G, nt, arr,
+                                                          tv.ctypes.data, tm.ctypes.data, loss.ctypes.data, acc.ctypes.data, self._stream()))
+        self.V = V
+        self._graph_keepalive = (adjs, indeg)
+        return loss, acc
+
     def run_dense_host(self, adjacency_matrix: np.ndarray, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         a = np.ascontiguousarray(np.asarray(adjacency_matrix, dtype=np.float32))
         if a.ndim != 4 or a.shape[1] != self.T or a.shape[2] != a.shape[3]:

@@ -141,6 +141,23 @@ int ggnn_readout_backward(ggnn_engine* e, const float* h_last, const float* h0, 
                           const float* w_trans, const float* b_trans, const float* d_out, float* d_h_last, float* d_w_gate,
                           float* d_b_gate, float* d_w_trans, float* d_b_trans, ggnn_stream_t stream);
 
+/* The whole fetch of the reference's training/validation step in ONE call -- sess.run([loss, accuracy_task*], feed_dict=batch),
+ * chem_tensorflow.py:231-235 with the ops of :145-170: propagation (sparse:117-218), gated_regression per task (sparse:220-231), masked
+ * 1/2-MSE loss and MAE per task (chem_tensorflow.py:161-166; the 1/task_sample_ratio factor of :168 is left to the caller).
+ * The batch comes in HOST buffers in the reference wire format (sparse:331-348): graph structure, h0 [V, D], graph_nodes_list [V],
+ * target_values / target_mask [num_tasks, num_graphs]; the readout trainables are DEVICE pointers, one ggnn_readout_task per task.
+ * Only 2 * num_tasks floats come back: loss_out [num_tasks], accuracy_out [num_tasks] (HOST).  Synchronous. */
+typedef struct ggnn_readout_task {
+    const float* w_gate;  /* [2D] regression_gate MLP kernel      (chem_tensorflow.py:153-154) */
+    const float* b_gate;  /* [1]                                                               */
+    const float* w_trans; /* [D]  regression_transform MLP kernel (chem_tensorflow.py:155-157) */
+    const float* b_trans; /* [1]                                                               */
+} ggnn_readout_task;
+int ggnn_run_sparse_host_readout(ggnn_engine* e, int32_t num_nodes, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                                 const float* num_incoming_edges_per_type, const float* h0_host, const int32_t* graph_nodes_list,
+                                 int32_t num_graphs, int32_t num_tasks, const ggnn_readout_task* tasks, const float* target_values,
+                                 const float* target_mask, float* loss_out, float* accuracy_out, ggnn_stream_t stream);
+
 /* Synchronises `stream` and reports asynchronous kernel-side failures (a bounded barrier wait that expired). */
 int ggnn_sync_check(ggnn_engine* e, ggnn_stream_t stream);
 
