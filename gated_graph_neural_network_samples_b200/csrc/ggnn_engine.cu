@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -134,6 +135,7 @@ struct ggnn_engine {
     float drop_keep = 1.0f; unsigned long long drop_seed = 0;          // state dropout for the next forward
     float saved_drop_keep = 1.0f; unsigned long long saved_drop_seed = 0; // ... and what the saved forward used
     int last_launches = 0;
+    std::vector<int> h_counts, h_diff;   // host scratch of ggnn_set_graph_sparse, kept between batches
     std::string err;
 
     int fail(int code, const char* fmt, ...) {
@@ -233,8 +235,9 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
                 e->ts_nc[i] = ((width + nblk - 1) / nblk + 15) / 16 * 16;
             }
             char buf[256];
-            snprintf(buf, sizeof buf, "tcgen05-%s STREAM(3 launches per step: gather-GEMM, gate GEMM, candidate GEMM) tiles=%d DP=%d N-blocks agg/cand=%dx%d gate=%dx%d max_component=%d",
-                     e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->ntiles, e->DP, e->ts_nblk[0], e->ts_nc[0], e->ts_nblk[1], e->ts_nc[1], max_span);
+            int len = snprintf(buf, sizeof buf, "tcgen05-%s STREAM(3 launches per step: gather-GEMM, gate GEMM, candidate GEMM) tiles=%d DP=%d N-blocks agg/cand=%dx%d gate=%dx%d",
+                               e->precision == GGNN_PREC_BF16X3 ? "bf16x3" : "bf16", e->ntiles, e->DP, e->ts_nblk[0], e->ts_nc[0], e->ts_nblk[1], e->ts_nc[1]);
+            if (e->DP <= 128) snprintf(buf + len, sizeof buf - len, " max_component=%d", max_span);   // (not computed for hidden sizes > 128: fixed tiles)
             e->plan_text = buf;
             return GGNN_OK;
         }
@@ -703,6 +706,15 @@ int ggnn_host_target_csr(int32_t V, int32_t T, const int32_t* const* adj, const 
 int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
                           const float* indeg, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
+    static const bool host_timing = getenv("GGNN_HOST_TIMING") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what, std::chrono::steady_clock::time_point& t) {
+        if (!host_timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ggnn host] %-18s %7.1f us\n", what, std::chrono::duration<double, std::micro>(now - t).count());
+        t = now;
+    };
+    auto t_lap = t_begin;
     e->graph_set = false; e->saved_valid = false;
     if (V < 0 || !adj || !num_edges || (!indeg && V > 0)) return e->fail(GGNN_EINVAL, "null/negative argument");
     CU_TRY(e, cudaSetDevice(e->device));
@@ -715,34 +727,50 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     if (M > 0x7fffffff || (int64_t)V * T + 1 > 0x7fffffff) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
     e->V = V; e->M = M; e->gather_mode = GATHER_SPARSE; e->dense_v = 0;
 
-    // ---- pass 1: validate, count per (target,type), mark which node boundaries are spanned by an edge
-    std::vector<int> counts((size_t)V * T + 1, 0);
-    std::vector<int> diff((size_t)V + 2, 0);
-    for (int t = 0; t < T; ++t) {
-        const int32_t* a = adj[t];
-        for (int i = 0; i < num_edges[t]; ++i) {
-            const int s = a[2 * i], d = a[2 * i + 1];
-            if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
-                return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
-            ++counts[(size_t)d * T + t + 1];
-            const int lo = std::min(s, d), hi = std::max(s, d);
-            if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
-        }
-    }
+    // ---- pass 1: validate, count per (target,type), mark which node boundaries are spanned by an edge (the cut points of the tile-local
+    // plans; the streaming plan of hidden sizes > 128 tiles by fixed 128-row blocks and skips that part)
+    std::vector<int>& counts = e->h_counts;
+    std::vector<int>& diff = e->h_diff;
+    counts.assign((size_t)V * T + 1, 0);
+    const bool need_cuts = !(e->precision != GGNN_PREC_FP32 && e->DP > 128);
     std::vector<int> cuts;
     cuts.push_back(0);
-    {
+    if (need_cuts) {
+        diff.assign((size_t)V + 2, 0);
+        for (int t = 0; t < T; ++t) {
+            const int32_t* a = adj[t];
+            for (int i = 0; i < num_edges[t]; ++i) {
+                const int s = a[2 * i], d = a[2 * i + 1];
+                if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
+                    return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
+                ++counts[(size_t)d * T + t + 1];
+                const int lo = std::min(s, d), hi = std::max(s, d);
+                if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
+            }
+        }
         int cover = 0;
         for (int i = 1; i < V; ++i) {
             cover += diff[i];
             if (cover == 0) cuts.push_back(i);
         }
-        if (V > 0) cuts.push_back(V);
+    } else {
+        for (int t = 0; t < T; ++t) {
+            const int32_t* a = adj[t];
+            for (int i = 0; i < num_edges[t]; ++i) {
+                const int s = a[2 * i], d = a[2 * i + 1];
+                if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
+                    return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
+                ++counts[(size_t)d * T + t + 1];
+            }
+        }
     }
+    if (V > 0) cuts.push_back(V);
+    lap("validate+count", t_lap);
     std::vector<int> tile_start;
     int rc = build_plan(e, cuts, tile_start);
     if (rc) return rc;
     const int ntiles = e->ntiles;
+    lap("tile plan", t_lap);
 
     // ---- layout of the packed upload
     size_t off = 0;
@@ -785,34 +813,68 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     int* h_tiles = (int*)(base + e->off_tiles);
     unsigned* h_mask = (unsigned*)(base + e->off_mask);
 
-    // ---- pass 2: exclusive scan + stable fill (iteration in message order keeps the reference's order per row)
-    fill_target_csr(V, T, adj, num_edges, counts, row_ptr, csr_src, csr_msg);
+    lap("stage reserve", t_lap);
+    // ---- pass 2, one sweep over the (target, type) rows: exclusive scan -> row_ptr, fill cursors (stored over the consumed counts), the
+    // tiles' edge-type masks and the largest per-tile message count; then the stable fill (iteration in message order keeps the
+    // reference's order per row: this IS NumPy's stable argsort by target, tests pin it bit for bit)
+    {
+        row_ptr[0] = 0;
+        int run = 0;
+        e->max_tile_msgs = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            unsigned mask = 0;
+            const int tile_first = run;
+            for (size_t k = (size_t)tile_start[i] * T, kend = (size_t)tile_start[i + 1] * T; k < kend; k += T)
+                for (int t = 0; t < T; ++t) {
+                    const int c = counts[k + t + 1];
+                    counts[k + t] = run;
+                    run += c;
+                    row_ptr[k + t + 1] = run;
+                    mask |= (unsigned)(c > 0) << t;
+                }
+            h_mask[i] = mask;
+            e->max_tile_msgs = std::max(e->max_tile_msgs, run - tile_first);
+        }
+        int* pair = e->stream ? (int*)(base + e->off_pair) : nullptr;   // streaming plan: (target, type) -> its one source / -2 "several"
+        if (pair) {
+            const size_t np = (size_t)std::max(ntiles, 1) * ts::TILE_M * T;
+            for (size_t k = 0; k < np; ++k) pair[k] = -1;
+        }
+        int m = 0;
+        for (int t = 0; t < T; ++t) {
+            const int32_t* a = adj[t];
+            for (int i = 0; i < num_edges[t]; ++i, ++m) {
+                const size_t key = (size_t)a[2 * i + 1] * T + t;
+                const int slot = counts[key]++;
+                csr_src[slot] = a[2 * i];
+                csr_msg[slot] = m;
+                if (pair) pair[key] = (slot == row_ptr[key]) ? a[2 * i] : -2;   // first message of the row: its source; any later one: "several"
+            }
+        }
+    }
+    lap("csr fill", t_lap);
     if (e->stream) {
         int* pair = (int*)(base + e->off_pair);
         int* vptr = (int*)(base + e->off_vptr);
         int* vsrc = (int*)(base + e->off_vsrc);
         int* tvp = (int*)(base + e->off_tvp);
         int* vinfo = (int*)(base + e->off_vinfo);
-        int vid = 0, vm = 0, next_tile = 0;
+        // number the pairs with several messages ("virtual rows") in row order and list their sources
+        int vid = 0, vm = 0;
         vptr[0] = 0;
-        for (int v = 0; v < V; ++v) {
-            while (next_tile <= ntiles && v == next_tile * ts::TILE_M) tvp[next_tile++] = vid;
-            for (int t = 0; t < T; ++t) {
-                const size_t k = (size_t)v * T + t;
+        for (int i = 0; i < ntiles; ++i) {
+            tvp[i] = vid;
+            for (size_t k = (size_t)tile_start[i] * T, kend = (size_t)tile_start[i + 1] * T; k < kend; ++k) {
+                if (pair[k] != -2) continue;
                 const int b = row_ptr[k], cnt = row_ptr[k + 1] - b;
-                if (cnt == 0) pair[k] = -1;
-                else if (cnt == 1) pair[k] = csr_src[b];
-                else {
-                    pair[k] = -(2 + vid);
-                    vinfo[8 * vid] = cnt;
-                    for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
-                    for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
-                    vptr[++vid] = vm;
-                }
+                pair[k] = -(2 + vid);
+                vinfo[8 * vid] = cnt;
+                for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
+                for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
+                vptr[++vid] = vm;
             }
         }
-        while (next_tile <= ntiles) tvp[next_tile++] = vid;
-        for (size_t k = (size_t)V * T; k < (size_t)std::max(ntiles, 1) * ts::TILE_M * T; ++k) pair[k] = -1;
+        tvp[ntiles] = vid;
     }
     if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
         int* trow = (int*)(base + e->off_trow);
@@ -837,26 +899,20 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
                 if (tslot) tslot[j] = slot_of_msg[m];
             }
     }
+    if (V > 0) memcpy(h_indeg, indeg, sizeof(float) * (size_t)V * T);
     for (int v = 0; v < V; ++v) {
+        const float* row = indeg + (size_t)v * T;
         float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
-        for (int t = 0; t < T; ++t) { h_indeg[(size_t)v * T + t] = indeg[(size_t)v * T + t]; s += indeg[(size_t)v * T + t]; }
+        for (int t = 0; t < T; ++t) s += row[t];
         h_denom[v] = s + 1e-7f;
     }
     for (int i = 0; i <= ntiles; ++i) h_tiles[i] = tile_start[i];
-    for (int i = 0; i < ntiles; ++i) {
-        unsigned mask = 0;
-        for (int v = tile_start[i]; v < tile_start[i + 1]; ++v)
-            for (int t = 0; t < T; ++t)
-                if (row_ptr[(size_t)v * T + t + 1] > row_ptr[(size_t)v * T + t]) mask |= 1u << t;
-        h_mask[i] = mask;
-    }
-    e->max_tile_msgs = 0;
-    for (int i = 0; i < ntiles; ++i)
-        e->max_tile_msgs = std::max(e->max_tile_msgs, row_ptr[(size_t)tile_start[i + 1] * T] - row_ptr[(size_t)tile_start[i] * T]);
+    lap("denom+masks+extra", t_lap);
     rc = upload_graph(e, off, (cudaStream_t)stream);
     if (rc) return rc;
     rc = reserve_states(e);
     if (rc) return rc;
+    lap("upload enqueue", t_lap);
     e->graph_set = true;
     return GGNN_OK;
 }
