@@ -95,7 +95,9 @@ def time_cpu_reference(w, budget_s=12.0, max_iters=200, threads=None):
     with torch.no_grad():
         for nt in candidates:
             torch.set_num_threads(nt)
-            fn(); fn()
+            t_warm, n_warm = time.perf_counter(), 0
+            while n_warm < 2 or (n_warm < 20 and time.perf_counter() - t_warm < 0.5):   # thread pool, allocator and caches warm in both arms alike
+                fn(); n_warm += 1
             times, t_start = [], time.perf_counter()
             while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s / len(candidates):
                 t0 = time.perf_counter(); fn(); times.append(time.perf_counter() - t0)

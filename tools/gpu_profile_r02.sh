@@ -9,18 +9,7 @@ full() {  # name kernel-regex skip count  bench-args...
   timeout 900 $NCU --set full --import-source on -k regex:$rx -s $skip -c $cnt -o $OUT/$name -f $B "$@" > $OUT/$name.log 2>&1
   echo "ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt $B $*" > $OUT/$name.summary.txt
   python tools/ncu_summary.py $OUT/$name.ncu-rep >> $OUT/$name.summary.txt 2>&1
-  ncu -i $OUT/$name.ncu-rep --page source --csv 2>/dev/null | python -c "
-import csv,sys
-rows=list(csv.reader(l for l in sys.stdin if l.startswith('\"')))
-if rows:
-    h=rows[0]; ix={n:i for i,n in enumerate(h)}
-    key=[n for n in h if 'Warp Stall Sampling (All' in n] or [n for n in h if 'Sampling' in n]
-    if key and 'Source' in ix:
-        k=ix[key[0]]; tot=sum(float(r[k] or 0) for r in rows[1:]) or 1
-        top=sorted(rows[1:], key=lambda r:-float(r[k] or 0))[:14]
-        print('top source lines by warp stall samples (%s):' % key[0])
-        for r in top: print('%6.2f%%  %s' % (100*float(r[k] or 0)/tot, r[ix['Source']].strip()[:150]))
-" > $OUT/$name.hotspots.txt 2>&1
+  python tools/ncu_hotspots.py $OUT/$name.ncu-rep 14 > $OUT/$name.hotspots.txt 2>&1
   [ "$KEEP" = "$name" ] || rm -f $OUT/$name.ncu-rep
 }
 echo "== launch lists"
