@@ -648,6 +648,29 @@ static void fill_target_csr(int V, int T, const int32_t* const* adj, const int32
     }
 }
 
+// Streaming plan: number the (target, type) pairs marked -2 ("several messages") in row order, replace the mark by -(2 + vid) and list
+// their sources (vinfo: count + the first seven inline; vptr / vsrc: the complete lists).  `pair` already holds -1 / the single source.
+static void number_virtual_rows(int ntiles, int T, const int* tile_start, const int* row_ptr, const int* csr_src, int* pair, int* vptr, int* vsrc,
+                                int* tvp, int* vinfo) {
+    int vid = 0, vm = 0;
+    vptr[0] = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        tvp[i] = vid;
+        for (size_t k = (size_t)tile_start[i] * T, kend = (size_t)tile_start[i + 1] * T; k < kend; ++k) {
+            if (pair[k] != -2) continue;
+            const int b = row_ptr[k], cnt = row_ptr[k + 1] - b;
+            pair[k] = -(2 + vid);
+            if (vinfo) {
+                vinfo[8 * vid] = cnt;
+                for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
+            }
+            for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
+            vptr[++vid] = vm;
+        }
+    }
+    tvp[ntiles] = vid;
+}
+
 // The tile plan ggnn_set_graph_sparse would make for this batch, without an engine or a GPU: the cut points (node boundaries no edge
 // crosses, from a difference array over the edge spans) and build_plan() on a scratch engine object that never touches CUDA.
 int ggnn_host_tile_plan(int32_t hidden_size, int32_t num_edge_types, int32_t precision, int32_t num_sms, int32_t V, const int32_t* const* adj,
@@ -700,6 +723,31 @@ int ggnn_host_target_csr(int32_t V, int32_t T, const int32_t* const* adj, const 
     }
     if (M > 0 && (!src || !msg)) return GGNN_EINVAL;
     fill_target_csr(V, T, adj, num_edges, counts, row_ptr, src, msg);
+    return GGNN_OK;
+}
+
+int ggnn_host_stream_tables(int32_t V, int32_t T, const int32_t* const* adj, const int32_t* num_edges, int32_t* pair_src, int32_t* vrow_ptr,
+                            int32_t vrow_capacity, int32_t* vsrc, int32_t vsrc_capacity, int32_t* tile_vptr, int32_t* num_virtual_rows) {
+    if (V < 0 || T <= 0 || !adj || !num_edges || !pair_src || !vrow_ptr || !vsrc || !tile_vptr || !num_virtual_rows) return GGNN_EINVAL;
+    std::vector<int> row_ptr((size_t)V * T + 1), src, msg;
+    int64_t M = 0;
+    for (int t = 0; t < T; ++t) M += num_edges[t];
+    src.resize((size_t)std::max<int64_t>(M, 1)); msg.resize((size_t)std::max<int64_t>(M, 1));
+    int rc = ggnn_host_target_csr(V, T, adj, num_edges, row_ptr.data(), src.data(), msg.data());
+    if (rc) return rc;
+    const int ntiles = (V + ts::TILE_M - 1) / ts::TILE_M;
+    std::vector<int> tile_start(ntiles + 1);
+    for (int i = 0; i <= ntiles; ++i) tile_start[i] = std::min(i * ts::TILE_M, V);
+    int nv = 0; int64_t nvm = 0;
+    for (size_t k = 0; k < (size_t)V * T; ++k) {
+        const int cnt = row_ptr[k + 1] - row_ptr[k];
+        pair_src[k] = cnt == 0 ? -1 : (cnt == 1 ? src[row_ptr[k]] : -2);
+        if (cnt >= 2) { ++nv; nvm += cnt; }
+    }
+    for (size_t k = (size_t)V * T; k < (size_t)ntiles * ts::TILE_M * T; ++k) pair_src[k] = -1;
+    if (nv + 1 > vrow_capacity || nvm > vsrc_capacity) return GGNN_EINVAL;
+    number_virtual_rows(ntiles, T, tile_start.data(), row_ptr.data(), src.data(), pair_src, vrow_ptr, vsrc, tile_vptr, nullptr);
+    *num_virtual_rows = nv;
     return GGNN_OK;
 }
 
@@ -859,22 +907,7 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
         int* vsrc = (int*)(base + e->off_vsrc);
         int* tvp = (int*)(base + e->off_tvp);
         int* vinfo = (int*)(base + e->off_vinfo);
-        // number the pairs with several messages ("virtual rows") in row order and list their sources
-        int vid = 0, vm = 0;
-        vptr[0] = 0;
-        for (int i = 0; i < ntiles; ++i) {
-            tvp[i] = vid;
-            for (size_t k = (size_t)tile_start[i] * T, kend = (size_t)tile_start[i + 1] * T; k < kend; ++k) {
-                if (pair[k] != -2) continue;
-                const int b = row_ptr[k], cnt = row_ptr[k + 1] - b;
-                pair[k] = -(2 + vid);
-                vinfo[8 * vid] = cnt;
-                for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
-                for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
-                vptr[++vid] = vm;
-            }
-        }
-        tvp[ntiles] = vid;
+        number_virtual_rows(ntiles, T, tile_start.data(), row_ptr, csr_src, pair, vptr, vsrc, tvp, vinfo);
     }
     if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
         int* trow = (int*)(base + e->off_trow);
@@ -1139,10 +1172,14 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     const size_t bias_b = (size_t)3 * DP * sizeof(float) + csr_b + 64;
     const size_t avail = e->max_smem > 1024 ? e->max_smem - 1024 : 0;
     if (avail < 3 * opb + bias_b + stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
-    p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - 3 * opb - bias_b) / stage);
+    // four gather buffers when the tiles are compact, more than two edge types can be present and at least four ring slots remain
+    p.ngbuf = (e->local && p.kgs == 1024 && e->T > 2 && avail >= 5 * opb + bias_b + 4 * stage) ? 4 : 2;
+    if (const char* gb = getenv("GGNN_TC_GBUFS")) p.ngbuf = (atoi(gb) == 4 && avail >= 5 * opb + bias_b + stage) ? 4 : 2;
+    const size_t ops = (size_t)(p.ngbuf + 1) * opb;
+    p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - ops - bias_b) / stage);
     if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(1, std::min(p.nstages, atoi(ns)));
     if (p.nstages < 1) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the weight ring (DP=%d)", DP);
-    const size_t smem = 3 * opb + bias_b + (size_t)p.nstages * stage;
+    const size_t smem = ops + bias_b + (size_t)p.nstages * stage;
     char* g = (char*)e->graph_buf.ptr;
     p.tile_start = (const int*)(g + e->off_tiles);
     p.tile_mask = (const unsigned*)(g + e->off_mask);

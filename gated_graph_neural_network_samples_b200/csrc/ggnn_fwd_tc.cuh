@@ -76,6 +76,8 @@ struct TcParams {
     int nparts;   // 3: bf16x3 (fp32-accurate), 1: single bf16 MMA
     int nstages;  // weight ring depth
     int kgs;            // A-operand k-group stride in bytes: 2048 (128-row tiles) or 1024 (compact: every tile has <= 64 rows)
+    int ngbuf;          // gather buffers: 2 (A_t alternates between the opA and opX tiles) or 4 (two more compact tiles: with <= 4 present edge
+                        // types every gather runs ahead of the MMAs of the previous type and the issuer never waits for an operand)
     int csr_cache;      // LOCAL sparse only: the tile's CSR slice is staged in shared memory (uint16 row offsets, uint8 local sources)
     int csr_cap_msgs;   // capacity of the shared source array
     const int* tile_start;
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     __shared__ __align__(8) uint64_t bar_xh_free;   // opH tile dead until the state update rewrites it (candidate phase)
     __shared__ __align__(8) uint64_t bar_a_ready;
     __shared__ __align__(8) uint64_t bar_mma_done;
-    __shared__ __align__(8) uint64_t bar_g1_done[2];   // one per gather buffer (opA, opX): its MMAs are complete
-    __shared__ __align__(8) uint64_t bar_g_ready[2];   // one per gather buffer: A_t written (never more than one phase pending each)
+    __shared__ __align__(8) uint64_t bar_g1_done[4];   // one per gather buffer (opA, opX, opB, opC): its MMAs are complete
+    __shared__ __align__(8) uint64_t bar_g_ready[4];   // one per gather buffer: A_t written (never more than one phase pending each)
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
 
@@ -281,7 +283,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
     uint8_t* opH = smem;
     uint8_t* opX = opH + OPB;
     uint8_t* opA = opX + OPB;
-    uint8_t* ring = opA + OPB;                             // nstages slots of 2*STAGE_B, 1024-byte aligned (DP*512 and DP*128 are multiples of 1024)
+    const int NGB = p.ngbuf;                               // gather buffers 2 and 3 (when present) sit between the opA tile and the ring
+    uint8_t* ring = opA + (size_t)OPB * (size_t)(NGB - 1); // nstages slots of 2*STAGE_B, 1024-byte aligned (DP*512 and DP*128 are multiples of 1024)
     float* sBias = reinterpret_cast<float*>(ring + (size_t)p.nstages * 2 * STAGE_B);   // [3*DP]: gate r | gate u | cand, zero padded
     uint16_t* sRowPtr = reinterpret_cast<uint16_t*>(sBias + 3 * DP);              // [128*T + 1] (csr_cache)
     uint8_t* sSrc = reinterpret_cast<uint8_t*>(sRowPtr + ((TILE_M * T + 1 + 7) & ~7)); // [csr_cap_msgs]
@@ -301,10 +304,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
         mbar_init(&bar_xh_free, NUM_ISSUERS);
         mbar_init(&bar_a_ready, NUM_WORKERS / 32);   // one arrival per worker warp
         mbar_init(&bar_mma_done, NUM_ISSUERS);      // one tcgen05.commit per issuer warp
-        mbar_init(&bar_g1_done[0], NUM_ISSUERS);
-        mbar_init(&bar_g1_done[1], NUM_ISSUERS);
-        mbar_init(&bar_g_ready[0], NUM_WORKERS / 32);
-        mbar_init(&bar_g_ready[1], NUM_WORKERS / 32);
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_g1_done[i], NUM_ISSUERS); mbar_init(&bar_g_ready[i], NUM_WORKERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == WARP_PROD) {
@@ -454,9 +454,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 const int g_nkc = gsplit ? nkc_tile : NKC;
                 for (int t = 0; t < T && ok; ++t) {
                     if (!((tmask >> t) & 1u)) continue;
-                    const int b = nty & 1;
-                    if (nty >= 2) { wait_g1(b); if (!ok) break; }   // the MMAs that read this buffer two types ago are done
-                    uint8_t* gdst = b ? opX : opA;
+                    const int b = nty % NGB;
+                    if (nty >= NGB) { wait_g1(b); if (!ok) break; }   // the MMAs that read this buffer NGB types ago are done
+                    uint8_t* gdst = b == 0 ? opA : (b == 1 ? opX : opA + (size_t)OPB * (size_t)(b - 1));
                     ++nty;
                     int beg = 0, end = 0, dg = 0, di = 0;
                     if (g_row_ok) {
@@ -542,8 +542,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                 if (!ok) break;
                 const bool have_msgs = nty > 0;
                 // all G1 MMAs complete (last use of each gather buffer) before opX is rewritten / the accumulators are read
-                if (nty >= 2) wait_g1((nty - 2) & 1);
-                if (nty >= 1) wait_g1((nty - 1) & 1);
+                for (int i = max(0, nty - NGB); i < nty && ok; ++i) wait_g1(i % NGB);
                 if (!ok) break;
                 stamp();   // G1 done (agg accumulators ready)
                 // ------------------------------------------------------------ agg epilogue: + indeg.B, / (deg + 1e-7) -> opX
@@ -824,9 +823,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) ggnn_fwd_tc_kernel(const __grid_c
                     int nty = 0;
                     for (int t = 0; t < T && ok; ++t) {
                         if (!((tmask >> t) & 1u)) continue;
-                        wait_g_ready(nty & 1);
-                        gemm((nty & 1) ? opX16 : opA16, (uint32_t)DP, false, SET_BASE);
-                        commit_to(&bar_g1_done[nty & 1]);
+                        const int b = nty % NGB;
+                        wait_g_ready(b);
+                        gemm(b == 0 ? opA16 : (b == 1 ? opX16 : opA16 + (uint32_t)(b - 1) * (OPB >> 4)), (uint32_t)DP, false, SET_BASE);
+                        commit_to(&bar_g1_done[b]);
                         ++nty;
                     }
                     commit_to(&bar_xa_free);                        // every MMA that reads the opA tile (this step's G1, last step's G3) is tracked

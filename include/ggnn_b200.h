@@ -184,6 +184,14 @@ int ggnn_backward(ggnn_engine* e, const float* d_h_out, const ggnn_layer_grads* 
 int ggnn_host_target_csr(int32_t num_nodes, int32_t num_edge_types, const int32_t* const* adjacency_lists, const int32_t* num_edges,
                          int32_t* row_ptr, int32_t* src, int32_t* msg);
 
+/* The streaming plan's gather tables on their own (host arithmetic only; what ggnn_set_graph_sparse uploads when hidden_size > 128 or a
+ * component exceeds a tile): pair_src [ceil(V/128)*128*T] -- per (target, type) pair -1 (no message), the source node (exactly one) or
+ * -(2 + vid) (several messages: "virtual row" vid, numbered in (target, type) order); vrow_ptr [NV+1] / vsrc: the sources of every virtual
+ * row in message order; tile_vptr [ceil(V/128)+1]: first vid of every 128-row tile.  Capacities in entries; returns the counts. */
+int ggnn_host_stream_tables(int32_t num_nodes, int32_t num_edge_types, const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                            int32_t* pair_src, int32_t* vrow_ptr, int32_t vrow_capacity, int32_t* vsrc, int32_t vsrc_capacity,
+                            int32_t* tile_vptr, int32_t* num_virtual_rows);
+
 /* The tile plan ggnn_set_graph_sparse would make for this batch on a GPU with `num_sms` SMs -- host arithmetic only: tile_start
  * [num_tiles + 1] (first node of every tile; tile_capacity entries available) and the plan description.  Tiles are unions of whole
  * connected components whenever the largest component fits a tile (LOCAL plan); used by the CPU test-suite. */

@@ -87,3 +87,47 @@ def _init_flat():
 
 
 _init_flat()
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 300), st.integers(1, 5), st.integers(0, 900), st.integers(0, 2 ** 31 - 1))
+def test_stream_gather_tables_against_numpy(V, T, M, seed):
+    """The streaming plan's (target, type) -> source table and virtual rows (ggnn_host_stream_tables, the code ggnn_set_graph_sparse uploads)
+    against a NumPy restatement: bit-exact, including the message order inside every virtual row and the 128-row tile offsets."""
+    import ctypes as C
+    from gated_graph_neural_network_samples_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    types = rng.integers(0, T, size=M)
+    # skewed targets so that many pairs collect several messages
+    tgt = np.minimum((rng.random(M) ** 2 * V).astype(np.int64), V - 1)
+    src = rng.integers(0, V, size=M)
+    adjs = [np.ascontiguousarray(np.stack([src[types == t], tgt[types == t]], 1).astype(np.int32).reshape(-1, 2)) for t in range(T)]
+    ptrs = (C.c_void_p * T)(*[a.ctypes.data for a in adjs])
+    counts = (C.c_int32 * T)(*[a.shape[0] for a in adjs])
+    ntiles = (V + 127) // 128
+    pair = np.empty(max(ntiles, 1) * 128 * T, np.int32)
+    vptr = np.empty(V * T + 2, np.int32); vsrc = np.empty(M + 1, np.int32); tvp = np.empty(ntiles + 1, np.int32)
+    nv = C.c_int32()
+    assert lib.ggnn_host_stream_tables(V, T, ptrs, counts, pair.ctypes.data, vptr.ctypes.data, vptr.size, vsrc.ctypes.data, vsrc.size,
+                                       tvp.ctypes.data, C.byref(nv)) == 0
+    # NumPy restatement: messages in the reference's order (type-major, list order), grouped by (target, type) with a stable sort
+    m_src = np.concatenate([a[:, 0] for a in adjs]) if M else np.zeros(0, np.int64)
+    m_key = np.concatenate([a[:, 1].astype(np.int64) * T + t for t, a in enumerate(adjs)]) if M else np.zeros(0, np.int64)
+    order = np.argsort(m_key, kind="stable")
+    keys, starts, cnts = np.unique(m_key[order], return_index=True, return_counts=True)
+    want = np.full(ntiles * 128 * T, -1, np.int64)
+    want_lists, vid = [], 0
+    for k, s0, c in zip(keys, starts, cnts):
+        if c == 1:
+            want[k] = m_src[order[s0]]
+        else:
+            want[k] = -(2 + vid); vid += 1
+            want_lists.append(m_src[order[s0:s0 + c]])
+    assert nv.value == vid
+    np.testing.assert_array_equal(pair[:ntiles * 128 * T], want)
+    for i, lst in enumerate(want_lists):
+        np.testing.assert_array_equal(vsrc[vptr[i]:vptr[i + 1]], lst)
+    multi_keys = keys[cnts >= 2]
+    for i in range(ntiles + 1):
+        assert tvp[i] == int(np.sum(multi_keys < min(i * 128, V) * T))
