@@ -1172,9 +1172,10 @@ static int forward_tc(ggnn_engine* e, const float* h0, float* h_out, cudaStream_
     const size_t bias_b = (size_t)3 * DP * sizeof(float) + csr_b + 64;
     const size_t avail = e->max_smem > 1024 ? e->max_smem - 1024 : 0;
     if (avail < 3 * opb + bias_b + stage) return e->fail(GGNN_EUNSUPPORTED, "not enough shared memory for the tensor-core tile (DP=%d)", DP);
-    // four gather buffers when the tiles are compact, more than two edge types can be present and at least four ring slots remain
-    p.ngbuf = (e->local && p.kgs == 1024 && e->T > 2 && avail >= 5 * opb + bias_b + 4 * stage) ? 4 : 2;
-    if (const char* gb = getenv("GGNN_TC_GBUFS")) p.ngbuf = (atoi(gb) == 4 && avail >= 5 * opb + bias_b + stage) ? 4 : 2;
+    // two gather buffers; GGNN_TC_GBUFS=4 adds two more compact tiles so that every gather runs ahead of the previous type's MMAs
+    // (measured: no gain -- cfg2 0.0870 vs 0.0862 ms, the G1 phase is bound by the gathers themselves, not by the number of buffers; opt-in)
+    p.ngbuf = 2;
+    if (const char* gb = getenv("GGNN_TC_GBUFS")) p.ngbuf = (atoi(gb) == 4 && e->local && p.kgs == 1024 && avail >= 5 * opb + bias_b + stage) ? 4 : 2;
     const size_t ops = (size_t)(p.ngbuf + 1) * opb;
     p.nstages = (int)std::min<size_t>(tc::MAX_STAGES, (avail - ops - bias_b) / stage);
     if (const char* ns = getenv("GGNN_TC_STAGES")) p.nstages = std::max(1, std::min(p.nstages, atoi(ns)));
