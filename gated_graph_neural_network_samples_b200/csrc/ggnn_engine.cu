@@ -677,19 +677,20 @@ int ggnn_host_tile_plan(int32_t hidden_size, int32_t num_edge_types, int32_t pre
                         const int32_t* num_edges, int32_t* tile_start, int32_t tile_capacity, int32_t* num_tiles, char* plan_text,
                         int32_t plan_text_capacity) {
     if (hidden_size <= 0 || num_edge_types <= 0 || V < 0 || !adj || !num_edges || !tile_start || !num_tiles || num_sms <= 0) return GGNN_EINVAL;
-    std::vector<int> diff((size_t)V + 2, 0);
+    // same cut detection as ggnn_set_graph_sparse: reach[j] = farthest node an edge starting at node j touches
+    std::vector<int> reach((size_t)V + 1, 0);
     for (int t = 0; t < num_edge_types; ++t)
         for (int i = 0; i < num_edges[t]; ++i) {
             const int s = adj[t][2 * i], d = adj[t][2 * i + 1];
             if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) return GGNN_ERANGE;
             const int lo = std::min(s, d), hi = std::max(s, d);
-            if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
+            if (hi > reach[lo]) reach[lo] = hi;
         }
     std::vector<int> cuts(1, 0);
-    int cover = 0;
+    int far = 0;
     for (int i = 1; i < V; ++i) {
-        cover += diff[i];
-        if (cover == 0) cuts.push_back(i);
+        far = std::max(far, reach[i - 1]);
+        if (far < i) cuts.push_back(i);
     }
     if (V > 0) cuts.push_back(V);
     ggnn_engine scratch;
@@ -784,7 +785,10 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     std::vector<int> cuts;
     cuts.push_back(0);
     if (need_cuts) {
-        diff.assign((size_t)V + 2, 0);
+        // reach[j] = the farthest node an edge starting at (or below) node j touches: the boundary before node i is crossed by an edge
+        // iff max_{j < i} reach[j] >= i  (one write per edge instead of the two of a difference array)
+        std::vector<int>& reach = diff;
+        reach.assign((size_t)V + 1, 0);
         for (int t = 0; t < T; ++t) {
             const int32_t* a = adj[t];
             for (int i = 0; i < num_edges[t]; ++i) {
@@ -793,13 +797,13 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
                     return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
                 ++counts[(size_t)d * T + t + 1];
                 const int lo = std::min(s, d), hi = std::max(s, d);
-                if (hi > lo) { ++diff[lo + 1]; --diff[hi + 1]; }
+                if (hi > reach[lo]) reach[lo] = hi;
             }
         }
-        int cover = 0;
+        int far = 0;
         for (int i = 1; i < V; ++i) {
-            cover += diff[i];
-            if (cover == 0) cuts.push_back(i);
+            far = std::max(far, reach[i - 1]);
+            if (far < i) cuts.push_back(i);
         }
     } else {
         for (int t = 0; t < T; ++t) {

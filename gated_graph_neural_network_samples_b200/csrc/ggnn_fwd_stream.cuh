@@ -304,6 +304,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
             const int wt = tid - 64;
             // ---- the tile's (target, type) -> source table
             for (int i = wt; i < TILE_M * T; i += NWORK * 32) sPair[i] = p.pair_src[(size_t)row0 * T + i];
+            const long long t_pair = stamp ? clock64() : 0;
             // ---- virtual rows: the pairs of this tile with several messages, summed in message order (fp32), re-split, stored as image rows.
             // (Batches where most pairs have several messages -- dense graphs -- sum them in the gather loop instead: p.virt_rows == 0.)
             if (p.virt_rows) {
@@ -319,7 +320,9 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                     *reinterpret_cast<uint4*>(vp + 4096) = l0;
                     *reinterpret_cast<uint4*>(vp + 6144) = l1;
                 }
+                const long long t_virt = stamp ? clock64() : 0;
                 __threadfence();   // the copies below read these rows back through L2 (cp.async.cg)
+                if (stamp) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[12] = t_pair - t0; d[13] = t_virt - t0; d[14] = clock64() - t0; d[15] = nv; }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
             if (stamp) t_setup = clock64();

@@ -42,7 +42,7 @@ for li in range(per_step * steps):
     ctas = ntiles * (nb[1] if kind == "gate" else nb[0])
     d = buf[li * stride: li * stride + ctas * 16].reshape(ctas, 16)
     med = lambda c: int(np.median(d[:, c]))
-    print("%-6s %5d %9d %9d %9d %9d | %9d %9d %9d | setup %6d load %7d wait %7d tail %7d" % (kind, med(7), med(1) if kind == "edge" else 0, med(2), med(3), med(3) - med(2), med(4), med(5), med(6), med(11), med(8), med(9), med(10)))
+    print("%-6s %5d %9d %9d %9d %9d | %9d %9d %9d | setup %6d load %7d wait %7d tail %7d" % (kind, med(7), med(1) if kind == "edge" else 0, med(2), med(3), med(3) - med(2), med(4), med(5), med(6), med(11), med(8), med(9), med(10)) + ("  [setup: pair table %d, virtual rows %d (nv %d), fence %d]" % (med(12), med(13), med(15), med(14)) if kind == "edge" else ""))
 
 # K-step timeline of CTA (0,0) for the first launch of each kind (clocks relative to the CTA's first stamp)
 for li in range(per_step):
