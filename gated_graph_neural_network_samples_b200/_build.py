@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libggnn_b200.so")
 NVCC_FLAGS = ["-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-std=c++17"]
+              "-std=c++17", "-Xcompiler", "-fopenmp", "-lgomp"]   # OpenMP: the host-side scan of a dense adjacency (ggnn_set_graph_dense)
 if os.environ.get("GGNN_TC_TRACE") == "1":   # trace build: phase stamps / event log of the tile-local tcgen05 kernel (tools/tc_trace.py)
     NVCC_FLAGS.append("-DGGNN_TC_TRACE")
 

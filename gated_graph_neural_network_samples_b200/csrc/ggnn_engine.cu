@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -970,33 +973,65 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
         std::vector<std::vector<int32_t>> lists(T);
         std::vector<float> indeg;
         if (binary) {
+            // The scan is a stream over b*T*v*v floats (4 MB at cfg3) of which ~99 % are zero: memory-bound on one core (~0.5 ms), so the
+            // graphs are split into contiguous ranges over a few OpenMP threads; every thread appends to its own per-type lists (order inside
+            // a range: graph, target row, source column) and the ranges are concatenated in order -- the result is the single-thread list.
             indeg.assign((size_t)std::max(V, 1) * T, 0.0f);
-            for (int t = 0; t < T; ++t) lists[t].reserve((size_t)V * 6);
-            for (int g = 0; g < b && binary; ++g)
-                for (int t = 0; t < T && binary; ++t) {
-                    const float* m = adjm + ((size_t)g * T + t) * v * v;
-                    std::vector<int32_t>& lst = lists[t];
-                    for (int i = 0; i < v && binary; ++i) {
-                        const float* row = m + (size_t)i * v;
-                        int cnt = 0;
-                        auto visit = [&](int j) {
-                            const float a = row[j];
-                            if (a != 0.0f) {
-                                if (a != 1.0f) { binary = false; return; }
-                                lst.push_back(g * v + j);   // source
-                                lst.push_back(g * v + i);   // target
-                                ++cnt;
+            int nthreads = 1;
+#ifdef _OPENMP
+            nthreads = std::max(1, std::min(std::min(8, omp_get_max_threads()), b / 8));
+            if (const char* nt = getenv("GGNN_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(nt), std::max(b, 1)));
+#endif
+            std::vector<std::vector<std::vector<int32_t>>> part(nthreads, std::vector<std::vector<int32_t>>(T));
+            std::vector<int> bad(nthreads, 0);
+            const int chunk = (b + nthreads - 1) / std::max(nthreads, 1);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+#endif
+            for (int k = 0; k < nthreads; ++k) {
+                std::vector<std::vector<int32_t>>& mine = part[k];
+                const int g0 = k * chunk, g1 = std::min(b, g0 + chunk);
+                for (int t = 0; t < T; ++t) mine[t].reserve((size_t)std::max(g1 - g0, 0) * v * 3);
+                bool ok = true;
+                for (int g = g0; g < g1 && ok; ++g)
+                    for (int t = 0; t < T && ok; ++t) {
+                        const float* m = adjm + ((size_t)g * T + t) * v * v;
+                        std::vector<int32_t>& lst = mine[t];
+                        for (int i = 0; i < v && ok; ++i) {
+                            const float* row = m + (size_t)i * v;
+                            int cnt = 0;
+                            auto visit = [&](int j) {
+                                const float a = row[j];
+                                if (a != 0.0f) {
+                                    if (a != 1.0f) { ok = false; return; }
+                                    lst.push_back(g * v + j);   // source
+                                    lst.push_back(g * v + i);   // target
+                                    ++cnt;
+                                }
+                            };
+                            int j = 0;
+                            for (; j + 4 <= v && ok; j += 4) {   // test 16 bytes at a time
+                                uint64_t w0, w1;
+                                memcpy(&w0, row + j, 8); memcpy(&w1, row + j + 2, 8);
+                                if ((w0 | w1) == 0) continue;
+                                visit(j); visit(j + 1); visit(j + 2); visit(j + 3);
                             }
-                        };
-                        int j = 0;
-                        for (; j + 4 <= v && binary; j += 4) {   // the matrix is ~99% zeros: test 16 bytes at a time
-                            uint64_t w0, w1;
-                            memcpy(&w0, row + j, 8); memcpy(&w1, row + j + 2, 8);
-                            if ((w0 | w1) == 0) continue;
-                            visit(j); visit(j + 1); visit(j + 2); visit(j + 3);
+                            for (; j < v && ok; ++j) visit(j);
+                            indeg[((size_t)g * v + i) * T + t] = (float)cnt;
                         }
-                        for (; j < v && binary; ++j) visit(j);
-                        indeg[((size_t)g * v + i) * T + t] = (float)cnt;
+                    }
+                bad[k] = ok ? 0 : 1;
+            }
+            for (int k = 0; k < nthreads; ++k) binary = binary && !bad[k];
+            if (binary)
+                for (int t = 0; t < T; ++t) {
+                    size_t total = 0;
+                    for (int k = 0; k < nthreads; ++k) total += part[k][t].size();
+                    lists[t].resize(total);
+                    size_t off = 0;
+                    for (int k = 0; k < nthreads; ++k) {
+                        if (!part[k][t].empty()) memcpy(lists[t].data() + off, part[k][t].data(), part[k][t].size() * sizeof(int32_t));
+                        off += part[k][t].size();
                     }
                 }
         }
