@@ -194,3 +194,83 @@ def test_error_growth_over_32_timesteps_stays_inside_the_bar(D, T, plan):
                                precision=PREC, return_engine=True)
     assert plan in eng.plan
     _check(got, ref, "32 timesteps D=%d" % D)
+
+
+def test_hub_nodes_with_many_messages_per_type():
+    """Virtual rows of every length: a hub receiving 40 messages of one type (the source list continues past the 7 inline entries of
+    vinfo), nodes with 3..12 messages, duplicates and self loops -- summed in message order like TF's CPU unsorted_segment_sum."""
+    rng = np.random.default_rng(7)
+    V, T, D = 300, 3, 256
+    p = dict(CFG4, layer_timesteps=[2], residual_connections={}, use_edge_bias=True)
+    adj = []
+    for t in range(T):
+        e = [(int(s), 0) for s in rng.integers(1, V, size=40)] if t == 1 else []          # the hub (node 0), type 1
+        for tgt in range(5, 120, 5):                                                       # 3 .. 12 messages into a few nodes
+            e += [(int(s), tgt) for s in rng.integers(0, V, size=3 + (tgt // 5) % 10)]
+        e += [(10, 10), (10, 10), (200, 299), (299, 200)]                                  # self loop twice, a pair across the tile boundary
+        e = np.asarray(sorted(e), np.int32).reshape(-1, 2)
+        adj.append(e)
+    indeg = np.zeros((V, T), np.float32)
+    for t in range(T):
+        np.add.at(indeg[:, t], adj[t][:, 1], 1)
+    h0 = rng.normal(0, 0.3, (V, D)).astype(np.float32)
+    w = O.init_sparse_weights(p, T, np.random.default_rng(1))
+    ref = O.sparse_propagation_np(h0, adj, indeg, w, p, dtype=np.float64)
+    got, eng = U.engine_sparse(p, T, w, adj, indeg, h0, precision=PREC, return_engine=True)
+    assert "STREAM" in eng.plan
+    _check(got, ref, "hub nodes")
+
+
+@pytest.mark.parametrize("ksteps,stages", [("1", "8"), ("1", "2"), ("2", "3"), ("4", "2"), ("4", "3"), ("3", "5")])
+def test_ring_geometry_does_not_change_the_result(monkeypatch, ksteps, stages):
+    """K-steps per stage and ring depth (incl. fewer stages than gather groups, partial last stages of a K segment) only change the
+    schedule: the result must stay bit-identical to the default geometry."""
+    _, b = U.molecule_batch(40, 256, T=8, seed=21)
+    w = O.init_sparse_weights(CFG4, 8, np.random.default_rng(1))
+    args = (CFG4, 8, w, b["adjacency_lists"], b["num_incoming_edges_per_type"], b["initial_node_representation"])
+    base = U.engine_sparse(*args, precision=PREC)
+    monkeypatch.setenv("GGNN_TS_KSTEPS", ksteps)
+    monkeypatch.setenv("GGNN_TS_STAGES", stages)
+    got = U.engine_sparse(*args, precision=PREC)
+    np.testing.assert_array_equal(got, base)
+
+
+def test_twelve_edge_types_and_hidden_100_padding(monkeypatch):
+    """More edge types than any BASELINE configuration (tile masks, K segments) on the forced streaming plan at a hidden size that is
+    not a multiple of 16 (DP = 112: seven K-steps per segment, a partial last stage)."""
+    monkeypatch.setenv("GGNN_TC_STREAM", "1")
+    rng = np.random.default_rng(3)
+    V, T, D = 500, 12, 100
+    p = dict(CFG2, hidden_size=D, layer_timesteps=[2, 1], residual_connections={"1": [0]})
+    adj = []
+    for t in range(T):
+        n = 0 if t == 5 else int(rng.integers(20, 400))                                    # one type without any edge
+        e = np.stack([rng.integers(0, V, n), rng.integers(0, V, n)], 1).astype(np.int32).reshape(-1, 2)
+        adj.append(e[np.lexsort((e[:, 1], e[:, 0]))] if n else e)
+    indeg = np.zeros((V, T), np.float32)
+    for t in range(T):
+        np.add.at(indeg[:, t], adj[t][:, 1], 1)
+    h0 = rng.normal(0, 0.3, (V, D)).astype(np.float32)
+    w = O.init_sparse_weights(p, T, np.random.default_rng(2))
+    ref = O.sparse_propagation_np(h0, adj, indeg, w, p, dtype=np.float64)
+    got, eng = U.engine_sparse(p, T, w, adj, indeg, h0, precision=PREC, return_engine=True)
+    assert "STREAM" in eng.plan
+    _check(got, ref, "12 edge types")
+
+
+def test_dense_binary_adjacency_at_hidden_256_and_weighted_refusal():
+    """The dense plug-in at hidden 256: a 0/1 adjacency becomes a CSR and streams; a weighted one has no tensor-core path above
+    hidden 128 and says so (it runs on GGNN_PREC_FP32)."""
+    from gated_graph_neural_network_samples_b200.engine import GgnnError
+    D, T, steps = 256, 4, 2
+    mols = synthetic.make_molecules(20, seed=9)
+    db = packing.pack_dense_batch(mols, 32, D, T)
+    h0 = (db["initial_node_representation"] + np.random.default_rng(2).normal(0, 0.1, db["initial_node_representation"].shape)).astype(np.float32)
+    dw = O.init_dense_weights({"hidden_size": D}, T, np.random.default_rng(5))
+    dp = {"num_timesteps": steps, "use_edge_bias": True}
+    _check(U.engine_dense(dp, T, dw, db["adjacency_matrix"], h0, precision=PREC), O.dense_propagation_loops(h0, db["adjacency_matrix"], dw, dp), "dense D=256")
+    weighted = db["adjacency_matrix"] * 0.5
+    with pytest.raises(GgnnError, match="weighted dense adjacency"):
+        U.engine_dense(dp, T, dw, weighted, h0, precision=PREC)
+    got = U.engine_dense(dp, T, dw, weighted, h0, precision="fp32")
+    assert U.max_rel_err(got, O.dense_propagation_loops(h0, weighted, dw, dp)) < 1e-4
