@@ -157,6 +157,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
     __shared__ __align__(8) uint64_t bar_afull[MAX_NS];   // gathered A written (GATHER)
     __shared__ __align__(8) uint64_t bar_empty[MAX_NS];   // the MMAs that read the stage are complete
     __shared__ __align__(8) uint64_t bar_acc;             // all MMAs of the tile are complete
+    __shared__ __align__(8) uint64_t bar_virt[16];        // GATHER: the virtual rows of K group j are written (by the gather groups that have no ring slot)
     __shared__ uint32_t s_tmem;
     __shared__ int s_abort;
     __shared__ int s_types[32];
@@ -179,6 +180,10 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         s_abort = 0;
         for (int i = 0; i < MAX_NS; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_afull[i], TILE_M); tc::mbar_init(&bar_empty[i], 1); }
         tc::mbar_init(&bar_acc, 1);
+        {   // gather groups beyond the ring depth have no stage to fill: they pre-sum the virtual rows of K groups 1.. while the others gather
+            const int idle_warps = (NWORK / 4 - min(NWORK / 4, NS)) * 4;
+            for (int i = 0; i < 16; ++i) tc::mbar_init(&bar_virt[i], idle_warps > 0 ? idle_warps : 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         int n = 0;
         if (GATHER) {
@@ -228,7 +233,10 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 }
                 tc::bulk_copy_g2s(st + A_REGION_B, wb + (size_t)seg_k0 * B_STEP_B, (uint32_t)nks * B_STEP_B, &bar_full[s]);
                 if (d2) d2[7] = clock64();
-                if (++j == GPS) { j = 0; ++sg; }
+                // K order: TMA-fed kernels walk segment by segment; the gather GEMM walks K group by K group over all edge types (the virtual
+                // rows of K group 0 are then enough to start, the rest are pre-summed while the ring already turns)
+                if (GATHER) { if (++sg == nsegs) { sg = 0; ++j; } }
+                else if (++j == GPS) { j = 0; ++sg; }
                 if (++s == NS) { s = 0; ++round; }
             }
             if (!ok) atomicExch(p.error_flag, 13);
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = STAGE_B >> 4, aregion16 = A_REGION_B >> 4, bstep16 = B_STEP_B >> 4;
         const uint32_t tm_d = __shfl_sync(0xffffffffu, tmem, 0);
         long long waited_b = 0, waited_a = 0;
-        int j = 0, s = 0;
+        int j = 0, sgi = 0, s = 0;
         uint32_t par = 0;
         for (int g = 0; g < ng && ok; ++g) {
             const long long w0 = p.dbg ? clock64() : 0;
@@ -276,7 +284,8 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
             }
             __syncwarp();
             if (d2) d2[2] = clock64();
-            if (++j == GPS) j = 0;
+            if (GATHER) { if (++sgi == nsegs) { sgi = 0; ++j; } }
+            else if (++j == GPS) j = 0;
             if (++s == NS) { s = 0; par ^= 1u; }
         }
         if (!ok && lane == 0) atomicExch(p.error_flag, 12);
@@ -306,11 +315,16 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
             for (int i = wt; i < TILE_M * T; i += NWORK * 32) sPair[i] = p.pair_src[(size_t)row0 * T + i];
             const long long t_pair = stamp ? clock64() : 0;
             // ---- virtual rows: the pairs of this tile with several messages, summed in message order (fp32), re-split, stored as image rows.
-            // (Batches where most pairs have several messages -- dense graphs -- sum them in the gather loop instead: p.virt_rows == 0.)
-            if (p.virt_rows) {
-                const int v0 = p.tile_vptr[tile], nv = p.tile_vptr[tile + 1] - v0;
-                for (int task = wt; task < nv * NKS; task += NWORK * 32) {
-                    const int vid = v0 + task / NKS, ks = task % NKS;
+            // The K loop of the gather GEMM is K-group major, so only the virtual rows of K group 0 must exist before the first stage:
+            // all workers pre-sum those; the groups beyond the ring depth (no stage to fill, see below) then pre-sum K groups 1.. and signal
+            // each one on bar_virt[j] while the other groups already gather.  Without surplus groups everything is pre-summed up front.
+            // (p.virt_rows == 0: pairs with several messages are summed inside the gather loop instead.)
+            const int NGE = min(NG, NS);
+            const int v0 = p.tile_vptr[tile], nv = p.virt_rows ? p.tile_vptr[tile + 1] - v0 : 0;
+            auto presum = [&](int jg, int first, int nthreads_) {   // virtual rows of K group jg, tasks dealt to `nthreads_` threads
+                const int ks0 = jg * KS, nks = min(KS, NKS - ks0);
+                for (int task = first; task < nv * nks; task += nthreads_) {
+                    const int vl = task / nks, vid = v0 + vl, ks = ks0 + (task - vl * nks);
                     const int4 i0 = __ldg(p.vinfo + 2 * (size_t)vid), i1 = __ldg(p.vinfo + 2 * (size_t)vid + 1);
                     uint4 h0, l0, h1, l1;
                     sum_pair_sources(p.g_img, NKS, ks, i0, i1, p.vsrc + p.vrow_ptr[i0.x > 7 ? vid : 0], h0, h1, l0, l1);
@@ -320,26 +334,45 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                     *reinterpret_cast<uint4*>(vp + 4096) = l0;
                     *reinterpret_cast<uint4*>(vp + 6144) = l1;
                 }
+            };
+            // worth it only if the surplus groups finish a K group's virtual rows (~7 k cycles per round of tasks) within the ~450 cycles per
+            // K-step the ring needs to get there: molecule batches yes (cfg4: 42 virtual rows per tile), dense graphs no (cfg5: ~300)
+            const int nidle_thr = (NG - NGE) * 128;
+            const bool overlap = NGE < NG && ((nv * KS + nidle_thr - 1) / max(nidle_thr, 1)) * 16 <= nsegs * KS;
+            if (p.virt_rows) {
+                for (int jg = 0; jg < (overlap ? 1 : GPS); ++jg) presum(jg, wt, NWORK * 32);
                 const long long t_virt = stamp ? clock64() : 0;
                 __threadfence();   // the copies below read these rows back through L2 (cp.async.cg)
                 if (stamp) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[12] = t_pair - t0; d[13] = t_virt - t0; d[14] = clock64() - t0; d[15] = nv; }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
             if (stamp) t_setup = clock64();
+            if (overlap && grp >= NGE && p.virt_rows) {
+                const int nidle = (NG - NGE) * 128, me = (grp - NGE) * 128 + gi;
+                for (int jg = 1; jg < GPS; ++jg) {
+                    presum(jg, me, nidle);
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_virt[jg]);
+                }
+            }
             // group `grp` fills stages grp, grp + NGE, ...: every row is an asynchronous 64-byte copy per K-step (or zeros).
             // No more groups than ring stages: a parity wait on a stage's barrier is only sound if the waiter cannot be two phases ahead
             // of it, and group X waiting for round r of a stage has (through its previous stage, NGE K-groups back) only seen round r-2
-            // complete when NS >= NGE.  Surplus groups idle (deep K-step stages leave room for 2-3 ring slots only).
-            const int NGE = min(NG, NS);
-            int sg = 0, j = grp;
-            while (j >= GPS) { j -= GPS; ++sg; }
+            // complete when NS >= NGE.  Surplus groups pre-sum virtual rows instead (above).
+            int j_seen = 0;
             for (int g = grp < NGE ? grp : ng; g < ng && ok; g += NGE) {
+                const int j = g / nsegs, sg = g - j * nsegs;   // K group major: stage g = (K group j, present edge type sg)
                 const long long c0 = stamp ? clock64() : 0;
                 const int s = g % NS, round = g / NS;
                 long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256 && gi == 0) ? p.dbg2 + g * 8 : nullptr;
                 if (d2) d2[3] = clock64();
                 const int ks0 = j * KS, nks = min(KS, NKS - ks0);
                 const int ps = sPair[gi * T + s_types[sg]];
+                if (ps < -1 && overlap && p.virt_rows && j > j_seen) {   // this K group's virtual rows come from the surplus groups
+                    if (!tc::mbar_wait(&bar_virt[j], 0, abortp)) *abortp = 1;
+                    j_seen = j;
+                }
                 const uint8_t* sp = nullptr;
                 if (ps >= 0) sp = p.g_img + ((size_t)(ps >> 7) * NKS + ks0) * A_STAGE_B + (size_t)(ps & 127) * 16;
                 else if (ps < -1 && p.virt_rows) { const int vid = -(ps + 2); sp = p.virt_img + ((size_t)(vid >> 7) * NKS + ks0) * A_STAGE_B + (size_t)(vid & 127) * 16; }
@@ -387,8 +420,6 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 }
                 if (d2) d2[5] = clock64();
                 if (stamp) { const long long c3 = clock64(); g_load += c1 - c0; g_wait += c2 - c1; g_tail += c3 - c2; }
-                j += NGE;
-                while (j >= GPS) { j -= GPS; ++sg; }
             }
             if (stamp) t_gather = clock64();
         }
