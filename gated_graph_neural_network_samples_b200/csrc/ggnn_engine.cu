@@ -1393,7 +1393,14 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
         dbg2_cur = q + dbg_slice;
         return q;
     };
-    auto tmem_cols = [](int NC) { int c = 32; while (c < NC) c *= 2; return c; };
+    auto tmem_cols = [](int cols) { int c = 32; while (c < cols) c *= 2; return c; };
+    // a TMA-fed launch whose N blocks would need more than one wave of CTAs lets every CTA compute two N blocks one after the other into two
+    // TMEM accumulators: the epilogue of the first runs under the mainloop of the second (the gate GEMM of a full batch: 2 x 256 columns)
+    auto passes_for = [&](int NC, int nblk) {
+        int np = ((long long)ntiles * nblk > e->num_sms && nblk % 2 == 0 && 2 * NC <= 512) ? 2 : 1;
+        if (const char* ev = getenv("GGNN_TS_PASSES")) np = (atoi(ev) == 2 && nblk % 2 == 0 && 2 * NC <= 512) ? 2 : 1;
+        return np;
+    };
     const int nc0 = e->ts_nc[0], nb0 = e->ts_nblk[0], nc1 = e->ts_nc[1], nb1 = e->ts_nblk[1];
     // one CTA per SM for all three kernels: the whole shared memory is the ring
     const int ns_edge = stages_for(nc0, avail > csr_b ? avail - csr_b : 0);
@@ -1432,7 +1439,7 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
             const size_t so = (size_t)gs * vd;
             // ---- aggregated messages
             ts::StreamParams p = base;
-            p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.ksteps = ksteps_for(nc0); p.tmem_cols = tmem_cols(nc0);
+            p.epi = ts::EPI_AGG; p.NC = nc0; p.nstages = ns_edge; p.ksteps = ksteps_for(nc0); p.npass = 1; p.tmem_cols = tmem_cols(nc0);
             p.g_img = img_in; p.w = wb + e->ts_off_edge[l]; p.kt_all = T * NKS;
             p.bias = e->use_bias ? e->w[l].edge_biases : nullptr;
             p.img_out = img_agg; p.sv_agg = e->save ? sv + per + so : nullptr; p.gstep = gs; p.dbg = next_dbg(); p.dbg2 = dbg2_cur;
@@ -1446,21 +1453,21 @@ static int forward_stream(ggnn_engine* e, const float* h0, float* h_out, cudaStr
             };
             if (gru) {
                 ts::StreamParams q = base;
-                q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.ksteps = ksteps_for(nc1); q.tmem_cols = tmem_cols(nc1);
+                q.epi = ts::EPI_GATE; q.NC = nc1; q.nstages = ns_gate; q.ksteps = ksteps_for(nc1); q.npass = passes_for(nc1, nb1); q.tmem_cols = tmem_cols(nc1 * q.npass);
                 set_segs(q, img_in);
                 q.w = wb + e->ts_off_gate[l]; q.bias = e->w[l].gate_bias; q.h_chk = chk_in; q.u_buf = u_chk; q.img_out = img_rh;
                 if (e->save) { q.sv_r = sv + 2 * per + so; q.sv_h = sv + so; q.sv_u = sv + 3 * per + so; }
                 q.gstep = gs; q.dbg = next_dbg(); q.dbg2 = dbg2_cur;
-                k_fed<<<dim3(ntiles, nb1), 18 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
+                k_fed<<<dim3(ntiles, nb1 / q.npass), 18 * 32, smem_of(nc1, ns_gate, false), st>>>(q);
                 ++e->last_launches;
             }
             ts::StreamParams c = base;
-            c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.ksteps = ksteps_for(nc0); c.tmem_cols = tmem_cols(nc0);
+            c.epi = ts::EPI_CAND; c.NC = nc0; c.nstages = ns_cand; c.ksteps = ksteps_for(nc0); c.npass = passes_for(nc0, nb0); c.tmem_cols = tmem_cols(nc0 * c.npass);
             set_segs(c, gru ? img_rh : img_in);
             c.w = wb + e->ts_off_cand[l]; c.bias = e->w[l].cand_bias; c.h_chk = chk_in; c.u_buf = u_chk; c.h_chk_out = chk_out; c.h_out = out; c.img_out = img_out;
             if (e->save) { if (gru) c.sv_c = sv + 4 * per + so; else c.sv_h = sv + so; }
             c.gstep = gs; c.dbg = next_dbg(); c.dbg2 = dbg2_cur;
-            k_fed<<<dim3(ntiles, nb0), 18 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
+            k_fed<<<dim3(ntiles, nb0 / c.npass), 18 * 32, smem_of(nc0, ns_cand, false), st>>>(c);
             ++e->last_launches;
             img_in = img_out; chk_in = chk_out;
         }

@@ -49,7 +49,9 @@ struct StreamParams {
     int nstages;           // ring depth
     int ksteps;            // K-steps (16 columns) per ring stage (4 unless the hidden size has fewer)
     int nparts;            // 3: bf16x3, 1: single bf16 MMA
-    int tmem_cols;         // power of two >= max(32, NC)
+    int npass;             // N blocks this CTA computes one after the other (TMA-fed kernels: accumulator of pass q in TMEM columns [q*NC, (q+1)*NC),
+                           // so the epilogue of pass q runs under the mainloop of pass q+1); grid.y * npass = number of N blocks
+    int tmem_cols;         // power of two >= max(32, npass*NC)
     int epi;               // EPI_*
     int cell, act, use_bias, use_avg;
     // ---- A operand, TMA-fed: nseg K segments, each a DP-wide tile-major image
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
     __shared__ __align__(8) uint64_t bar_full[MAX_NS];    // B (and TMA-fed A) bytes landed
     __shared__ __align__(8) uint64_t bar_afull[MAX_NS];   // gathered A written (GATHER)
     __shared__ __align__(8) uint64_t bar_empty[MAX_NS];   // the MMAs that read the stage are complete
-    __shared__ __align__(8) uint64_t bar_acc;             // all MMAs of the tile are complete
+    __shared__ __align__(8) uint64_t bar_acc[2];          // all MMAs of pass q are complete
     __shared__ __align__(8) uint64_t bar_virt[16];        // GATHER: the virtual rows of K group j are written (by the gather groups that have no ring slot)
     __shared__ uint32_t s_tmem;
     __shared__ int s_abort;
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
     __shared__ int s_ntypes;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tile = blockIdx.x, nb = blockIdx.y;
+    const int npass = GATHER ? 1 : p.npass;
+    const int tile = blockIdx.x, nb0 = blockIdx.y * npass;   // first N block of this CTA
     const int D = p.D, DP = p.DP, T = p.T, NC = p.NC, NS = p.nstages, KS = p.ksteps;
     const int NKS = DP >> 4;
     const int GPS = (NKS + KS - 1) / KS;              // stages ("K groups") per K segment; the last one of a segment may be partial
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < MAX_NS; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_afull[i], TILE_M); tc::mbar_init(&bar_empty[i], 1); }
-        tc::mbar_init(&bar_acc, 1);
+        tc::mbar_init(&bar_acc[0], 1); tc::mbar_init(&bar_acc[1], 1);
         {   // gather groups beyond the ring depth have no stage to fill: they pre-sum the virtual rows of K groups 1.. while the others gather
             const int idle_warps = (NWORK / 4 - min(NWORK / 4, NS)) * 4;
             for (int i = 0; i < 16; ++i) tc::mbar_init(&bar_virt[i], idle_warps > 0 ? idle_warps : 1);
@@ -211,16 +214,18 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         // those K-steps is ONE contiguous piece of the image, their B operand ONE contiguous piece of the pre-tiled weights.
         if (lane == 0) {
             bool ok = true;
-            const uint8_t* wb = p.w + (size_t)nb * p.kt_all * B_STEP_B;
             long long waited = 0;
-            int sg = 0, j = 0, s = 0, round = 0;
+            int s = 0, round = 0;
+            for (int pass = 0; pass < npass && ok; ++pass) {
+            const uint8_t* wb = p.w + (size_t)(nb0 + pass) * p.kt_all * B_STEP_B;
+            int sg = 0, j = 0;
             for (int g = 0; g < ng && ok; ++g) {
                 if (round > 0) {
                     const long long w0 = p.dbg ? clock64() : 0;
                     if (!tc::mbar_wait(&bar_empty[s], (uint32_t)(round - 1) & 1u, abortp)) { ok = false; break; }
                     if (p.dbg) waited += clock64() - w0;
                 }
-                long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256) ? p.dbg2 + g * 8 : nullptr;
+                long long* d2 = (p.dbg2 && tile == 0 && nb0 == 0 && g < 256) ? p.dbg2 + g * 8 : nullptr;
                 if (d2) d2[6] = clock64();
                 const int ks0 = j * KS, nks = min(KS, NKS - ks0);
                 uint8_t* st = smem + (size_t)s * STAGE_B;
@@ -239,8 +244,9 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 else if (++j == GPS) { j = 0; ++sg; }
                 if (++s == NS) { s = 0; ++round; }
             }
+            }
             if (!ok) atomicExch(p.error_flag, 13);
-            if (p.dbg) p.dbg[((size_t)nb * gridDim.x + tile) * 16 + 4] = waited;
+            if (p.dbg) p.dbg[((size_t)blockIdx.y * gridDim.x + tile) * 16 + 4] = waited;
         }
     } else if (warp == 1) {
         // =============================================================================== MMA ISSUER
@@ -253,15 +259,18 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         const uint32_t smem16 = smem_u32(smem) >> 4, stage16 = STAGE_B >> 4, aregion16 = A_REGION_B >> 4, bstep16 = B_STEP_B >> 4;
         const uint32_t tm_d = __shfl_sync(0xffffffffu, tmem, 0);
         long long waited_b = 0, waited_a = 0;
-        int j = 0, sgi = 0, s = 0;
+        int s = 0;
         uint32_t par = 0;
+        for (int pass = 0; pass < npass && ok; ++pass) {
+        const uint32_t tm_p = tm_d + (uint32_t)(pass * NC);
+        int j = 0, sgi = 0;
         for (int g = 0; g < ng && ok; ++g) {
             const long long w0 = p.dbg ? clock64() : 0;
             if (!tc::mbar_wait(&bar_full[s], par, abortp)) ok = false;
             const long long w1 = p.dbg ? clock64() : 0;
             if (GATHER && ok && !tc::mbar_wait(&bar_afull[s], par, abortp)) ok = false;
             if (p.dbg) { waited_b += w1 - w0; waited_a += clock64() - w1; }
-            long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256 && lane == 0) ? p.dbg2 + g * 8 : nullptr;
+            long long* d2 = (p.dbg2 && tile == 0 && nb0 == 0 && g < 256 && lane == 0) ? p.dbg2 + g * 8 : nullptr;
             if (d2) { d2[0] = w1; d2[1] = clock64(); }
             ok = __all_sync(0xffffffffu, ok);
             if (!ok) break;
@@ -273,14 +282,14 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 for (int i = 0; i < nks; ++i) {
                     const uint64_t ah = descA | (uint64_t)(a16 + (uint32_t)i * (A_STAGE_B >> 4)), al = ah + (4096u >> 4);
                     const uint64_t bh = descB | (uint64_t)(b16 + (uint32_t)i * bstep16), bl = bh + b_lo16;
-                    tc::umma_bf16(tm_d, ah, bh, idesc, (g > 0 || i > 0) ? 1u : 0u);
+                    tc::umma_bf16(tm_p, ah, bh, idesc, (g > 0 || i > 0) ? 1u : 0u);
                     if (x3) {
-                        tc::umma_bf16(tm_d, ah, bl, idesc, 1u);
-                        tc::umma_bf16(tm_d, al, bh, idesc, 1u);
+                        tc::umma_bf16(tm_p, ah, bl, idesc, 1u);
+                        tc::umma_bf16(tm_p, al, bh, idesc, 1u);
                     }
                 }
                 tc::umma_commit(&bar_empty[s]);
-                if (g == ng - 1) tc::umma_commit(&bar_acc);
+                if (g == ng - 1) tc::umma_commit(&bar_acc[pass]);
             }
             __syncwarp();
             if (d2) d2[2] = clock64();
@@ -288,8 +297,9 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
             else if (++j == GPS) j = 0;
             if (++s == NS) { s = 0; par ^= 1u; }
         }
+        }
         if (!ok && lane == 0) atomicExch(p.error_flag, 12);
-        if (p.dbg && lane == 0) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[5] = waited_b; d[6] = waited_a; }
+        if (p.dbg && lane == 0) { long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + tile) * 16; d[5] = waited_b; d[6] = waited_a; }
     } else {
         // =============================================================================== WORKERS
         const int wi = warp - 2;
@@ -300,7 +310,6 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         constexpr int NCG = NWORK / 4;                // epilogue column groups
         const int cgp = wi >> 2;
         const int nchunks = NC >> 3;
-        const int colb = nb * NC;                     // first (padded) output column of this CTA
         bool ok = true;
         const bool stamp = p.dbg && wi == 0 && lane == 0;
         long long t0 = 0, t_gather = 0, t_acc = 0, g_load = 0, g_wait = 0, g_tail = 0, t_setup = 0;
@@ -343,7 +352,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 for (int jg = 0; jg < (overlap ? 1 : GPS); ++jg) presum(jg, wt, NWORK * 32);
                 const long long t_virt = stamp ? clock64() : 0;
                 __threadfence();   // the copies below read these rows back through L2 (cp.async.cg)
-                if (stamp) { long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16; d[12] = t_pair - t0; d[13] = t_virt - t0; d[14] = clock64() - t0; d[15] = nv; }
+                if (stamp) { long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + tile) * 16; d[12] = t_pair - t0; d[13] = t_virt - t0; d[14] = clock64() - t0; d[15] = nv; }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
             if (stamp) t_setup = clock64();
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                 const int j = g / nsegs, sg = g - j * nsegs;   // K group major: stage g = (K group j, present edge type sg)
                 const long long c0 = stamp ? clock64() : 0;
                 const int s = g % NS, round = g / NS;
-                long long* d2 = (p.dbg2 && tile == 0 && nb == 0 && g < 256 && gi == 0) ? p.dbg2 + g * 8 : nullptr;
+                long long* d2 = (p.dbg2 && tile == 0 && nb0 == 0 && g < 256 && gi == 0) ? p.dbg2 + g * 8 : nullptr;
                 if (d2) d2[3] = clock64();
                 const int ks0 = j * KS, nks = min(KS, NKS - ks0);
                 const int ps = sPair[gi * T + s_types[sg]];
@@ -425,9 +434,11 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         }
         // ---- epilogue: accumulator -> registers -> outputs.  The global operands of the first chunk are requested BEFORE the wait for the
         // accumulator, those of chunk c+1 before the math of chunk c (the loads are L2 hits after the prefetch above).
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const bool have_acc = nk > 0;
         const bool gru = p.cell == CELL_GRU;
+        for (int pass = 0; pass < npass; ++pass) {
+        const int colb = (nb0 + pass) * NC;           // first (padded) output column of this pass
+        const uint32_t lane_addr = ((uint32_t)(q * 32) << 16) + (uint32_t)(pass * NC);
         // the global operands of this thread's next chunk are requested before the math of the current one
         float hA[8], uA[8];
 #pragma unroll
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
         };
         if (!GATHER) load_ops(cgp, hA, uA);
         if (nk > 0) {   // worker warp 0 polls for the accumulator, the others block on the hardware barrier behind it
-            if (wi == 0 && ok && !tc::mbar_wait(&bar_acc, 0, abortp)) *abortp = 1;
+            if (wi == 0 && ok && !tc::mbar_wait(&bar_acc[pass], 0, abortp)) *abortp = 1;
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
             if (*abortp) ok = false;
             tc::tc_fence_after();
@@ -550,9 +561,10 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 1) ggnn_stream_kernel(const 
                     if (!cand_chunk(c, hA, uA)) break;
             }
         }
+        }   // passes
         if (!ok && lane == 0) atomicExch(p.error_flag, 11);
         if (stamp) {
-            long long* d = p.dbg + ((size_t)nb * gridDim.x + tile) * 16;
+            long long* d = p.dbg + ((size_t)blockIdx.y * gridDim.x + tile) * 16;
             d[0] = t0; d[1] = t_gather - t0; d[2] = t_acc - t0; d[3] = clock64() - t0; d[7] = nk;
             d[8] = g_load; d[9] = g_wait; d[10] = g_tail; d[11] = t_setup - t0;
         }

@@ -40,6 +40,8 @@ print("%-6s %5s %9s %9s %9s %9s | %9s %9s %9s  (median cycles over CTAs; start s
 for li in range(per_step * steps):
     kind = names[li % per_step]
     ctas = ntiles * (nb[1] if kind == "gate" else nb[0])
+    if kind == "gate" and ntiles * nb[1] > 148 and nb[1] % 2 == 0:
+        ctas //= 2          # two N blocks per CTA (npass = 2)
     d = buf[li * stride: li * stride + ctas * 16].reshape(ctas, 16)
     med = lambda c: int(np.median(d[:, c]))
     print("%-6s %5d %9d %9d %9d %9d | %9d %9d %9d | setup %6d load %7d wait %7d tail %7d" % (kind, med(7), med(1) if kind == "edge" else 0, med(2), med(3), med(3) - med(2), med(4), med(5), med(6), med(11), med(8), med(9), med(10)) + ("  [setup: pair table %d, virtual rows %d (nv %d), fence %d]" % (med(12), med(13), med(15), med(14)) if kind == "edge" else ""))
