@@ -21,7 +21,8 @@ class GgnnConfig(C.Structure):
 
 class GgnnLayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")]
+                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights",
+                 "cand_hidden_bias")]
 
 
 class GgnnReadoutTask(C.Structure):
@@ -30,7 +31,8 @@ class GgnnReadoutTask(C.Structure):
 
 class GgnnLayerGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")]
+                ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights",
+                 "cand_hidden_bias")]
 
 
 # name -> (restype, argtypes): every symbol include/ggnn_b200.h declares

@@ -85,8 +85,10 @@ class SparseGGNNChemModel(ChemModel):
         if activation_name not in ('tanh', 'relu'):
             raise Exception("Unknown activation function type '%s'." % activation_name)          # sparse:81
         cell_type = self.params['graph_rnn_cell'].lower()
-        if cell_type not in ('gru', 'rnn'):
-            raise Exception("Unknown RNN cell type '%s'." % cell_type)                           # sparse:112 (CudnnCompatibleGRUCell: see DESIGN.md)
+        if cell_type not in ('gru', 'rnn', 'cudnncompatiblegrucell'):
+            raise Exception("Unknown RNN cell type '%s'." % cell_type)                           # sparse:112
+        if cell_type == 'cudnncompatiblegrucell':
+            assert activation_name == 'tanh'                                                     # sparse:106
         dev = self.device
 
         def var(a):
@@ -103,6 +105,14 @@ class SparseGGNNChemModel(ChemModel):
             if cell_type == 'gru':   # TF-1.3 GRUCell variables: gates kernel/bias (bias init 1.0), candidate kernel/bias
                 cell = {'gate_kernel': var(glorot_init([din + h_dim, 2 * h_dim])), 'gate_bias': var(np.ones(2 * h_dim)),
                         'cand_kernel': var(glorot_init([din + h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
+            elif cell_type == 'cudnncompatiblegrucell':
+                # tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell (sparse:105-108): gates as GRUCell; the candidate has two projections,
+                # input_projection [din, D] and hidden_projection [D, D] (each with its own zero-initialised bias, each glorot-
+                # initialised on its OWN shape by _linear).  They stay separate variables with TF's shapes (checkpoints); hook 2 stacks
+                # them into the engine's [din + D, D] candidate kernel
+                cell = {'gate_kernel': var(glorot_init([din + h_dim, 2 * h_dim])), 'gate_bias': var(np.ones(2 * h_dim)),
+                        'cand_input_kernel': var(glorot_init([din, h_dim])), 'cand_bias': var(np.zeros(h_dim)),
+                        'cand_hidden_kernel': var(glorot_init([h_dim, h_dim])), 'cand_hidden_bias': var(np.zeros(h_dim))}
             else:                    # BasicRNNCell
                 cell = {'cand_kernel': var(glorot_init([din + h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
             self.gnn_weights.rnn_cells.append(cell)
@@ -120,6 +130,11 @@ class SparseGGNNChemModel(ChemModel):
                    'cand_kernel': 'gru_cell/candidate/kernel', 'cand_bias': 'gru_cell/candidate/bias'}
         if self.params['graph_rnn_cell'].lower() == 'rnn':
             tf_cell = {'cand_kernel': 'basic_rnn_cell/kernel', 'cand_bias': 'basic_rnn_cell/bias'}
+        elif self.params['graph_rnn_cell'].lower() == 'cudnncompatiblegrucell':   # tf.contrib.cudnn_rnn (TF >= 1.4) variable scopes
+            c = 'cudnn_compatible_gru_cell/'
+            tf_cell = {'gate_kernel': c + 'gates/kernel', 'gate_bias': c + 'gates/bias',
+                       'cand_input_kernel': c + 'candidate/input_projection/kernel', 'cand_bias': c + 'candidate/input_projection/bias',
+                       'cand_hidden_kernel': c + 'candidate/hidden_projection/kernel', 'cand_hidden_bias': c + 'candidate/hidden_projection/bias'}
         for l, w in enumerate(self.gnn_weights.edge_weights):
             out.append(("graph_model/gnn_layer_%i/gnn_edge_weights_%i:0" % (l, l), w))            # [T*D, D], sparse:88
         for l, a in enumerate(self.gnn_weights.edge_type_attention_weights):
@@ -155,7 +170,12 @@ class SparseGGNNChemModel(ChemModel):
                 lay['edge_biases'] = len(flat); flat.append(self.gnn_weights.edge_biases[l])
             if self.params['use_propagation_attention']:
                 lay['edge_type_attention_weights'] = len(flat); flat.append(self.gnn_weights.edge_type_attention_weights[l])
-            for k, v in self.gnn_weights.rnn_cells[l].items():
+            cell = self.gnn_weights.rnn_cells[l]
+            if 'cand_input_kernel' in cell:   # CudnnCompatibleGRUCell: [input_projection ; hidden_projection] is the engine's candidate kernel
+                cell = {k: v for k, v in cell.items() if k not in ('cand_input_kernel', 'cand_hidden_kernel')}
+                cell['cand_kernel'] = torch.cat([self.gnn_weights.rnn_cells[l]['cand_input_kernel'],
+                                                 self.gnn_weights.rnn_cells[l]['cand_hidden_kernel']], dim=0)
+            for k, v in cell.items():
                 lay[k] = len(flat); flat.append(v)
             layout.append(lay)
         h0 = self.initial_node_representation_tensor()

@@ -7,6 +7,8 @@
 //          dr = drh*h   dh += drh*r   dpr = dr*r(1-r)   dpu = du*u(1-u)
 //          d[res..,x,h] += [dpr|dpu] . K_g^T                       dK_g += [res..,x,h]^T . [dpr|dpu]  db_g += sum
 //   RNN :  dpc = dh'*act'(h')      d[res..,x,h] = dpc . K^T        dK += [res..,x,h]^T . dpc          db += sum dpc
+//   CudnnCompatibleGRUCell: dpc as GRU;  d[res..,x] = dpc . K_in^T   dK_in += [res..,x]^T . dpc   db_in += sum dpc
+//          dq = dpc*r   dh += dq . K_hid^T   dK_hid += h^T . dq   db_hid += sum dq   dpr = dpc*q*r(1-r)   gates as GRU
 //   msgs:  dx' = dx / (deg+1e-7)   dB[t] += sum_v indeg[v,t] dx'[v]
 //          dW_t += A_t^T . dx'   (A_t = per-type gathered source states, recomputed from the target CSR)
 //          dh   += G_t . W_t^T   (G_t[s] = sum of dx'[target] over the type-t messages LEAVING s: source CSR)
@@ -240,6 +242,23 @@ __global__ void gru_bwd2_kernel(const float* __restrict__ dXc, int ldx, int rh_o
         const float drh = dXc[row * ldx + rh_off + col], rr = r[i];
         dh[i] += drh * rr;
         dpg[row * 2 * D + col] = drh * h[i] * rr * (1.0f - rr);
+    }
+}
+// CudnnCompatibleGRUCell (sparse:105-108):  c = act(x.K_in + b_in + r*q),  q = h.K_hid + b_hid (saved by the forward)
+//   dpc = dh'(1-u) act'(c)   dq = dpc r   dpg[:, 0:D] = dpc q r(1-r)   dpg[:, D:2D] = dh'(h-c) u(1-u)   dh = dh' u
+__global__ void cudnn_gru_bwd1_kernel(const float* __restrict__ dhn, const float* __restrict__ h, const float* __restrict__ r, const float* __restrict__ u,
+                                      const float* __restrict__ c, const float* __restrict__ q, float* __restrict__ dpc, float* __restrict__ dq,
+                                      float* __restrict__ dpg, float* __restrict__ dh, long long n, int D, int act) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / D;
+        const int col = (int)(i - row * D);
+        const float g = dhn[i], uu = u[i], cc = c[i], hh = h[i], rr = r[i];
+        const float dp = g * (1.0f - uu) * act_grad_from_output(cc, act);
+        dpc[i] = dp;
+        dq[i] = dp * rr;
+        dpg[row * 2 * D + col] = dp * q[i] * rr * (1.0f - rr);
+        dpg[row * 2 * D + D + col] = g * (hh - cc) * uu * (1.0f - uu);
+        dh[i] = g * uu;
     }
 }
 // RNN: dpc = dh' act'(h')   (yscale = keep_prob undoes the state dropout's 1/keep on the saved output; dropped entries have dh' = 0)

@@ -9,7 +9,7 @@ constexpr int MAX_LAYERS = 16;
 constexpr int MAX_RES = 4;     // residual inputs per layer
 constexpr int KC = 16;         // K rows of a weight operand per shared-memory stage (FFMA path)
 
-enum { CELL_GRU = 0, CELL_RNN = 1 };
+enum { CELL_GRU = 0, CELL_RNN = 1, CELL_CUDNN_GRU = 2 };
 enum { ACT_TANH = 0, ACT_RELU = 1 };
 enum { GATHER_SPARSE = 0, GATHER_DENSE = 1 };
 
@@ -21,6 +21,7 @@ struct LayerDev {
     const float* cand_k;   // [(Din+D)][D]   (RNN: the only kernel)
     const float* cand_b;   // [D]
     const float* att_w;    // [T] edge_type_attention_weights or nullptr (sparse:94-96)
+    const float* cand_hb;  // [D] hidden-projection bias of CudnnCompatibleGRUCell (sparse:105-108) or nullptr
     int steps;
     int nres;
     int res[MAX_RES];      // indices into node_states_per_layer
@@ -33,6 +34,7 @@ struct SaveDev {
     float* r;      // reset gate   (GRU)
     float* u;      // update gate  (GRU)
     float* c;      // candidate    (GRU) -- for RNN the new state itself is enough
+    float* q;      // CudnnCompatibleGRUCell only: h . K_hid + b_hid, the recurrent projection BEFORE the reset gate
 };
 
 struct FwdParams {

@@ -108,7 +108,7 @@ struct ggnn_engine {
     bool has_transpose = false;
     int64_t edges_of_type[32] = {0};
     DevBuf state_buf;   // intermediate layer states (L-1) + 2 ping-pong step buffers, each [V][D]
-    DevBuf save_bufs;   // 5 x total_steps x [V][D]
+    DevBuf save_bufs;   // 5 (CudnnCompatibleGRUCell: 6) x total_steps x [V][D]
     DevBuf io_buf;      // h0 / h_out staging for ggnn_forward_host
     DevBuf bwd_buf;     // backward scratch
     DevBuf tc_weights;  // pre-split, pre-tiled bf16 copies of the weights (tensor-core path)
@@ -329,7 +329,8 @@ int build_plan(ggnn_engine* e, const std::vector<int>& cuts, std::vector<int>& t
     if (V == 0) tile_start.assign(1, 0);
     e->ntiles = (int)tile_start.size() - 1;
     char buf[256];
-    snprintf(buf, sizeof buf, "fp32-ffma%s %s tiles=%d rows/tile<=%d warps=8 colsplit=%d nb1=%d max_component=%d smem=%zuB", e->use_att ? "+attention" : "",
+    snprintf(buf, sizeof buf, "fp32-ffma%s%s %s tiles=%d rows/tile<=%d warps=8 colsplit=%d nb1=%d max_component=%d smem=%zuB", e->use_att ? "+attention" : "",
+             e->cell == CELL_CUDNN_GRU ? "+cudnn-gru" : "",
              local ? "LOCAL(all layers+steps fused, 1 launch)" : "GLOBAL(1 launch per step)", e->ntiles, MT,
              variant_cs(variant), e->nb1, max_span, fwd_smem_bytes(variant, e->nb1, D, e->T));
     e->plan_text = buf;
@@ -347,8 +348,8 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     if (!e->has_transpose) return e->fail(GGNN_ESTATE, "enable save_for_backward BEFORE ggnn_set_graph_sparse (the source-keyed CSR is built there)");
     if (!grads || num_layers != e->L || (!d_h_out && e->V > 0)) return e->fail(GGNN_EINVAL, "bad backward arguments");
     for (int l = 0; l < e->L; ++l) {   // the weight-gradient kernels use 16-byte vector atomics
-        const void* ps[7] = {grads[l].edge_weights, grads[l].edge_biases, grads[l].gate_kernel, grads[l].gate_bias, grads[l].cand_kernel, grads[l].cand_bias,
-                             grads[l].edge_type_attention_weights};
+        const void* ps[8] = {grads[l].edge_weights, grads[l].edge_biases, grads[l].gate_kernel, grads[l].gate_bias, grads[l].cand_kernel, grads[l].cand_bias,
+                             grads[l].edge_type_attention_weights, grads[l].cand_hidden_bias};
         for (const void* q : ps)
             if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: gradient pointers must be 16-byte aligned", l);
     }
@@ -384,7 +385,7 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
     for (int l = 1; l < L; ++l) fstate[l] = (const float*)e->state_buf.ptr + (size_t)(l - 1) * vd;
     const float* sv = (const float*)e->save_bufs.ptr;
     const size_t per = vd * (size_t)std::max(e->total_steps, 1);
-    const float *sv_h = sv, *sv_x = sv + per, *sv_r = sv + 2 * per, *sv_u = sv + 3 * per, *sv_c = sv + 4 * per;
+    const float *sv_h = sv, *sv_x = sv + per, *sv_r = sv + 2 * per, *sv_u = sv + 3 * per, *sv_c = sv + 4 * per, *sv_q = sv + 5 * per;
     char* g = (char*)e->graph_buf.ptr;
     const int* row_ptr = (const int*)(g + e->off_row_ptr);
     const int* csr_src = (const int*)(g + e->off_src);
@@ -462,6 +463,25 @@ static int ggnn_backward_impl(ggnn_engine* e, const float* d_h_out, const ggnn_l
                 gemm_tn(cell_segs(h), R + 2, true, dpg, 2 * D, gw.gate_kernel, 2 * D, (size_t)D * 2 * D, gw.gate_bias, V, 2 * D, D);
                 split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, dxg, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 0, 1, 1, n, D);
                 ++e->last_launches;
+            } else if (e->cell == CELL_CUDNN_GRU) {
+                // c = act(x.K_in + b_in + r*q), q = h.K_hid + b_hid: the candidate kernel's first din rows see [res.., x], its last D rows see h
+                const float *r = sv_r + so, *u = sv_u + so, *c = sv_c + so, *q = sv_q + so;
+                float* dq = rh;   // the r*h scratch of the GRU branch is free here
+                cudnn_gru_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, h, r, u, c, q, dpc, dq, dpg, dh_new, n, D, e->act); ++e->last_launches;
+                gemm_nt(false, dpc, D, 0, w.cand_kernel, D, 0, 1, dxc, ldx, V, din, D);                                  // d[res.., x] = dpc . K_in^T
+                gemm_nt(true, dq, D, 0, w.cand_kernel + (size_t)din * D, D, 0, 1, dh_new, D, V, D, D);                   // dh += dq . K_hid^T
+                gemm_tn(cell_segs(nullptr), R + 1, true, dpc, D, gw.cand_kernel, D, (size_t)D * D, gw.cand_bias, V, D, D);
+                {
+                    SegList sl;
+                    memset(&sl, 0, sizeof sl);
+                    sl.p[0] = h; sl.ld[0] = D;
+                    gemm_tn(sl, 1, true, dq, D, gw.cand_kernel ? gw.cand_kernel + (size_t)din * D : nullptr, D, 0, gw.cand_hidden_bias, V, D, D);
+                }
+                gemm_nt(false, dpg, 2 * D, 0, w.gate_kernel, 2 * D, 0, 1, dxg, ldx, V, ldx, 2 * D);
+                gemm_tn(cell_segs(h), R + 2, true, dpg, 2 * D, gw.gate_kernel, 2 * D, (size_t)D * 2 * D, gw.gate_bias, V, 2 * D, D);
+                // dxc holds only the din input columns: the recurrent gradient of the candidate went into dh_new through dq above
+                split_input_grad_kernel<<<eb, 256, 0, st>>>(dxc, dxg, ldx, R, d_ptrs, dxp, e->use_avg ? denom : nullptr, dh_new, 0, 1, 1, n, D);
+                ++e->last_launches;
             } else {
                 const float* hnew = (s == e->steps[l] - 1) ? fstate[l + 1] : sv_h + so + vd;
                 rnn_bwd1_kernel<<<eb, 256, 0, st>>>(dhn, hnew, dpc, n, e->act, e->saved_drop_keep < 1.0f ? e->saved_drop_keep : 1.0f); ++e->last_launches;
@@ -533,7 +553,8 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     if (cfg->num_edge_types <= 0 || cfg->num_edge_types > 32) return bad("num_edge_types must be in 1..32");
     if (cfg->num_layers <= 0 || cfg->num_layers > MAX_LAYERS) return bad("num_layers must be in 1..16");
     if (!cfg->layer_timesteps) return bad("layer_timesteps is null");
-    if (cfg->cell != GGNN_CELL_GRU && cfg->cell != GGNN_CELL_RNN) return bad("Unknown RNN cell type");              // sparse:112
+    if (cfg->cell != GGNN_CELL_GRU && cfg->cell != GGNN_CELL_RNN && cfg->cell != GGNN_CELL_CUDNN_GRU) return bad("Unknown RNN cell type");   // sparse:112
+    if (cfg->cell == GGNN_CELL_CUDNN_GRU && cfg->activation != GGNN_ACT_TANH) return bad("CudnnCompatibleGRUCell requires the tanh activation");   // sparse:106
     if (cfg->activation != GGNN_ACT_TANH && cfg->activation != GGNN_ACT_RELU) return bad("Unknown activation function type");  // sparse:81
     if (cfg->precision != GGNN_PREC_FP32 && cfg->precision != GGNN_PREC_BF16X3 && cfg->precision != GGNN_PREC_BF16) return bad("unknown precision");
     ggnn_engine* e = new ggnn_engine();
@@ -543,6 +564,7 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     e->use_att = cfg->use_propagation_attention != 0;
     if (e->use_att && e->T > 16) { delete e; g_create_error = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
     if (e->use_att) e->precision = GGNN_PREC_FP32;   // the softmax-weighted gather lives in the fp32 kernel only (the plan text says so)
+    if (e->cell == CELL_CUDNN_GRU) e->precision = GGNN_PREC_FP32;   // so does the reset-after-matmul candidate of CudnnCompatibleGRUCell
     int total = 0;
     for (int l = 0; l < e->L; ++l) {
         if (cfg->layer_timesteps[l] < 0) { delete e; return bad("negative layer_timesteps entry"); }
@@ -604,9 +626,10 @@ int ggnn_set_weights(ggnn_engine* e, const ggnn_layer_weights* layers, int32_t n
         const ggnn_layer_weights& w = layers[l];
         if (!w.edge_weights || !w.cand_kernel || !w.cand_bias) return e->fail(GGNN_EINVAL, "layer %d: null edge_weights/cand_kernel/cand_bias", l);
         if (e->use_bias && !w.edge_biases) return e->fail(GGNN_EINVAL, "layer %d: use_edge_bias set but edge_biases is null", l);
-        if (e->cell == CELL_GRU && (!w.gate_kernel || !w.gate_bias)) return e->fail(GGNN_EINVAL, "layer %d: GRU needs gate_kernel/gate_bias", l);
+        if (e->cell != CELL_RNN && (!w.gate_kernel || !w.gate_bias)) return e->fail(GGNN_EINVAL, "layer %d: GRU needs gate_kernel/gate_bias", l);
+        if (e->cell == CELL_CUDNN_GRU && !w.cand_hidden_bias) return e->fail(GGNN_EINVAL, "layer %d: CudnnCompatibleGRUCell needs cand_hidden_bias", l);
         if (e->use_att && !w.edge_type_attention_weights) return e->fail(GGNN_EINVAL, "layer %d: use_propagation_attention set but edge_type_attention_weights is null", l);
-        const void* ps[6] = {w.edge_weights, w.edge_biases, w.gate_kernel, w.gate_bias, w.cand_kernel, w.cand_bias};
+        const void* ps[7] = {w.edge_weights, w.edge_biases, w.gate_kernel, w.gate_bias, w.cand_kernel, w.cand_bias, w.cand_hidden_bias};
         for (const void* q : ps)
             if (q && ((uintptr_t)q & 15)) return e->fail(GGNN_EINVAL, "layer %d: weight pointers must be 16-byte aligned", l);
         e->w[l] = w;
@@ -627,7 +650,7 @@ static int upload_graph(ggnn_engine* e, size_t bytes, cudaStream_t st) {
 static int reserve_states(ggnn_engine* e) {
     const size_t vd = (size_t)std::max(e->V, 1) * e->D * sizeof(float);
     CU_TRY(e, e->state_buf.reserve(vd * (size_t)(e->L + 1)));
-    if (e->save) CU_TRY(e, e->save_bufs.reserve(vd * 5 * (size_t)std::max(e->total_steps, 1)));
+    if (e->save) CU_TRY(e, e->save_bufs.reserve(vd * (e->cell == CELL_CUDNN_GRU ? 6 : 5) * (size_t)std::max(e->total_steps, 1)));
     return GGNN_OK;
 }
 
@@ -1141,6 +1164,7 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
         ld.gate_k = e->w[l].gate_kernel; ld.gate_b = e->w[l].gate_bias;
         ld.cand_k = e->w[l].cand_kernel; ld.cand_b = e->w[l].cand_bias;
         ld.att_w = e->use_att ? e->w[l].edge_type_attention_weights : nullptr;
+        ld.cand_hb = e->cell == CELL_CUDNN_GRU ? e->w[l].cand_hidden_bias : nullptr;
         ld.steps = e->steps[l]; ld.nres = e->nres[l];
         for (int i = 0; i < MAX_RES; ++i) ld.res[i] = e->res[l][i];
         p.step_base[l] = e->step_base[l];
@@ -1149,6 +1173,7 @@ static void fill_params(ggnn_engine* e, FwdParams& p, const float* h0, float* h_
         float* s = (float*)e->save_bufs.ptr;
         const size_t per = vd * (size_t)std::max(e->total_steps, 1);
         p.save_buf.h_in = s; p.save_buf.agg = s + per; p.save_buf.r = s + 2 * per; p.save_buf.u = s + 3 * per; p.save_buf.c = s + 4 * per;
+        p.save_buf.q = e->cell == CELL_CUDNN_GRU ? s + 5 * per : nullptr;
     }
 }
 

@@ -8,6 +8,7 @@
 //                                                agg     += A_t . W[l][t]                            (matmul :163, summed over types)
 //     agg += indeg . B[l]  (:202-204);  agg /= (sum indeg + 1e-7)  (:206-209)
 //     GRU: [r|u] = sigmoid([res..., agg, h] . K_g + b_g);  c = act([res..., agg, r*h] . K_c + b_c);  h = u*h + (1-u)*c   (:215, TF-1.3 GRUCell)
+//     CudnnCompatibleGRUCell (:105-108): same gates;  c = tanh([res..., agg] . K_in + b_in + r*(h . K_hid + b_hid))
 //     RNN: h = act([res..., agg, h] . K + b)                                                         (BasicRNNCell)
 // (sum-then-transform is algebraically identical to the reference's transform-then-sum and needs V*T*D*D
 // instead of M*D*D MACs only where a (target,type) pair exists; types absent from a tile are skipped.)
@@ -313,7 +314,10 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
             segs[nseg++] = ASeg{sX, D, D, 0};
             segs[nseg++] = ASeg{sH, D, D, 0};
 
-            if (p.cell == CELL_GRU) {
+            if (p.cell == CELL_GRU || p.cell == CELL_CUDNN_GRU) {
+                // CudnnCompatibleGRUCell (tf.contrib.cudnn_rnn, sparse:105-108): same gates, but the reset gate multiplies the recurrent
+                // projection AFTER the matmul:  c = tanh(x . K_in + b_in + r * (h . K_hid + b_hid)),  K_in / K_hid = the first Din / last D rows of cand_k
+                const bool cudnn = p.cell == CELL_CUDNN_GRU;
                 const int N2 = 2 * D;
                 for (int col0 = 0; col0 < N2; col0 += PW2) {
                     const int ncols = min(PW2, N2 - col0);
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
                                 if (row < rows) {
                                     const float sg = sigmoidf_acc(acc2[j][r] + bg);
                                     if (g < D) {
-                                        sA[row * D + g] = sg * sH[row * D + g];  // r*h, the candidate's recurrent operand
+                                        sA[row * D + g] = cudnn ? sg : sg * sH[row * D + g];  // r*h, the candidate's recurrent operand (cudnn: r itself)
                                         if (p.save) p.save_buf.r[save_off + (size_t)(row0 + row) * D + g] = sg;
                                     } else {
                                         sU[row * D + (g - D)] = sg;
@@ -344,9 +348,34 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
                     }
                 }
                 __syncthreads();
-                segs[nseg - 1] = ASeg{sA, D, D, 0};
+                if (cudnn) {
+                    // q = h . K_hid + b_hid (kept for the backward pass);  sA <- r * q.  The thread that wrote sA[row][col] = r in the gate
+                    // epilogue is not this one (different column mapping) -- the __syncthreads above orders the two.
+                    ASeg hseg{sH, D, D, 0};
+                    zero_acc<NB1>(acc1);
+                    gemm_accumulate<NB1, RG, CS>(acc1, &hseg, 1, ly.cand_k + (size_t)D * (ly.nres + 1) * D, D, 0, D, sB, sStage, row0, rows);
+#pragma unroll
+                    for (int j = 0; j < NB1; ++j) {
+                        const int col = cs * 32 * NB1 + lane + 32 * j;
+                        if (col < D) {
+                            const float bh = ly.cand_hb[col];
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                const int row = rg * 8 + r;
+                                if (row < rows) {
+                                    const float q = acc1[j][r] + bh;
+                                    sA[row * D + col] *= q;
+                                    if (p.save) p.save_buf.q[save_off + (size_t)(row0 + row) * D + col] = q;
+                                }
+                            }
+                        }
+                    }
+                    // the same thread reads sA[row][col] again in the candidate epilogue below (same mapping): no barrier needed for it
+                } else {
+                    segs[nseg - 1] = ASeg{sA, D, D, 0};
+                }
                 zero_acc<NB1>(acc1);
-                gemm_accumulate<NB1, RG, CS>(acc1, segs, nseg, ly.cand_k, D, 0, D, sB, sStage, row0, rows);
+                gemm_accumulate<NB1, RG, CS>(acc1, segs, cudnn ? nseg - 1 : nseg, ly.cand_k, D, 0, D, sB, sStage, row0, rows);
 #pragma unroll
                 for (int j = 0; j < NB1; ++j) {
                     const int col = cs * 32 * NB1 + lane + 32 * j;
@@ -356,7 +385,9 @@ __global__ void __launch_bounds__(RG * CS * 32, MINB) ggnn_fwd_ffma_kernel(const
                         for (int r = 0; r < 8; ++r) {
                             const int row = rg * 8 + r;
                             if (row < rows) {
-                                const float c = activate(acc1[j][r] + bc, p.act);
+                                float pre = acc1[j][r] + bc;
+                                if (cudnn) pre += sA[row * D + col];
+                                const float c = activate(pre, p.act);
                                 const float u = sU[row * D + col];
                                 const float h = sH[row * D + col];
                                 float hn = u * h + (1.0f - u) * c;

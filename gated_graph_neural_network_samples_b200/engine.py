@@ -13,7 +13,10 @@ import numpy as np
 from . import _lib
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
-WEIGHT_FIELDS = ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights")
+WEIGHT_FIELDS = ("edge_weights", "edge_biases", "gate_kernel", "gate_bias", "cand_kernel", "cand_bias", "edge_type_attention_weights",
+                 "cand_hidden_bias")
+# params['graph_rnn_cell'].lower() (sparse:102-112) -> GGNN_CELL_*
+CELL_CODES = {"gru": 0, "rnn": 1, "cudnncompatiblegrucell": 2}
 
 
 def residual_inputs_of_layer(params: dict, layer_idx: int) -> List[int]:
@@ -35,8 +38,11 @@ def weight_shapes(params: dict, num_edge_types: int, layer_idx: int) -> Dict[str
         shapes["edge_biases"] = (T, D)
     if params.get("use_propagation_attention", False):
         shapes["edge_type_attention_weights"] = (T,)                                            # sparse:94-96
-    if params.get("graph_rnn_cell", "GRU").lower() == "gru":
+    cell = params.get("graph_rnn_cell", "GRU").lower()
+    if cell == "gru":
         shapes.update(gate_kernel=(din + D, 2 * D), gate_bias=(2 * D,), cand_kernel=(din + D, D), cand_bias=(D,))
+    elif cell == "cudnncompatiblegrucell":   # sparse:105-108: cand_kernel = [input_projection/kernel ; hidden_projection/kernel]
+        shapes.update(gate_kernel=(din + D, 2 * D), gate_bias=(2 * D,), cand_kernel=(din + D, D), cand_bias=(D,), cand_hidden_bias=(D,))
     else:
         shapes.update(cand_kernel=(din + D, D), cand_bias=(D,))
     return shapes
@@ -59,10 +65,10 @@ class PropagationEngine:
         if act not in ("tanh", "relu"):
             raise Exception("Unknown activation function type '%s'." % act)                  # sparse:81
         cell = params.get("graph_rnn_cell", "GRU").lower()
-        if cell not in ("gru", "rnn"):
-            # CudnnCompatibleGRUCell (sparse:105-108) is a different cell (reset gate applied after the
-            # recurrent matmul); it is in no BASELINE config and not provided by tensorflow==1.3.0.
+        if cell not in CELL_CODES:
             raise Exception("Unknown RNN cell type '%s'." % cell)                            # sparse:112
+        if cell == "cudnncompatiblegrucell":
+            assert act == "tanh"                                                             # sparse:106
         offs, flat = [0], []
         for l in range(self.L):
             flat += residual_inputs_of_layer(params, l)
@@ -73,7 +79,7 @@ class PropagationEngine:
         cfg = _lib.GgnnConfig(self.D, self.T, self.L, self._steps, self._offs, self._flat,
                               int(bool(params.get("use_edge_bias", False))),
                               int(bool(params.get("use_edge_msg_avg_aggregation", False))),
-                              0 if cell == "gru" else 1, 0 if act == "tanh" else 1,
+                              CELL_CODES[cell], 0 if act == "tanh" else 1,
                               PRECISIONS[precision], int(device), int(bool(params.get("use_propagation_attention", False))))
         rc = self.lib.ggnn_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:

@@ -32,7 +32,8 @@ typedef struct ggnn_engine ggnn_engine;
 typedef void* ggnn_stream_t; /* a cudaStream_t (0 = default stream) */
 
 enum { GGNN_OK = 0, GGNN_EINVAL = -1, GGNN_ECUDA = -2, GGNN_ESTATE = -3, GGNN_EUNSUPPORTED = -4, GGNN_ERANGE = -5 };
-enum { GGNN_CELL_GRU = 0, GGNN_CELL_RNN = 1 };  /* params['graph_rnn_cell']        sparse:102-112 */
+enum { GGNN_CELL_GRU = 0, GGNN_CELL_RNN = 1,    /* params['graph_rnn_cell']        sparse:102-112 */
+       GGNN_CELL_CUDNN_GRU = 2 };               /* 'CudnnCompatibleGRUCell', sparse:105-108 (fp32 path; tanh only, as the reference asserts) */
 enum { GGNN_ACT_TANH = 0, GGNN_ACT_RELU = 1 };  /* params['graph_rnn_activation']  sparse:75-81   */
 /* arithmetic of the dense contractions */
 enum { GGNN_PREC_FP32 = 0,   /* fp32 FFMA on CUDA cores (bit-for-bit fp32 semantics, order aside) */
@@ -62,6 +63,10 @@ typedef struct ggnn_config {
  *   GRU: gate_kernel [Din+D, 2D], gate_bias [2D]  (columns: r first, u second)
  *        cand_kernel [Din+D, D],  cand_bias [D]
  *   RNN: cand_kernel [Din+D, D], cand_bias [D] hold BasicRNNCell's kernel/bias; gate_* are NULL.
+ *   CudnnCompatibleGRUCell (tf.contrib.cudnn_rnn, sparse:105-108): gates as GRU;
+ *        c = tanh(x . K_in + b_in + r * (h . K_hid + b_hid)) -- the reset gate is applied AFTER the recurrent product.
+ *        cand_kernel [Din+D, D] = [candidate/input_projection/kernel ; candidate/hidden_projection/kernel] (rows stacked in that
+ *        order, so the row order below still holds), cand_bias [D] = b_in, cand_hidden_bias [D] = b_hid.
  * Din = D * (1 + number of residual inputs of the layer); kernel rows are ordered
  * [residual states ..., aggregated messages, recurrent state] (sparse:211-216 + TF-1.3 _linear).   */
 typedef struct ggnn_layer_weights {
@@ -72,6 +77,7 @@ typedef struct ggnn_layer_weights {
     const float* cand_kernel;
     const float* cand_bias;
     const float* edge_type_attention_weights; /* [T] (sparse:94-96) or NULL when !use_propagation_attention */
+    const float* cand_hidden_bias;            /* [D] CudnnCompatibleGRUCell only (candidate/hidden_projection/bias), else NULL */
 } ggnn_layer_weights;
 
 /* Same layout, device pointers the backward pass ACCUMULATES into (caller zeroes them). */
@@ -83,6 +89,7 @@ typedef struct ggnn_layer_grads {
     float* cand_kernel;
     float* cand_bias;
     float* edge_type_attention_weights;
+    float* cand_hidden_bias;
 } ggnn_layer_grads;
 
 /* prepare_specific_graph_model (sparse:63-115 / dense:68-91): fix the model shape. */

@@ -26,7 +26,7 @@ class _Config(C.Structure):
 
 class _Layer(C.Structure):
     _fields_ = [(n, _f64p) for n in ("edge_weights", "edge_biases", "edge_type_attention_weights", "gate_kernel", "gate_bias",
-                                     "cand_kernel", "cand_bias")]
+                                     "cand_kernel", "cand_bias", "cand_hidden_bias")]
 
 
 def build(force: bool = False) -> str:
@@ -81,7 +81,7 @@ def sparse_propagation_c(h0, adjacency_lists, num_incoming_edges_per_type, weigh
     cfg = _Config(D, T, L, steps.ctypes.data_as(_i32p), offs.ctypes.data_as(_i32p), flat.ctypes.data_as(_i32p),
                   int(bool(params.get("use_edge_bias", False))), int(bool(params.get("use_edge_msg_avg_aggregation", False))),
                   int(bool(params.get("use_propagation_attention", False))),
-                  int(params.get("graph_rnn_cell", "GRU").lower() == "rnn"), int(params.get("graph_rnn_activation", "tanh").lower() == "relu"))
+                  {"gru": 0, "rnn": 1, "cudnncompatiblegrucell": 2}[params.get("graph_rnn_cell", "GRU").lower()], int(params.get("graph_rnn_activation", "tanh").lower() == "relu"))
     layers = (_Layer * L)(*[_layer(w, keep) for w in weights])
     adjs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, 2)) for a in adjacency_lists]
     ptrs = (_i32p * T)(*[a.ctypes.data_as(_i32p) for a in adjs])

@@ -5,6 +5,7 @@
  *   chem_tensorflow_dense.py:93-117    (DenseGGNNChemModel.compute_final_node_representations)
  *   TF-1.3 rnn_cell_impl.py GRUCell / BasicRNNCell (un-vendored tensorflow==1.3.0, requirements.txt:2; restated from the release:
  *     [r|u] = sigmoid([x,h].K_g + b_g),  c = act([x, r*h].K_c + b_c),  h' = u*h + (1-u)*c ;   h' = act([x,h].K + b))
+ *   tf.contrib.cudnn_rnn CudnnCompatibleGRUCell (sparse:105-108; TF >= 1.4): same gates, c = tanh(x.K_in + b_in + r*(h.K_hid + b_hid))
  * It shares no code with oracle/ggnn_oracle.py; tests/test_oracle.py requires the two to agree to 1e-12 on the golden fixtures and on
  * random batches, which is what pins each against transcription slips (PARITY UNPINNED BY THE REFERENCE itself: it ships no tests or
  * vectors and TensorFlow 1.3 cannot run here -- see the header of ggnn_oracle.py).
@@ -29,7 +30,7 @@ typedef struct {
     int32_t use_edge_bias;                /* sparse:202 */
     int32_t use_edge_msg_avg_aggregation; /* sparse:206 */
     int32_t use_propagation_attention;    /* sparse:170 */
-    int32_t cell_is_rnn;                  /* 0 GRUCell, 1 BasicRNNCell   sparse:102-112 */
+    int32_t cell_is_rnn;                  /* 0 GRUCell, 1 BasicRNNCell, 2 CudnnCompatibleGRUCell   sparse:102-112 */
     int32_t act_is_relu;                  /* 0 tanh, 1 relu              sparse:75-81 */
 } oracle_config;
 
@@ -41,6 +42,7 @@ typedef struct {
     const double* gate_bias;                   /* [2D] */
     const double* cand_kernel;                 /* [(Din+D)][D]  (RNN: the only kernel) */
     const double* cand_bias;                   /* [D] */
+    const double* cand_hidden_bias;            /* [D] CudnnCompatibleGRUCell: candidate/hidden_projection/bias, else NULL */
 } oracle_layer;
 
 static double act(double v, int relu) { return relu ? (v > 0.0 ? v : 0.0) : tanh(v); }
@@ -63,7 +65,7 @@ static void cell(const oracle_config* c, const oracle_layer* w, const double* x,
     double* in = scratch;                 /* [Din + D] */
     double* ru = scratch + Din + D;       /* [2D] */
     memcpy(in, x, sizeof(double) * (size_t)Din);
-    if (c->cell_is_rnn) {
+    if (c->cell_is_rnn == 1) {
         memcpy(in + Din, h, sizeof(double) * (size_t)D);
         linear(in, Din + D, w->cand_kernel, w->cand_bias, D, hnew);
         for (int d = 0; d < D; ++d) hnew[d] = act(hnew[d], c->act_is_relu);
@@ -72,6 +74,19 @@ static void cell(const oracle_config* c, const oracle_layer* w, const double* x,
     memcpy(in + Din, h, sizeof(double) * (size_t)D);
     linear(in, Din + D, w->gate_kernel, w->gate_bias, 2 * D, ru);
     for (int d = 0; d < 2 * D; ++d) ru[d] = sigmoid(ru[d]);                 /* r = ru[0..D), u = ru[D..2D) */
+    if (c->cell_is_rnn == 2) {
+        /* tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell (TF >= 1.4, sparse:105-108; restated from the release):
+         *   c = tanh(_linear(x; input_projection) + r * _linear(h; hidden_projection)),  h' = u*h + (1-u)*c.
+         * cand_kernel stacks the two kernels: rows [0, Din) input projection (bias cand_bias), rows [Din, Din+D) hidden projection. */
+        double* hh = in + Din;            /* [D], reuses the concat buffer's tail */
+        linear(h, D, w->cand_kernel + (size_t)Din * D, w->cand_hidden_bias, D, hh);
+        linear(x, Din, w->cand_kernel, w->cand_bias, D, hnew);
+        for (int d = 0; d < D; ++d) {
+            const double cand = act(hnew[d] + ru[d] * hh[d], c->act_is_relu);
+            hnew[d] = ru[D + d] * h[d] + (1.0 - ru[D + d]) * cand;
+        }
+        return;
+    }
     for (int d = 0; d < D; ++d) in[Din + d] = ru[d] * h[d];                 /* [x, r*h] */
     linear(in, Din + D, w->cand_kernel, w->cand_bias, D, hnew);
     for (int d = 0; d < D; ++d) {

@@ -18,6 +18,8 @@ SURVEY.md section 8c):
                    c     = act([x, r*h] . K_c + b_c)
                    h'    = u*h + (1-u)*c
     BasicRNNCell:  h'    = act([x, h] . K + b)
+    CudnnCompatibleGRUCell (tf.contrib.cudnn_rnn, TF >= 1.4 -- what sparse:105-108 instantiates; not in 1.3.0 itself):
+                   gates as GRUCell;  c = tanh(x . K_in + b_in + r * (h . K_hid + b_hid));  h' = u*h + (1-u)*c
     DropoutWrapper(state_keep_prob=1.0): identity on the new state.
 
 PARITY: the reference ships no tests, golden vectors or fixtures and TensorFlow 1.3 cannot run here, so the reference itself pins
@@ -86,6 +88,12 @@ def init_sparse_weights(params, num_edge_types, rng, edge_bias_scale=0.1, attent
             w["gate_bias"] = np.ones([2 * D], dtype=np.float32)
             w["cand_kernel"] = glorot_init([din + D, D], rng)
             w["cand_bias"] = np.zeros([D], dtype=np.float32)
+        elif cell == "cudnncompatiblegrucell":   # sparse:105-108; _linear initialises each projection on its own shape
+            w["gate_kernel"] = glorot_init([din + D, 2 * D], rng)
+            w["gate_bias"] = np.ones([2 * D], dtype=np.float32)
+            w["cand_kernel"] = np.concatenate([glorot_init([din, D], rng), glorot_init([D, D], rng)], axis=0)
+            w["cand_bias"] = rng.uniform(-0.1, 0.1, size=D).astype(np.float32)          # the reference initialises zeros: perturbed so that
+            w["cand_hidden_bias"] = rng.uniform(-0.1, 0.1, size=D).astype(np.float32)   # both bias paths are exercised
         elif cell == "rnn":
             w["rnn_kernel"] = glorot_init([din + D, D], rng)
             w["rnn_bias"] = np.zeros([D], dtype=np.float32)
@@ -134,6 +142,18 @@ def gru_cell(x, h, w, act):
     return u * h + (1.0 - u) * c
 
 
+def cudnn_gru_cell(x, h, w, act):
+    """tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell.call (TF >= 1.4; the class the reference instantiates at sparse:105-108):
+    gates as GRUCell; c = act(_linear(x; candidate/input_projection) + r * _linear(h; candidate/hidden_projection)) -- the reset gate is
+    applied AFTER the recurrent product.  ``cand_kernel`` stacks [input_projection/kernel ; hidden_projection/kernel]."""
+    D = h.shape[-1]
+    din = x.shape[-1]
+    ru = _sigmoid(np.concatenate([x, h], axis=-1) @ w["gate_kernel"] + w["gate_bias"])
+    r, u = ru[..., :D], ru[..., D:]
+    c = act(x @ w["cand_kernel"][:din] + w["cand_bias"] + r * (h @ w["cand_kernel"][din:] + w["cand_hidden_bias"]))
+    return u * h + (1.0 - u) * c
+
+
 def rnn_cell(x, h, w, act):
     """TF-1.3 BasicRNNCell.__call__."""
     return act(np.concatenate([x, h], axis=-1) @ w["rnn_kernel"] + w["rnn_bias"])
@@ -146,6 +166,8 @@ def _cell_fn(params):
         return lambda x, h, w: gru_cell(x, h, w, act)
     if cell == "rnn":
         return lambda x, h, w: rnn_cell(x, h, w, act)
+    if cell == "cudnncompatiblegrucell":
+        return lambda x, h, w: cudnn_gru_cell(x, h, w, act)
     raise Exception("Unknown RNN cell type '%s'." % cell)
 
 
@@ -385,6 +407,13 @@ def sparse_propagation_torch(h0, adjacency_lists, num_incoming_edges_per_type, w
                 ru = torch.sigmoid(torch.matmul(torch.cat([x, h], -1), w["gate_kernel"]) + w["gate_bias"])
                 r, u = ru[:, :D], ru[:, D:]
                 c = act(torch.matmul(torch.cat([x, r * h], -1), w["cand_kernel"]) + w["cand_bias"])
+                states[-1] = u * h + (1 - u) * c
+            elif cell_type == "cudnncompatiblegrucell":                                          # sparse:105-108
+                ru = torch.sigmoid(torch.matmul(torch.cat([x, h], -1), w["gate_kernel"]) + w["gate_bias"])
+                r, u = ru[:, :D], ru[:, D:]
+                din = x.shape[-1]
+                c = act(torch.matmul(x, w["cand_kernel"][:din]) + w["cand_bias"]
+                        + r * (torch.matmul(h, w["cand_kernel"][din:]) + w["cand_hidden_bias"]))
                 states[-1] = u * h + (1 - u) * c
             else:
                 states[-1] = act(torch.matmul(torch.cat([x, h], -1), w["rnn_kernel"]) + w["rnn_bias"])

@@ -34,6 +34,7 @@ from gated_graph_neural_network_samples_b200 import synthetic  # noqa: E402
 
 def import_reference():
     sys.modules["tensorflow"] = tf_shim
+    tf_shim.register_submodules(sys.modules)
     d = types.ModuleType("docopt")
     d.docopt = lambda *a, **k: {}
     sys.modules["docopt"] = d
@@ -153,6 +154,12 @@ def sparse_case(ref_sparse, ref_utils, name, cfg, mols):
     h0 = h0 * 1.5 + np.random.RandomState(3).normal(0, 0.3, h0.shape)      # every column live, attention scores of order 1
     feed[m.placeholders["initial_node_representation"]] = h0
     out_final, out_ro, loss, acc = evaluate_model(m, feed)
+    if cfg["graph_rnn_cell"].lower() == "cudnncompatiblegrucell":
+        # the cell's variables exist after the first evaluation; its two candidate biases are initialised to zero: perturb, evaluate again
+        for cell in m.gnn_weights.rnn_cells:
+            cell.vars["cand_bias"] = rng.uniform(-0.1, 0.1, cell.vars["cand_bias"].shape)
+            cell.vars["cand_hidden_bias"] = rng.uniform(-0.1, 0.1, cell.vars["cand_hidden_bias"].shape)
+        out_final, out_ro, loss, acc = evaluate_model(m, feed)
     out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0, "final": out_final, "readout": out_ro, "loss": np.float64(loss),
            "accuracy": np.float64(acc), "target_values": np.asarray(feed[m.placeholders["target_values"]], np.float64),
            "target_mask": np.asarray(feed[m.placeholders["target_mask"]], np.float64),
@@ -167,7 +174,10 @@ def sparse_case(ref_sparse, ref_utils, name, cfg, mols):
             out["w%d_edge_biases" % l] = m.gnn_weights.edge_biases[l].value
         if cfg.get("use_propagation_attention"):
             out["w%d_edge_type_attention_weights" % l] = m.gnn_weights.edge_type_attention_weights[l].value
-        for k, v in (m.gnn_weights.rnn_cells[l].vars or {}).items():
+        cv = dict(m.gnn_weights.rnn_cells[l].vars or {})
+        if "cand_input_kernel" in cv:   # CudnnCompatibleGRUCell: the engine's candidate kernel stacks [input_projection ; hidden_projection]
+            cv["cand_kernel"] = np.concatenate([cv.pop("cand_input_kernel"), cv.pop("cand_hidden_kernel")], axis=0)
+        for k, v in cv.items():
             out["w%d_%s" % (l, k)] = v
     for k, v in ro_w.items():
         out["ro_" + k] = v.value
@@ -220,6 +230,10 @@ def main():
         "attention_bias_avg": {"hidden_size": 12, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]},
                                "use_edge_bias": True, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU",
                                "graph_rnn_activation": "tanh", "use_propagation_attention": True},
+        # sparse:105-108 -- tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell (reset gate after the recurrent matmul)
+        "cudnn_gru": {"hidden_size": 12, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]},
+                      "use_edge_bias": True, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "CudnnCompatibleGRUCell",
+                      "graph_rnn_activation": "tanh"},
     }
     for name, cfg in cases.items():
         sparse_case(ref_sparse, ref_utils, name, cfg, mols)

@@ -171,6 +171,35 @@ class GRUCell:
         return new_h, new_h
 
 
+class CudnnCompatibleGRUCell:
+    """tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell (TF >= 1.4; what chem_tensorflow_sparse.py:105-108 instantiates), restated from that
+    release: gates as GRUCell (bias 1.0); the candidate has two `_linear`s in their own scopes, candidate/input_projection over the inputs
+    and candidate/hidden_projection over the state (biases 0), and the reset gate multiplies the hidden projection AFTER the matmul:
+    c = tanh(x.K_in + b_in + r*(h.K_hid + b_hid)); h' = u*h + (1-u)*c; returns (h', h')."""
+
+    def __init__(self, num_units, **_):
+        self.n, self.act = int(num_units), _tanh
+        self.vars = None
+
+    def _build(self, din):
+        n = self.n
+        self.vars = {"gate_kernel": _glorot([din + n, 2 * n]), "gate_bias": np.ones(2 * n), "cand_input_kernel": _glorot([din, n]),
+                     "cand_bias": np.zeros(n), "cand_hidden_kernel": _glorot([n, n]), "cand_hidden_bias": np.zeros(n)}
+
+    def __call__(self, inputs, state):
+        def gates(x, h):
+            if self.vars is None:
+                self._build(x.shape[-1])
+            return 1.0 / (1.0 + np.exp(-(np.concatenate([x, h], -1) @ self.vars["gate_kernel"] + self.vars["gate_bias"])))
+        ru = Node(gates, inputs, state)
+        r, u = ru[:, :self.n], ru[:, self.n:]
+        hi = Node(lambda x, _ru: x @ self.vars["cand_input_kernel"] + self.vars["cand_bias"], inputs, ru)      # ru: the variables exist
+        hh = r * Node(lambda h, _ru: h @ self.vars["cand_hidden_kernel"] + self.vars["cand_hidden_bias"], state, ru)
+        c = self.act(hi + hh)
+        new_h = u * state + (1 - u) * c
+        return new_h, new_h
+
+
 class BasicRNNCell:
     """tf.nn.rnn_cell.BasicRNNCell (1.3): h' = act([x,h].K + b(=0)); returns (h', h')."""
 
@@ -203,4 +232,11 @@ class DropoutWrapper:
 
 nn = types.SimpleNamespace(embedding_lookup=lambda params, ids: gather(params, ids), dropout=_dropout, sigmoid=_sigmoid, tanh=_tanh,
                            relu=_relu, rnn_cell=types.SimpleNamespace(GRUCell=GRUCell, BasicRNNCell=BasicRNNCell, DropoutWrapper=DropoutWrapper))
-contrib = types.SimpleNamespace(rnn=types.SimpleNamespace(GRUCell=GRUCell))
+contrib = types.SimpleNamespace(rnn=types.SimpleNamespace(GRUCell=GRUCell),
+                                cudnn_rnn=types.SimpleNamespace(CudnnCompatibleGRUCell=CudnnCompatibleGRUCell))
+
+
+def register_submodules(sys_modules, top="tensorflow"):
+    """``import tensorflow.contrib.cudnn_rnn as cudnn_rnn`` (chem_tensorflow_sparse.py:107) needs the dotted names in sys.modules."""
+    sys_modules[top + ".contrib"] = contrib
+    sys_modules[top + ".contrib.cudnn_rnn"] = contrib.cudnn_rnn

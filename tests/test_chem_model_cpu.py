@@ -59,7 +59,8 @@ def _args(tmp_path, mols, **cfg):
     return {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:48], "--valid_data": mols[48:], "--config": base}
 
 
-@pytest.mark.parametrize("cfg", [{}, {"use_propagation_attention": True}, {"graph_rnn_cell": "RNN", "graph_rnn_activation": "ReLU"}])
+@pytest.mark.parametrize("cfg", [{}, {"use_propagation_attention": True}, {"graph_rnn_cell": "RNN", "graph_rnn_activation": "ReLU"},
+                                 {"graph_rnn_cell": "CudnnCompatibleGRUCell"}])
 def test_sparse_model_trains_saves_and_restores_on_the_host(tmp_path, stand_in, cfg):
     mols = synthetic.make_molecules(64, seed=1)
     m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, **cfg))
@@ -74,6 +75,11 @@ def test_sparse_model_trains_saves_and_restores_on_the_host(tmp_path, stand_in, 
     saved = pickle.load(open(path, "rb"))["weights"]
     assert "graph_model/gnn_layer_0/gnn_edge_weights_0:0" in saved and "out_layer_task0/regression/MLP_W_layer0:0" in saved
     assert "beta1_power:0" in saved and any(k.endswith("/Adam_1:0") for k in saved)
+    if cfg.get("graph_rnn_cell") == "CudnnCompatibleGRUCell":   # sparse:105-108: the cell's own variable scopes, TF's shapes (Din = 2D in layer 1)
+        c = "graph_model/gnn_layer_1/timestep_0/cudnn_compatible_gru_cell/"
+        assert saved[c + "candidate/input_projection/kernel:0"].shape == (32, 16) and saved[c + "candidate/hidden_projection/kernel:0"].shape == (16, 16)
+        assert saved[c + "candidate/hidden_projection/bias:0"].shape == (16,) and saved[c + "gates/kernel:0"].shape == (48, 32)
+        assert np.abs(saved[c + "candidate/hidden_projection/bias:0"]).max() > 0          # it is trained
     m2 = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, **cfg))
     assert m2.restore_progress(path) == (3, 1)
     for (n, a), (_, b) in zip(m.trainable_variables(), m2.trainable_variables()):

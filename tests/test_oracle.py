@@ -23,6 +23,10 @@ PARAM_SETS = {
     "gru_relu_bias_avg": {"hidden_size": 7, "layer_timesteps": [2, 1], "residual_connections": {"1": [0, 1]},
                           "use_edge_bias": True, "use_edge_msg_avg_aggregation": True,
                           "graph_rnn_cell": "gru", "graph_rnn_activation": "relu"},
+    # sparse:105-108: tf.contrib.cudnn_rnn.CudnnCompatibleGRUCell (reset gate applied after the recurrent matmul), residual input
+    "cudnn_gru": {"hidden_size": 8, "layer_timesteps": [2, 2], "residual_connections": {"1": [0]},
+                  "use_edge_bias": True, "use_edge_msg_avg_aggregation": True,
+                  "graph_rnn_cell": "CudnnCompatibleGRUCell", "graph_rnn_activation": "tanh"},
 }
 
 
@@ -198,7 +202,7 @@ def test_propagation_attention_three_statements_agree():
     np.testing.assert_allclose(att, mean, rtol=1e-6, atol=1e-7)
 
 
-REFGRAPH_SPARSE = ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg"]
+REFGRAPH_SPARSE = ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg", "cudnn_gru"]
 
 
 def _load_refgraph_sparse(golden_dir, name):
