@@ -138,7 +138,8 @@ struct ggnn_engine {
     float drop_keep = 1.0f; unsigned long long drop_seed = 0;          // state dropout for the next forward
     float saved_drop_keep = 1.0f; unsigned long long saved_drop_seed = 0; // ... and what the saved forward used
     int last_launches = 0;
-    std::vector<int> h_counts, h_diff;   // host scratch of ggnn_set_graph_sparse, kept between batches
+    std::vector<int> h_counts, h_diff;   // host scratch of the sparse-graph builder, kept between batches
+    struct ggnn_prepared_graph* own_prep = nullptr;   // the prepared graph ggnn_set_graph_sparse builds and uploads from (reused every batch)
     std::string err;
 
     int fail(int code, const char* fmt, ...) {
@@ -150,6 +151,21 @@ struct ggnn_engine {
         err = buf;
         return code;
     }
+};
+
+// The host half of ggnn_set_graph_sparse as an object: `plan` is a shadow engine that carries the model shape in and the batch / tile-plan
+// fields out and never touches the device; the packed image (CSR, in-degrees, tiles, streaming tables) sits in pinned memory, or in plain
+// memory when no CUDA device is present (host-only construction, CPU test-suite).  Built by a producer thread, uploaded by the engine's
+// thread (ggnn_set_graph_prepared) -- the ThreadedIterator overlap of the reference's training loop (chem_tensorflow.py:225, utils.py:16-36).
+struct ggnn_prepared_graph {
+    ggnn_engine plan;
+    HostPinned stage;
+    std::vector<char> plain;         // image when !use_cuda
+    char* image = nullptr;
+    size_t bytes = 0;
+    bool use_cuda = true;
+    bool valid = false;
+    cudaEvent_t uploaded = nullptr;  // recorded after the H2D copy of the image: the next build waits for it before overwriting
 };
 
 #define CU_TRY(e, call)                                                                           \
