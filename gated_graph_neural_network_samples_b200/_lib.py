@@ -42,6 +42,15 @@ SYMBOLS = {
     "ggnn_last_error": (C.c_char_p, [C.c_void_p]),
     "ggnn_set_weights": (C.c_int, [C.c_void_p, C.POINTER(GgnnLayerWeights), C.c_int32]),
     "ggnn_set_graph_sparse": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), c_i32p, C.c_void_p, C.c_void_p]),
+    "ggnn_prepare_graph_sparse": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ggnn_set_graph_prepared": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ggnn_free_prepared_graph": (C.c_int, [C.c_void_p]),
+    "ggnn_prepared_graph_error": (C.c_char_p, [C.c_void_p]),
+    "ggnn_host_prepare_graph_sparse": (C.c_int, [C.POINTER(GgnnConfig), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, C.c_void_p,
+                                                 C.POINTER(C.c_void_p)]),
+    "ggnn_prepared_graph_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
+                                           C.POINTER(C.c_int32), C.c_char_p, C.c_int32]),
+    "ggnn_prepared_graph_arrays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6),
     "ggnn_set_graph_dense": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ggnn_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ggnn_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

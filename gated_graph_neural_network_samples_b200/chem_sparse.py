@@ -153,7 +153,13 @@ class SparseGGNNChemModel(ChemModel):
         T, D = self.num_edge_types, self.params['hidden_size']
         adjacency_lists = [feed[k] for k in self.placeholders['adjacency_lists']]
         self.engine.set_save_for_backward(torch.is_grad_enabled())   # before set_graph: the source-keyed CSR is built there
-        self.engine.set_graph_sparse(adjacency_lists, feed[self.placeholders['num_incoming_edges_per_type']])
+        prepared = feed.get('_prepared_graph')
+        if prepared is not None and prepared.for_training == torch.is_grad_enabled():
+            # the host half (CSR, tile plan, pinned image) was built by the batch producer thread: only the upload is left
+            self.engine.set_graph_prepared(prepared)
+            self._prepared_pool.append(prepared)    # rebuilt in place for a later batch; a rebuild first waits for this upload
+        else:
+            self.engine.set_graph_sparse(adjacency_lists, feed[self.placeholders['num_incoming_edges_per_type']])
         state_keep = float(feed.get(self.placeholders['graph_state_keep_prob'], 1.0))
         # DropoutWrapper(state_keep_prob), sparse:113-114: done inside the kernels; a fresh mask seed per run, drawn from
         # torch's generator (seeded by params['random_seed'] like tf.set_random_seed, chem_tensorflow.py:85)
@@ -243,4 +249,14 @@ class SparseGGNNChemModel(ChemModel):
             feed['edge_weight_dropout_keep_prob'] = edge_keep
             for e, key in enumerate(self.placeholders['adjacency_lists']):
                 feed[key] = b['adjacency_lists'][e]
+            # This generator runs in ChemModel.run_epoch's ThreadedIterator (chem_tensorflow.py:225): the engine's host half -- index
+            # validation, stable target-sorted CSR, tile plan, one pinned image -- is done HERE, next to the packing it follows in the
+            # reference (sparse:288-350), so the consumer thread only enqueues the upload and the kernels
+            if getattr(self, 'prepare_graphs_in_producer', True) and hasattr(getattr(self, 'engine', None), 'prepare_graph_sparse'):
+                pool = self.__dict__.setdefault('_prepared_pool', [])
+                reuse = pool.pop() if pool else None
+                g = self.engine.prepare_graph_sparse(b['adjacency_lists'], b['num_incoming_edges_per_type'], save_for_backward=is_training,
+                                                     reuse=reuse)
+                g.for_training = bool(is_training)
+                feed['_prepared_graph'] = g
             yield feed

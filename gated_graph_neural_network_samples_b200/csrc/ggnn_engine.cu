@@ -560,10 +560,10 @@ extern "C" {
 
 const char* ggnn_last_error(const ggnn_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
-int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
+// The model shape of a ggnn_config (what prepare_specific_graph_model fixes) -> e; no CUDA.  Shared by ggnn_create and the host-only
+// constructor of prepared graphs.  Returns GGNN_OK or an error code with the text in g_create_error.
+static int init_model_shape(ggnn_engine* e, const ggnn_config* cfg) {
     auto bad = [&](const char* msg) { g_create_error = msg; return (int)GGNN_EINVAL; };
-    if (!cfg || !out) return bad("null argument");
-    *out = nullptr;
     if (cfg->hidden_size <= 0 || cfg->hidden_size % 4 != 0) return bad("hidden_size must be a positive multiple of 4");
     if (cfg->hidden_size > 256) { g_create_error = "hidden_size > 256 is not supported by this build"; return GGNN_EUNSUPPORTED; }
     if (cfg->num_edge_types <= 0 || cfg->num_edge_types > 32) return bad("num_edge_types must be in 1..32");
@@ -573,28 +573,27 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     if (cfg->cell == GGNN_CELL_CUDNN_GRU && cfg->activation != GGNN_ACT_TANH) return bad("CudnnCompatibleGRUCell requires the tanh activation");   // sparse:106
     if (cfg->activation != GGNN_ACT_TANH && cfg->activation != GGNN_ACT_RELU) return bad("Unknown activation function type");  // sparse:81
     if (cfg->precision != GGNN_PREC_FP32 && cfg->precision != GGNN_PREC_BF16X3 && cfg->precision != GGNN_PREC_BF16) return bad("unknown precision");
-    ggnn_engine* e = new ggnn_engine();
     e->D = cfg->hidden_size; e->T = cfg->num_edge_types; e->L = cfg->num_layers;
     e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
     e->cell = cfg->cell; e->act = cfg->activation; e->precision = cfg->precision; e->device = cfg->device;
     e->use_att = cfg->use_propagation_attention != 0;
-    if (e->use_att && e->T > 16) { delete e; g_create_error = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
+    if (e->use_att && e->T > 16) { g_create_error = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
     if (e->use_att) e->precision = GGNN_PREC_FP32;   // the softmax-weighted gather lives in the fp32 kernel only (the plan text says so)
     if (e->cell == CELL_CUDNN_GRU) e->precision = GGNN_PREC_FP32;   // so does the reset-after-matmul candidate of CudnnCompatibleGRUCell
     int total = 0;
     for (int l = 0; l < e->L; ++l) {
-        if (cfg->layer_timesteps[l] < 0) { delete e; return bad("negative layer_timesteps entry"); }
+        if (cfg->layer_timesteps[l] < 0) return bad("negative layer_timesteps entry");
         e->steps[l] = cfg->layer_timesteps[l];
         e->step_base[l] = total;
         total += e->steps[l];
         int nr = 0;
         if (cfg->residual_offsets && cfg->residual_layers) {
             nr = cfg->residual_offsets[l + 1] - cfg->residual_offsets[l];
-            if (nr < 0 || nr > MAX_RES) { delete e; return bad("a layer has more than 4 residual inputs"); }
+            if (nr < 0 || nr > MAX_RES) return bad("a layer has more than 4 residual inputs");
             for (int i = 0; i < nr; ++i) {
                 int r = cfg->residual_layers[cfg->residual_offsets[l] + i];
                 // node_states_per_layer has l+1 entries when layer l is built (sparse:144: IndexError otherwise)
-                if (r < 0 || r > l) { delete e; return bad("residual connection refers to a layer that does not exist yet"); }
+                if (r < 0 || r > l) return bad("residual connection refers to a layer that does not exist yet");
                 e->res[l][i] = r;
             }
         }
@@ -602,6 +601,14 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     }
     e->total_steps = total;
     e->DP = (e->D + 15) / 16 * 16;
+    return GGNN_OK;
+}
+
+int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return GGNN_EINVAL; }
+    *out = nullptr;
+    ggnn_engine* e = new ggnn_engine();
+    if (int rc = init_model_shape(e, cfg)) { delete e; return rc; }
     cudaError_t st = cudaSetDevice(e->device);
     cudaDeviceProp prop;
     if (st == cudaSuccess) st = cudaGetDeviceProperties(&prop, e->device);
@@ -628,6 +635,7 @@ int ggnn_destroy(ggnn_engine* e) {
     e->graph_buf.release(); e->state_buf.release(); e->save_bufs.release(); e->io_buf.release(); e->bwd_buf.release();
     e->tc_weights.release(); e->tc_respre.release(); e->ts_weights.release(); e->ts_images.release(); e->ts_u.release(); e->ts_virt.release(); e->err_flag.release(); e->dbg_buf.release();
     e->graph_stage.release();
+    if (e->own_prep) { ggnn_free_prepared_graph(e->own_prep); e->own_prep = nullptr; }
     if (e->stage_done) cudaEventDestroy(e->stage_done);
     if (e->ro_stage_done) cudaEventDestroy(e->ro_stage_done);
     e->ro_buf.release(); e->ro_stage.release(); e->att_buf.release();
@@ -794,9 +802,12 @@ int ggnn_host_stream_tables(int32_t V, int32_t T, const int32_t* const* adj, con
     return GGNN_OK;
 }
 
-int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
-                          const float* indeg, ggnn_stream_t stream) {
-    if (!e) return GGNN_EINVAL;
+// ---- the host half of ggnn_set_graph_sparse: validation, tile plan, stable target-sorted CSR, streaming tables -> g->image.
+// `e` below is the prepared graph's shadow engine (model shape in, batch / plan fields out): nothing here touches the device except the
+// pinned allocation of the image and the wait for the previous upload out of the same image.
+static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* const* adj, const int32_t* num_edges, const float* indeg) {
+    ggnn_engine* e = &g->plan;
+    g->valid = false;
     static const bool host_timing = getenv("GGNN_HOST_TIMING") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto lap = [&](const char* what, std::chrono::steady_clock::time_point& t) {
@@ -808,7 +819,6 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     auto t_lap = t_begin;
     e->graph_set = false; e->saved_valid = false;
     if (V < 0 || !adj || !num_edges || (!indeg && V > 0)) return e->fail(GGNN_EINVAL, "null/negative argument");
-    CU_TRY(e, cudaSetDevice(e->device));
     const int T = e->T;
     int64_t M = 0;
     for (int t = 0; t < T; ++t) {
@@ -896,9 +906,16 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     }
     e->ts_nv = nv;
     for (int t = 0; t < T; ++t) e->edges_of_type[t] = num_edges[t];
-    if (e->stage_done) CU_TRY(e, cudaEventSynchronize(e->stage_done));   // previous upload may still be reading the stage
-    CU_TRY(e, e->graph_stage.reserve(off));
-    char* base = (char*)e->graph_stage.ptr;
+    if (g->use_cuda) {
+        if (g->uploaded) CU_TRY(e, cudaEventSynchronize(g->uploaded));   // the previous upload may still be reading this image
+        CU_TRY(e, g->stage.reserve(off));
+        g->image = (char*)g->stage.ptr;
+    } else {
+        if (g->plain.size() < off) g->plain.resize(off + off / 4 + 256);
+        g->image = g->plain.data();
+    }
+    g->bytes = off;
+    char* base = g->image;
     int* row_ptr = (int*)(base + e->off_row_ptr);
     int* csr_src = (int*)(base + e->off_src);
     int* csr_msg = (int*)(base + e->off_msg);
@@ -987,14 +1004,139 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
     }
     for (int i = 0; i <= ntiles; ++i) h_tiles[i] = tile_start[i];
     lap("denom+masks+extra", t_lap);
-    rc = upload_graph(e, off, (cudaStream_t)stream);
+    g->valid = true;
+    return GGNN_OK;
+}
+
+// Model shape (what ggnn_create fixed) -> the shadow engine of a prepared graph.
+static void copy_model_shape(ggnn_engine* dst, const ggnn_engine* src) {
+    dst->D = src->D; dst->T = src->T; dst->L = src->L; dst->DP = src->DP;
+    memcpy(dst->steps, src->steps, sizeof dst->steps); memcpy(dst->nres, src->nres, sizeof dst->nres);
+    memcpy(dst->res, src->res, sizeof dst->res); memcpy(dst->step_base, src->step_base, sizeof dst->step_base);
+    dst->total_steps = src->total_steps;
+    dst->use_bias = src->use_bias; dst->use_avg = src->use_avg; dst->cell = src->cell; dst->act = src->act;
+    dst->precision = src->precision; dst->device = src->device; dst->num_sms = src->num_sms; dst->max_smem = src->max_smem;
+    dst->use_att = src->use_att;
+    dst->save = src->save;   // decides whether the source-keyed CSR of the backward pass is part of the image
+}
+
+// Batch / tile-plan fields (everything build_plan and build_sparse_image derive from a batch) -> the engine that uploads the image.
+static void adopt_plan(ggnn_engine* dst, const ggnn_engine* src) {
+    dst->V = src->V; dst->M = src->M; dst->gather_mode = src->gather_mode; dst->dense_v = src->dense_v;
+    dst->variant = src->variant; dst->nb1 = src->nb1; dst->local = src->local; dst->ntiles = src->ntiles;
+    dst->max_span = src->max_span; dst->max_tile_msgs = src->max_tile_msgs; dst->plan_text = src->plan_text;
+    dst->stream = src->stream;
+    for (int i = 0; i < 2; ++i) { dst->ts_nc[i] = src->ts_nc[i]; dst->ts_nblk[i] = src->ts_nblk[i]; }
+    dst->ts_nv = src->ts_nv; dst->tc_row_budget = src->tc_row_budget; dst->tc_kgs = src->tc_kgs;
+    dst->off_row_ptr = src->off_row_ptr; dst->off_src = src->off_src; dst->off_msg = src->off_msg; dst->off_indeg = src->off_indeg;
+    dst->off_denom = src->off_denom; dst->off_tiles = src->off_tiles; dst->off_mask = src->off_mask; dst->off_adj = src->off_adj;
+    dst->has_transpose = src->has_transpose; dst->off_trow = src->off_trow; dst->off_ttgt = src->off_ttgt; dst->off_tslot = src->off_tslot;
+    dst->off_pair = src->off_pair; dst->off_vptr = src->off_vptr; dst->off_vsrc = src->off_vsrc; dst->off_tvp = src->off_tvp;
+    dst->off_vinfo = src->off_vinfo;
+    memcpy(dst->edges_of_type, src->edges_of_type, sizeof dst->edges_of_type);
+}
+
+int ggnn_free_prepared_graph(ggnn_prepared_graph* g) {
+    if (!g) return GGNN_OK;
+    if (g->use_cuda) {
+        cudaSetDevice(g->plan.device);
+        if (g->uploaded) { cudaEventSynchronize(g->uploaded); cudaEventDestroy(g->uploaded); }
+        g->stage.release();
+    }
+    delete g;
+    return GGNN_OK;
+}
+
+const char* ggnn_prepared_graph_error(const ggnn_prepared_graph* g) { return g ? g->plan.err.c_str() : "null prepared graph"; }
+
+int ggnn_host_prepare_graph_sparse(const ggnn_config* cfg, int32_t num_sms, int32_t save_for_backward, int32_t V, const int32_t* const* adj,
+                                   const int32_t* num_edges, const float* indeg, ggnn_prepared_graph** inout) {
+    if (!cfg || !inout || num_sms <= 0) return GGNN_EINVAL;
+    ggnn_prepared_graph* g = *inout;
+    if (!g) { g = new ggnn_prepared_graph(); *inout = g; }
+    g->use_cuda = false;
+    g->valid = false;
+    if (int rc = init_model_shape(&g->plan, cfg)) { g->plan.err = g_create_error; return rc; }
+    g->plan.num_sms = num_sms; g->plan.max_smem = 227 * 1024;
+    g->plan.save = save_for_backward != 0;
+    return build_sparse_image(g, V, adj, num_edges, indeg);
+}
+
+int ggnn_prepared_graph_info(const ggnn_prepared_graph* g, int32_t* num_nodes, int64_t* num_messages, int32_t* num_tiles, int64_t* image_bytes,
+                             int32_t* is_streaming, char* plan_text, int32_t plan_text_capacity) {
+    if (!g || !g->valid) return GGNN_ESTATE;
+    if (num_nodes) *num_nodes = g->plan.V;
+    if (num_messages) *num_messages = g->plan.M;
+    if (num_tiles) *num_tiles = g->plan.ntiles;
+    if (image_bytes) *image_bytes = (int64_t)g->bytes;
+    if (is_streaming) *is_streaming = g->plan.stream ? 1 : 0;
+    if (plan_text && plan_text_capacity > 0) snprintf(plan_text, (size_t)plan_text_capacity, "%s", g->plan.plan_text.c_str());
+    return GGNN_OK;
+}
+
+int ggnn_prepared_graph_arrays(const ggnn_prepared_graph* g, int32_t* row_ptr, int32_t* src, int32_t* msg, int32_t* tile_start, float* denom,
+                               int32_t* pair_src) {
+    if (!g || !g->valid) return GGNN_ESTATE;
+    const ggnn_engine& q = g->plan;
+    const char* base = g->image;
+    const size_t V = (size_t)q.V, T = (size_t)q.T, M = (size_t)q.M;
+    if (row_ptr) memcpy(row_ptr, base + q.off_row_ptr, sizeof(int) * (V * T + 1));
+    if (src && M) memcpy(src, base + q.off_src, sizeof(int) * M);
+    if (msg && M) memcpy(msg, base + q.off_msg, sizeof(int) * M);
+    if (tile_start) memcpy(tile_start, base + q.off_tiles, sizeof(int) * (size_t)(q.ntiles + 1));
+    if (denom && V) memcpy(denom, base + q.off_denom, sizeof(float) * V);
+    if (pair_src && q.stream) memcpy(pair_src, base + q.off_pair, sizeof(int) * (size_t)std::max(q.ntiles, 1) * ts::TILE_M * T);
+    return GGNN_OK;
+}
+
+int ggnn_prepare_graph_sparse(const ggnn_engine* e, int32_t save_for_backward, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
+                              const float* indeg, ggnn_prepared_graph** inout) {
+    if (!e || !inout) return GGNN_EINVAL;
+    ggnn_prepared_graph* g = *inout;
+    if (!g) { g = new ggnn_prepared_graph(); *inout = g; }
+    g->use_cuda = true;
+    copy_model_shape(&g->plan, e);
+    if (save_for_backward >= 0) g->plan.save = save_for_backward != 0;   // a producer thread says what the batch will be used for
+    if (cudaSetDevice(e->device) != cudaSuccess) return g->plan.fail(GGNN_ECUDA, "cudaSetDevice(%d) failed", e->device);   // this may be a producer thread
+    return build_sparse_image(g, V, adj, num_edges, indeg);
+}
+
+int ggnn_set_graph_prepared(ggnn_engine* e, ggnn_prepared_graph* g, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    e->graph_set = false; e->saved_valid = false;
+    if (!g || !g->valid) return e->fail(GGNN_ESTATE, "the prepared graph is empty (its build failed or never ran)");
+    const ggnn_engine& q = g->plan;
+    if (q.D != e->D || q.T != e->T || q.precision != e->precision || q.DP != e->DP || q.num_sms != e->num_sms || q.cell != e->cell || q.use_att != e->use_att)
+        return e->fail(GGNN_EINVAL, "the prepared graph was built for a different engine configuration");
+    if (e->save && !q.has_transpose)
+        return e->fail(GGNN_ESTATE, "save_for_backward is on but the graph was prepared without it (the source-keyed CSR is built at prepare time)");
+    CU_TRY(e, cudaSetDevice(e->device));
+    adopt_plan(e, &q);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(e, e->graph_buf.reserve(g->bytes));
+    CU_TRY(e, cudaMemcpyAsync(e->graph_buf.ptr, g->image, g->bytes, cudaMemcpyHostToDevice, st));
+    if (g->use_cuda) {
+        if (!g->uploaded) CU_TRY(e, cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming));
+        CU_TRY(e, cudaEventRecord(g->uploaded, st));
+    } else {
+        CU_TRY(e, cudaStreamSynchronize(st));   // a pageable image (host-only construction) must be consumed before the caller may reuse it
+    }
+    int rc = reserve_states(e);
     if (rc) return rc;
-    rc = reserve_states(e);
-    if (rc) return rc;
-    lap("upload enqueue", t_lap);
     e->graph_set = true;
     return GGNN_OK;
 }
+
+int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, const int32_t* num_edges,
+                          const float* indeg, ggnn_stream_t stream) {
+    if (!e) return GGNN_EINVAL;
+    e->graph_set = false; e->saved_valid = false;
+    // the same two halves a caller can run on two threads: build into the engine's own prepared graph, then upload it
+    int rc = ggnn_prepare_graph_sparse(e, -1, V, adj, num_edges, indeg, &e->own_prep);
+    if (rc) { if (e->own_prep) e->err = e->own_prep->plan.err; return rc; }
+    return ggnn_set_graph_prepared(e, e->own_prep, stream);
+}
+
 
 int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;

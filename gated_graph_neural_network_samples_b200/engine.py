@@ -48,8 +48,95 @@ def weight_shapes(params: dict, num_edge_types: int, layer_idx: int) -> Dict[str
     return shapes
 
 
+def make_config(params: dict, num_edge_types: int, device: int = 0, precision: str = "fp32"):
+    """``ggnn_config`` of a parameter dict (the keys the two hooks read, sparse:40-61) + the ctypes arrays it points into (keep them alive)."""
+    steps = [int(s) for s in params["layer_timesteps"]]
+    L = len(steps)
+    act = params.get("graph_rnn_activation", "tanh").lower()
+    if act not in ("tanh", "relu"):
+        raise Exception("Unknown activation function type '%s'." % act)                      # sparse:81
+    cell = params.get("graph_rnn_cell", "GRU").lower()
+    if cell not in CELL_CODES:
+        raise Exception("Unknown RNN cell type '%s'." % cell)                                # sparse:112
+    if cell == "cudnncompatiblegrucell":
+        assert act == "tanh"                                                                 # sparse:106
+    offs, flat = [0], []
+    for l in range(L):
+        flat += residual_inputs_of_layer(params, l)
+        offs.append(len(flat))
+    keep = ((C.c_int32 * L)(*steps), (C.c_int32 * (L + 1))(*offs), (C.c_int32 * max(len(flat), 1))(*flat))
+    cfg = _lib.GgnnConfig(int(params["hidden_size"]), int(num_edge_types), L, keep[0], keep[1], keep[2],
+                          int(bool(params.get("use_edge_bias", False))), int(bool(params.get("use_edge_msg_avg_aggregation", False))),
+                          CELL_CODES[cell], 0 if act == "tanh" else 1, PRECISIONS[precision], int(device),
+                          int(bool(params.get("use_propagation_attention", False))))
+    return cfg, keep
+
+
 class GgnnError(Exception):
     """Raised for every non-zero return of the C ABI (the reference raises plain ``Exception``s too)."""
+
+
+class PreparedGraph:
+    """Handle of a ``ggnn_prepared_graph`` (include/ggnn_b200.h): the host half of one batch's graph structure."""
+
+    def __init__(self, lib=None):
+        self.lib = lib or _lib.load()
+        self._h = C.c_void_p()
+        self.V = 0
+
+    @classmethod
+    def host_only(cls, params: dict, num_edge_types: int, adjacency_lists, num_incoming_edges_per_type, precision: str = "fp32",
+                  num_sms: int = 148, save_for_backward: bool = False, reuse: Optional["PreparedGraph"] = None) -> "PreparedGraph":
+        """``ggnn_host_prepare_graph_sparse``: no engine, no GPU (plain memory instead of pinned)."""
+        g = reuse if reuse is not None else cls()
+        cfg, keep = make_config(params, num_edge_types, 0, precision)
+        T = int(num_edge_types)
+        adjs = [np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, 2)) for a in adjacency_lists]
+        indeg = np.ascontiguousarray(np.asarray(num_incoming_edges_per_type, dtype=np.float32))
+        ptrs = (C.c_void_p * T)(*[a.ctypes.data for a in adjs])
+        counts = (C.c_int32 * T)(*[a.shape[0] for a in adjs])
+        h = C.c_void_p(g._h.value)
+        rc = g.lib.ggnn_host_prepare_graph_sparse(C.byref(cfg), int(num_sms), int(bool(save_for_backward)), indeg.shape[0], ptrs, counts,
+                                                  indeg.ctypes.data, C.byref(h))
+        g._h = h
+        if rc != 0:
+            raise GgnnError(g.lib.ggnn_prepared_graph_error(g._h).decode())
+        g.V = indeg.shape[0]
+        g.T = T
+        return g
+
+    def info(self) -> dict:
+        V, M, nt, nb, st = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int64(), C.c_int32()
+        buf = C.create_string_buffer(512)
+        if self.lib.ggnn_prepared_graph_info(self._h, C.byref(V), C.byref(M), C.byref(nt), C.byref(nb), C.byref(st), buf, 512) != 0:
+            raise GgnnError("the prepared graph is empty")
+        return {"num_nodes": V.value, "num_messages": M.value, "num_tiles": nt.value, "image_bytes": nb.value, "streaming": bool(st.value),
+                "plan": buf.value.decode()}
+
+    def arrays(self, T: int) -> dict:
+        i = self.info()
+        V, M = i["num_nodes"], i["num_messages"]
+        out = {"row_ptr": np.empty(V * T + 1, np.int32), "src": np.empty(M, np.int32), "msg": np.empty(M, np.int32),
+               "tile_start": np.empty(i["num_tiles"] + 1, np.int32), "denom": np.empty(V, np.float32)}
+        pair = np.empty(((V + 127) // 128) * 128 * T, np.int32) if i["streaming"] else None
+        if self.lib.ggnn_prepared_graph_arrays(self._h, out["row_ptr"].ctypes.data, out["src"].ctypes.data, out["msg"].ctypes.data,
+                                               out["tile_start"].ctypes.data, out["denom"].ctypes.data,
+                                               None if pair is None else pair.ctypes.data) != 0:
+            raise GgnnError("the prepared graph is empty")
+        if pair is not None:
+            out["pair_src"] = pair
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.ggnn_free_prepared_graph(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class PropagationEngine:
@@ -59,28 +146,8 @@ class PropagationEngine:
         self.params = dict(params)
         self.D = int(params["hidden_size"])
         self.T = int(num_edge_types)
-        steps = [int(s) for s in params["layer_timesteps"]]
-        self.L = len(steps)
-        act = params.get("graph_rnn_activation", "tanh").lower()
-        if act not in ("tanh", "relu"):
-            raise Exception("Unknown activation function type '%s'." % act)                  # sparse:81
-        cell = params.get("graph_rnn_cell", "GRU").lower()
-        if cell not in CELL_CODES:
-            raise Exception("Unknown RNN cell type '%s'." % cell)                            # sparse:112
-        if cell == "cudnncompatiblegrucell":
-            assert act == "tanh"                                                             # sparse:106
-        offs, flat = [0], []
-        for l in range(self.L):
-            flat += residual_inputs_of_layer(params, l)
-            offs.append(len(flat))
-        self._steps = (C.c_int32 * self.L)(*steps)
-        self._offs = (C.c_int32 * (self.L + 1))(*offs)
-        self._flat = (C.c_int32 * max(len(flat), 1))(*flat)
-        cfg = _lib.GgnnConfig(self.D, self.T, self.L, self._steps, self._offs, self._flat,
-                              int(bool(params.get("use_edge_bias", False))),
-                              int(bool(params.get("use_edge_msg_avg_aggregation", False))),
-                              CELL_CODES[cell], 0 if act == "tanh" else 1,
-                              PRECISIONS[precision], int(device), int(bool(params.get("use_propagation_attention", False))))
+        self.L = len(params["layer_timesteps"])
+        cfg, self._cfg_keepalive = make_config(params, num_edge_types, device, precision)
         rc = self.lib.ggnn_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             self._h = C.c_void_p()
@@ -152,6 +219,29 @@ class PropagationEngine:
         self._check(self.lib.ggnn_set_graph_sparse(self._h, V, ptrs, counts, indeg.ctypes.data, self._stream()))
         self.V = V
         self._graph_keepalive = (adjs, indeg)
+
+    def prepare_graph_sparse(self, adjacency_lists, num_incoming_edges_per_type, save_for_backward: Optional[bool] = None,
+                             reuse: Optional["PreparedGraph"] = None) -> "PreparedGraph":
+        """The HOST half of ``set_graph_sparse`` (validation, CSR, tile plan, one pinned image) -- may run in a producer thread while the
+        engine's stream works on the previous batch (ThreadedIterator, chem_tensorflow.py:225).  ``save_for_backward``: whether the batch
+        will be trained on (None = the engine's current flag).  ``reuse``: rebuild a prepared graph in place (its pinned image is kept; the
+        call waits for its previous upload first)."""
+        adjs, indeg, ptrs, counts = self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+        g = reuse if reuse is not None else PreparedGraph(self.lib)
+        h = C.c_void_p(g._h.value)
+        rc = self.lib.ggnn_prepare_graph_sparse(self._h, -1 if save_for_backward is None else int(bool(save_for_backward)), indeg.shape[0], ptrs,
+                                                counts, indeg.ctypes.data, C.byref(h))
+        g._h = h
+        if rc != 0:
+            raise GgnnError(self.lib.ggnn_prepared_graph_error(g._h).decode())
+        g.V = indeg.shape[0]
+        return g
+
+    def set_graph_prepared(self, g: "PreparedGraph"):
+        """The DEVICE half: adopt the plan, enqueue the one H2D copy of the image.  Keep ``g`` alive until the stream has passed it."""
+        self._check(self.lib.ggnn_set_graph_prepared(self._h, g._h, self._stream()))
+        self.V = g.V
+        self._graph_keepalive = (g,)
 
     def run_sparse_host(self, adjacency_lists, num_incoming_edges_per_type, h0: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """One call per batch (the shape of ``sess.run(fetch, feed_dict)``, chem_tensorflow.py:235): graph + initial

@@ -109,6 +109,38 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t num_nodes, const int32_t* cons
                           const int32_t* num_edges, const float* num_incoming_edges_per_type,
                           ggnn_stream_t stream);
 
+/* The two halves of ggnn_set_graph_sparse as separate calls, so that the host half can run in a PRODUCER THREAD while the engine's
+ * stream is still busy with the previous batch -- the overlap the reference gets from ThreadedIterator around its batch packer
+ * (chem_tensorflow.py:225, utils.py:16-36):
+ *   ggnn_prepare_graph_sparse   host only: index validation, stable target-sorted CSR, tile plan, streaming tables, packed into ONE
+ *                               pinned image.  Reads the engine's configuration and nothing else of it: thread-safe against calls on the
+ *                               engine from another thread.  save_for_backward: 1 / 0 = whether the batch will be trained on (the
+ *                               source-keyed CSR of ggnn_backward is part of the image), -1 = the engine's flag at this moment.
+ *                               *inout = NULL allocates a prepared graph, a non-NULL one is rebuilt in place (it first waits for its own
+ *                               previous upload).
+ *   ggnn_set_graph_prepared     engine thread: adopts the plan and enqueues the single H2D copy of the image on `stream`.  The prepared
+ *                               graph must stay alive (and must not be rebuilt from a thread that skips the wait above) until that copy ran.
+ * ggnn_set_graph_sparse is exactly these two calls on an engine-owned prepared graph.  On failure the text is in
+ * ggnn_prepared_graph_error (prepare) / ggnn_last_error (set). */
+typedef struct ggnn_prepared_graph ggnn_prepared_graph;
+int ggnn_prepare_graph_sparse(const ggnn_engine* e, int32_t save_for_backward, int32_t num_nodes, const int32_t* const* adjacency_lists,
+                              const int32_t* num_edges, const float* num_incoming_edges_per_type, ggnn_prepared_graph** inout);
+int ggnn_set_graph_prepared(ggnn_engine* e, ggnn_prepared_graph* g, ggnn_stream_t stream);
+int ggnn_free_prepared_graph(ggnn_prepared_graph* g);
+const char* ggnn_prepared_graph_error(const ggnn_prepared_graph* g);
+/* The same host half without an engine or a GPU (plain memory instead of pinned): what the CPU test-suite pins against
+ * ggnn_host_target_csr / ggnn_host_tile_plan / ggnn_host_stream_tables, and a way to prepare batches on a machine without a device. */
+int ggnn_host_prepare_graph_sparse(const ggnn_config* cfg, int32_t num_sms, int32_t save_for_backward, int32_t num_nodes,
+                                   const int32_t* const* adjacency_lists, const int32_t* num_edges,
+                                   const float* num_incoming_edges_per_type, ggnn_prepared_graph** inout);
+/* Introspection of a prepared graph: sizes and plan text; copies of its CSR (row_ptr [V*T+1], src [M], msg [M]), tile starts
+ * [num_tiles+1], per-node mean-aggregation denominators [V] and, for a streaming plan, the (target, type) -> source table
+ * [ceil(V/128)*128*T] (NULL pointers are skipped; pair_src of a non-streaming plan is left untouched and *is_streaming = 0). */
+int ggnn_prepared_graph_info(const ggnn_prepared_graph* g, int32_t* num_nodes, int64_t* num_messages, int32_t* num_tiles, int64_t* image_bytes,
+                             int32_t* is_streaming, char* plan_text, int32_t plan_text_capacity);
+int ggnn_prepared_graph_arrays(const ggnn_prepared_graph* g, int32_t* row_ptr, int32_t* src, int32_t* msg, int32_t* tile_start, float* denom,
+                               int32_t* pair_src);
+
 /* Dense wire format (dense:214-224): adjacency_matrix [b, T, v, v] float32 HOST pointer with
  * A[g, t, dest, src] (dense:30-36).  Rows are the b*v padded nodes. */
 int ggnn_set_graph_dense(ggnn_engine* e, int32_t num_graphs, int32_t num_vertices,
