@@ -561,11 +561,11 @@ extern "C" {
 const char* ggnn_last_error(const ggnn_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
 
 // The model shape of a ggnn_config (what prepare_specific_graph_model fixes) -> e; no CUDA.  Shared by ggnn_create and the host-only
-// constructor of prepared graphs.  Returns GGNN_OK or an error code with the text in g_create_error.
-static int init_model_shape(ggnn_engine* e, const ggnn_config* cfg) {
-    auto bad = [&](const char* msg) { g_create_error = msg; return (int)GGNN_EINVAL; };
+// constructor of prepared graphs (which may run in any thread: the text goes to `err`, not to a global).  Returns GGNN_OK or an error code.
+static int init_model_shape(ggnn_engine* e, const ggnn_config* cfg, std::string& err) {
+    auto bad = [&](const char* msg) { err = msg; return (int)GGNN_EINVAL; };
     if (cfg->hidden_size <= 0 || cfg->hidden_size % 4 != 0) return bad("hidden_size must be a positive multiple of 4");
-    if (cfg->hidden_size > 256) { g_create_error = "hidden_size > 256 is not supported by this build"; return GGNN_EUNSUPPORTED; }
+    if (cfg->hidden_size > 256) { err = "hidden_size > 256 is not supported by this build"; return GGNN_EUNSUPPORTED; }
     if (cfg->num_edge_types <= 0 || cfg->num_edge_types > 32) return bad("num_edge_types must be in 1..32");
     if (cfg->num_layers <= 0 || cfg->num_layers > MAX_LAYERS) return bad("num_layers must be in 1..16");
     if (!cfg->layer_timesteps) return bad("layer_timesteps is null");
@@ -577,7 +577,7 @@ static int init_model_shape(ggnn_engine* e, const ggnn_config* cfg) {
     e->use_bias = cfg->use_edge_bias != 0; e->use_avg = cfg->use_edge_msg_avg_aggregation != 0;
     e->cell = cfg->cell; e->act = cfg->activation; e->precision = cfg->precision; e->device = cfg->device;
     e->use_att = cfg->use_propagation_attention != 0;
-    if (e->use_att && e->T > 16) { g_create_error = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
+    if (e->use_att && e->T > 16) { err = "propagation attention supports at most 16 edge types"; return GGNN_EUNSUPPORTED; }
     if (e->use_att) e->precision = GGNN_PREC_FP32;   // the softmax-weighted gather lives in the fp32 kernel only (the plan text says so)
     if (e->cell == CELL_CUDNN_GRU) e->precision = GGNN_PREC_FP32;   // so does the reset-after-matmul candidate of CudnnCompatibleGRUCell
     int total = 0;
@@ -608,7 +608,7 @@ int ggnn_create(const ggnn_config* cfg, ggnn_engine** out) {
     if (!cfg || !out) { g_create_error = "null argument"; return GGNN_EINVAL; }
     *out = nullptr;
     ggnn_engine* e = new ggnn_engine();
-    if (int rc = init_model_shape(e, cfg)) { delete e; return rc; }
+    if (int rc = init_model_shape(e, cfg, g_create_error)) { delete e; return rc; }
     cudaError_t st = cudaSetDevice(e->device);
     cudaDeviceProp prop;
     if (st == cudaSuccess) st = cudaGetDeviceProperties(&prop, e->device);
@@ -841,6 +841,7 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
         // iff max_{j < i} reach[j] >= i  (one write per edge instead of the two of a difference array)
         std::vector<int>& reach = diff;
         reach.assign((size_t)V + 1, 0);
+        lap("  clear scratch", t_lap);
         for (int t = 0; t < T; ++t) {
             const int32_t* a = adj[t];
             for (int i = 0; i < num_edges[t]; ++i) {
@@ -849,9 +850,10 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
                     return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
                 ++counts[(size_t)d * T + t + 1];
                 const int lo = std::min(s, d), hi = std::max(s, d);
-                if (hi > reach[lo]) reach[lo] = hi;
+                reach[lo] = std::max(reach[lo], hi);   // unconditional store: the compare-and-branch form mispredicts on every other edge
             }
         }
+        lap("  edges pass 1", t_lap);
         int far = 0;
         for (int i = 1; i < V; ++i) {
             far = std::max(far, reach[i - 1]);
@@ -1056,7 +1058,7 @@ int ggnn_host_prepare_graph_sparse(const ggnn_config* cfg, int32_t num_sms, int3
     if (!g) { g = new ggnn_prepared_graph(); *inout = g; }
     g->use_cuda = false;
     g->valid = false;
-    if (int rc = init_model_shape(&g->plan, cfg)) { g->plan.err = g_create_error; return rc; }
+    if (int rc = init_model_shape(&g->plan, cfg, g->plan.err)) return rc;
     g->plan.num_sms = num_sms; g->plan.max_smem = 227 * 1024;
     g->plan.save = save_for_backward != 0;
     return build_sparse_image(g, V, adj, num_edges, indeg);
