@@ -138,7 +138,7 @@ struct ggnn_engine {
     float drop_keep = 1.0f; unsigned long long drop_seed = 0;          // state dropout for the next forward
     float saved_drop_keep = 1.0f; unsigned long long saved_drop_seed = 0; // ... and what the saved forward used
     int last_launches = 0;
-    std::vector<int> h_counts, h_diff;   // host scratch of the sparse-graph builder, kept between batches
+    std::vector<int> h_counts, h_diff, h_cursor;   // host scratch of the sparse-graph builder, kept between batches
     struct ggnn_prepared_graph* own_prep = nullptr;   // the prepared graph ggnn_set_graph_sparse builds and uploads from (reused every batch)
     std::string err;
 
@@ -802,6 +802,28 @@ int ggnn_host_stream_tables(int32_t V, int32_t T, const int32_t* const* adj, con
     return GGNN_OK;
 }
 
+#ifdef _OPENMP
+// One-time probe per process: is a parallel region of `team` threads cheap to enter here?  (Third of three empty regions under 150 us.)
+static bool host_team_is_fast(int team) {
+    static int verdict[65] = {0};   // 0 unknown, 1 fast, -1 slow; a benign race at worst probes twice
+    if (team < 2 || team > 64) return false;
+    if (verdict[team] == 0) {
+        double us = 0.0;
+        for (int rep = 0; rep < 3; ++rep) {
+            const auto t0 = std::chrono::steady_clock::now();
+            int seen = 0;
+#pragma omp parallel num_threads(team) reduction(+ : seen)
+            { seen += 1; }
+            us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+            if (seen < 1) us = 1e9;
+        }
+        verdict[team] = us < 150.0 ? 1 : -1;
+        if (getenv("GGNN_HOST_TIMING")) fprintf(stderr, "[ggnn host] OpenMP team of %d: region entry %.1f us -> %s\n", team, us, us < 150.0 ? "used" : "not used");
+    }
+    return verdict[team] > 0;
+}
+#endif
+
 // ---- the host half of ggnn_set_graph_sparse: validation, tile plan, stable target-sorted CSR, streaming tables -> g->image.
 // `e` below is the prepared graph's shadow engine (model shape in, batch / plan fields out): nothing here touches the device except the
 // pinned allocation of the image and the wait for the previous upload out of the same image.
@@ -828,46 +850,106 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
     if (M > 0x7fffffff || (int64_t)V * T + 1 > 0x7fffffff) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
     e->V = V; e->M = M; e->gather_mode = GATHER_SPARSE; e->dense_v = 0;
 
+    // ---- host threads.  Every pass below is split over `nth` threads by TARGET ranges (pass 1: equal node ranges; later passes: equal
+    // tile ranges): each thread scans the whole edge list (sequential reads) and performs only the scattered writes of its own rows, in the
+    // list's order -- so every row keeps the reference's message order and the image is bit-identical for every thread count
+    // (tests/test_prepared_graph_cpu.py pins it against the single-pass ggnn_host_target_csr and NumPy's stable sort).
+    // Small batches stay on one thread (a cfg2-sized build is ~80 us: less than a team's wake-up).  Large ones use ONE team size per
+    // process, and only after host_team_is_fast() has seen that entering a parallel region of that size is cheap here: libgomp's region
+    // entry can cost milliseconds in some containers (measured: 8-18 ms per region for 2-3 threads on an 8-CPU box, 2 us for 8).
+    int nth = 1;
+#ifdef _OPENMP
+    if (M >= 24000) {
+        const int team = std::min(8, omp_get_max_threads());
+        if (team > 1 && host_team_is_fast(team)) nth = team;
+    }
+    if (const char* nt = getenv("GGNN_HOST_THREADS")) nth = std::max(1, std::min(atoi(nt), 64));
+#endif
     // ---- pass 1: validate, count per (target,type), mark which node boundaries are spanned by an edge (the cut points of the tile-local
     // plans; the streaming plan of hidden sizes > 128 tiles by fixed 128-row blocks and skips that part)
     std::vector<int>& counts = e->h_counts;
-    std::vector<int>& diff = e->h_diff;
-    counts.assign((size_t)V * T + 1, 0);
+    std::vector<int>& reach = e->h_diff;   // reach[j] = the farthest node an edge whose lower end is node j touches
     const bool need_cuts = !(e->precision != GGNN_PREC_FP32 && e->DP > 128);
-    std::vector<int> cuts;
-    cuts.push_back(0);
-    if (need_cuts) {
-        // reach[j] = the farthest node an edge starting at (or below) node j touches: the boundary before node i is crossed by an edge
-        // iff max_{j < i} reach[j] >= i  (one write per edge instead of the two of a difference array)
-        std::vector<int>& reach = diff;
-        reach.assign((size_t)V + 1, 0);
-        lap("  clear scratch", t_lap);
-        for (int t = 0; t < T; ++t) {
-            const int32_t* a = adj[t];
-            for (int i = 0; i < num_edges[t]; ++i) {
-                const int s = a[2 * i], d = a[2 * i + 1];
-                if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
-                    return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
-                ++counts[(size_t)d * T + t + 1];
-                const int lo = std::min(s, d), hi = std::max(s, d);
-                reach[lo] = std::max(reach[lo], hi);   // unconditional store: the compare-and-branch form mispredicts on every other edge
+    counts.resize((size_t)V * T + 1);
+    if (need_cuts) reach.resize((size_t)V + 1);
+    std::vector<int64_t> type_base(T + 1, 0);   // position of every type's first message in the reference's type-major message order
+    for (int t = 0; t < T; ++t) type_base[t + 1] = type_base[t] + num_edges[t];
+    int bad_edge = 0;
+    // Pass 1 is split by EDGE ranges: counting is commutative, so the threads add into the shared per-row counts with relaxed atomic
+    // increments (and an atomic max for `reach`) -- same totals for every thread count; a single thread uses plain increments.
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nth) if (nth > 1)
+#endif
+    {
+        int k = 0, n = 1;
+#ifdef _OPENMP
+        k = omp_get_thread_num(); n = omp_get_num_threads();
+#endif
+        {   // clear this thread's slice of the scratch arrays
+            const size_t nc = (size_t)V * T + 1, c0 = nc * k / n, c1 = nc * (k + 1) / n;
+            std::fill(counts.begin() + c0, counts.begin() + c1, 0);
+            if (need_cuts) {
+                const size_t nr = (size_t)V + 1, r0 = nr * k / n, r1 = nr * (k + 1) / n;
+                std::fill(reach.begin() + r0, reach.begin() + r1, 0);
             }
         }
-        lap("  edges pass 1", t_lap);
+#ifdef _OPENMP
+#pragma omp barrier
+#endif
+        const int64_t e0 = M * k / n, e1 = M * (k + 1) / n;   // this thread's messages, in the type-major order
+        int* const cnt = counts.data();
+        int* const rch = need_cuts ? reach.data() : nullptr;
+        bool bad = false;
+        for (int t = 0; t < T && !bad; ++t) {
+            const int32_t* a = adj[t];
+            const int i0 = (int)(std::max(e0, type_base[t]) - type_base[t]);
+            const int i1 = (int)(std::min(e1, type_base[t + 1]) - type_base[t]);
+            if (n == 1) {
+                for (int i = i0; i < i1; ++i) {
+                    const int s = a[2 * i], d = a[2 * i + 1];
+                    if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) { bad = true; break; }
+                    ++cnt[(size_t)d * T + t + 1];
+                    if (need_cuts) {
+                        const int lo = std::min(s, d), hi = std::max(s, d);
+                        rch[lo] = std::max(rch[lo], hi);   // unconditional store: the compare-and-branch form mispredicts on every other edge
+                    }
+                }
+            } else {
+                for (int i = i0; i < i1; ++i) {
+                    const int s = a[2 * i], d = a[2 * i + 1];
+                    if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V) { bad = true; break; }
+                    __atomic_fetch_add(cnt + ((size_t)d * T + t + 1), 1, __ATOMIC_RELAXED);
+                    if (need_cuts) {
+                        const int lo = std::min(s, d), hi = std::max(s, d);
+                        int cur = __atomic_load_n(rch + lo, __ATOMIC_RELAXED);
+                        while (hi > cur && !__atomic_compare_exchange_n(rch + lo, &cur, hi, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                    }
+                }
+            }
+        }
+        if (bad) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+            bad_edge = 1;
+        }
+    }
+    if (bad_edge) {   // name the first offending edge, like the single pass did
+        for (int t = 0; t < T; ++t)
+            for (int i = 0; i < num_edges[t]; ++i) {
+                const int s = adj[t][2 * i], d = adj[t][2 * i + 1];
+                if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
+                    return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
+            }
+    }
+    lap("  edges pass 1", t_lap);
+    std::vector<int> cuts;
+    cuts.push_back(0);
+    if (need_cuts) {   // the boundary before node i is crossed by an edge iff max_{j < i} reach[j] >= i
         int far = 0;
         for (int i = 1; i < V; ++i) {
             far = std::max(far, reach[i - 1]);
             if (far < i) cuts.push_back(i);
-        }
-    } else {
-        for (int t = 0; t < T; ++t) {
-            const int32_t* a = adj[t];
-            for (int i = 0; i < num_edges[t]; ++i) {
-                const int s = a[2 * i], d = a[2 * i + 1];
-                if ((unsigned)s >= (unsigned)V || (unsigned)d >= (unsigned)V)
-                    return e->fail(GGNN_ERANGE, "edge %d of type %d = (%d,%d) is out of range for %d nodes", i, t, s, d, V);
-                ++counts[(size_t)d * T + t + 1];
-            }
         }
     }
     if (V > 0) cuts.push_back(V);
@@ -877,6 +959,30 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
     if (rc) return rc;
     const int ntiles = e->ntiles;
     lap("tile plan", t_lap);
+    nth = std::max(1, std::min(nth, ntiles));
+    // tile ranges of the threads for all later passes: tiles [tb[k], tb[k+1]), i.e. nodes [tile_start[tb[k]], tile_start[tb[k+1]])
+    std::vector<int> tb(nth + 1);
+    for (int k = 0; k <= nth; ++k) tb[k] = (int)((int64_t)ntiles * k / nth);
+    // per-range totals: messages, and (streaming plan) virtual rows = (target, type) pairs with several messages, with their message count
+    std::vector<int64_t> part_msgs(nth + 1, 0), part_nv(nth + 1, 0), part_nvm(nth + 1, 0);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nth) if (nth > 1)
+#endif
+    for (int k = 0; k < nth; ++k) {
+        int64_t sm = 0, nv = 0, nvm = 0;
+        const size_t k0 = (size_t)tile_start[tb[k]] * T, k1 = (size_t)tile_start[tb[k + 1]] * T;
+        if (e->stream) {
+            for (size_t r = k0; r < k1; ++r) {
+                const int c = counts[r + 1];
+                sm += c;
+                if (c >= 2) { ++nv; nvm += c; }
+            }
+        } else {
+            for (size_t r = k0; r < k1; ++r) sm += counts[r + 1];
+        }
+        part_msgs[k + 1] = sm; part_nv[k + 1] = nv; part_nvm[k + 1] = nvm;
+    }
+    for (int k = 0; k < nth; ++k) { part_msgs[k + 1] += part_msgs[k]; part_nv[k + 1] += part_nv[k]; part_nvm[k + 1] += part_nvm[k]; }
 
     // ---- layout of the packed upload
     size_t off = 0;
@@ -896,10 +1002,9 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
         if (e->use_att) off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(M, 1), 16);
     }
     // streaming plan: per (target, type) pair the ONE node to copy from (or none / a virtual row), see ggnn_fwd_stream.cuh
-    int nv = 0; int64_t nvm = 0;
+    const int nv = (int)part_nv[nth];
+    const int64_t nvm = part_nvm[nth];
     if (e->stream) {
-        for (size_t k = 0; k < (size_t)V * T; ++k)
-            if (counts[k + 1] >= 2) { ++nv; nvm += counts[k + 1]; }
         e->off_pair = off; off = align_up(off + sizeof(int) * (size_t)std::max(ntiles, 1) * ts::TILE_M * T, 16);
         e->off_vptr = off; off = align_up(off + sizeof(int) * (size_t)(nv + 1), 16);
         e->off_vsrc = off; off = align_up(off + sizeof(int) * (size_t)std::max<int64_t>(nvm, 1), 16);
@@ -925,55 +1030,112 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
     float* h_denom = (float*)(base + e->off_denom);
     int* h_tiles = (int*)(base + e->off_tiles);
     unsigned* h_mask = (unsigned*)(base + e->off_mask);
-
+    int* pair = e->stream ? (int*)(base + e->off_pair) : nullptr;   // streaming plan: (target, type) -> its one source / virtual row
+    int* vptr = e->stream ? (int*)(base + e->off_vptr) : nullptr;
+    int* vsrc = e->stream ? (int*)(base + e->off_vsrc) : nullptr;
+    int* tvp = e->stream ? (int*)(base + e->off_tvp) : nullptr;
+    int* vinfo = e->stream ? (int*)(base + e->off_vinfo) : nullptr;
     lap("stage reserve", t_lap);
-    // ---- pass 2, one sweep over the (target, type) rows: exclusive scan -> row_ptr, fill cursors (stored over the consumed counts), the
-    // tiles' edge-type masks and the largest per-tile message count; then the stable fill (iteration in message order keeps the
-    // reference's order per row: this IS NumPy's stable argsort by target, tests pin it bit for bit)
-    {
-        row_ptr[0] = 0;
-        int run = 0;
-        e->max_tile_msgs = 0;
-        for (int i = 0; i < ntiles; ++i) {
+
+    // ---- pass 2, per thread over its tile range: exclusive scan of the (target, type) rows -> row_ptr, fill cursors (stored over the
+    // consumed counts), the tiles' edge-type masks and the largest per-tile message count; then the stable fill -- every thread walks the
+    // lists in the reference's order (type-major, then list order, sparse:124-129) and places the messages of ITS rows, so within a row
+    // they stay in message order: this IS NumPy's stable argsort by target, tests pin it bit for bit; then (streaming plan) the gather
+    // table and the virtual rows of its range, numbered from the range's offset; then in-degrees / denominators of its nodes.
+    std::vector<int>& cursor = e->h_cursor;   // next free slot of every (target, type) row (its own array: the counts of a range's last
+    cursor.resize((size_t)V * T + 1);         // row are read by one thread while the next range's thread already writes cursors)
+    int max_tile_msgs = 0;
+    row_ptr[0] = 0;
+    if (vptr) vptr[0] = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nth) if (nth > 1) reduction(max : max_tile_msgs)
+#endif
+    for (int k = 0; k < nth; ++k) {
+        int run = (int)part_msgs[k];
+        for (int i = tb[k]; i < tb[k + 1]; ++i) {
             unsigned mask = 0;
             const int tile_first = run;
-            for (size_t k = (size_t)tile_start[i] * T, kend = (size_t)tile_start[i + 1] * T; k < kend; k += T)
+            for (size_t r = (size_t)tile_start[i] * T, rend = (size_t)tile_start[i + 1] * T; r < rend; r += T)
                 for (int t = 0; t < T; ++t) {
-                    const int c = counts[k + t + 1];
-                    counts[k + t] = run;
+                    const int c = counts[r + t + 1];
+                    cursor[r + t] = run;
                     run += c;
-                    row_ptr[k + t + 1] = run;
+                    row_ptr[r + t + 1] = run;
                     mask |= (unsigned)(c > 0) << t;
                 }
             h_mask[i] = mask;
-            e->max_tile_msgs = std::max(e->max_tile_msgs, run - tile_first);
+            max_tile_msgs = std::max(max_tile_msgs, run - tile_first);
+            h_tiles[i] = tile_start[i];
         }
-        int* pair = e->stream ? (int*)(base + e->off_pair) : nullptr;   // streaming plan: (target, type) -> its one source / -2 "several"
-        if (pair) {
-            const size_t np = (size_t)std::max(ntiles, 1) * ts::TILE_M * T;
-            for (size_t k = 0; k < np; ++k) pair[k] = -1;
-        }
-        int m = 0;
+        if (k == nth - 1) h_tiles[ntiles] = tile_start[ntiles];
+    }
+    e->max_tile_msgs = max_tile_msgs;
+    lap("row sweep", t_lap);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nth) if (nth > 1)
+#endif
+    for (int k = 0; k < nth; ++k) {
+        const int v0 = tile_start[tb[k]], v1 = tile_start[tb[k + 1]];
         for (int t = 0; t < T; ++t) {
             const int32_t* a = adj[t];
-            for (int i = 0; i < num_edges[t]; ++i, ++m) {
-                const size_t key = (size_t)a[2 * i + 1] * T + t;
-                const int slot = counts[key]++;
-                csr_src[slot] = a[2 * i];
-                csr_msg[slot] = m;
-                if (pair) pair[key] = (slot == row_ptr[key]) ? a[2 * i] : -2;   // first message of the row: its source; any later one: "several"
+            const int ne = num_edges[t];
+            const int mb = (int)type_base[t];
+            if (nth == 1) {
+                for (int i = 0; i < ne; ++i) {
+                    const int slot = cursor[(size_t)a[2 * i + 1] * T + t]++;
+                    csr_src[slot] = a[2 * i];
+                    csr_msg[slot] = mb + i;
+                }
+            } else {
+                int dummy_cursor = 0, dummy_src = 0, dummy_msg = 0;   // see pass 1: select, do not branch
+                int* const cur = cursor.data();
+                const unsigned span = (unsigned)(v1 - v0);
+                for (int i = 0; i < ne; ++i) {
+                    const int d = a[2 * i + 1];
+                    const bool mine = (unsigned)(d - v0) < span;
+                    int* pc = mine ? cur + ((size_t)d * T + t) : &dummy_cursor;
+                    const int slot = *pc;
+                    *pc = slot + 1;
+                    *(mine ? csr_src + slot : &dummy_src) = a[2 * i];
+                    *(mine ? csr_msg + slot : &dummy_msg) = mb + i;
+                }
             }
         }
+        if (pair) {   // one sequential pass over the range's rows: no message -> -1, one -> its source, several -> virtual row
+            int vid = (int)part_nv[k], vm = (int)part_nvm[k];
+            for (int i = tb[k]; i < tb[k + 1]; ++i) {
+                tvp[i] = vid;
+                size_t r = (size_t)tile_start[i] * T;
+                const size_t rend = (size_t)tile_start[i + 1] * T, rpad = (size_t)(i + 1) * ts::TILE_M * T;
+                for (; r < rend; ++r) {
+                    const int b = row_ptr[r], cnt = row_ptr[r + 1] - b;
+                    if (cnt == 0) pair[r] = -1;
+                    else if (cnt == 1) pair[r] = csr_src[b];
+                    else {
+                        pair[r] = -(2 + vid);
+                        vinfo[8 * vid] = cnt;
+                        for (int m = 0; m < 7; ++m) vinfo[8 * vid + 1 + m] = m < cnt ? csr_src[b + m] : 0;
+                        for (int m = 0; m < cnt; ++m) vsrc[vm++] = csr_src[b + m];
+                        vptr[++vid] = vm;
+                    }
+                }
+                for (; r < rpad; ++r) pair[r] = -1;   // rows of the last tile beyond V
+            }
+            if (k == nth - 1) tvp[ntiles] = vid;
+        }
+        if (v1 > v0) memcpy(h_indeg + (size_t)v0 * T, indeg + (size_t)v0 * T, sizeof(float) * (size_t)(v1 - v0) * T);
+        for (int v = v0; v < v1; ++v) {
+            const float* row = indeg + (size_t)v * T;
+            float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
+            for (int t = 0; t < T; ++t) s += row[t];
+            h_denom[v] = s + 1e-7f;
+        }
+    }
+    if (ntiles == 0) {
+        h_tiles[0] = 0;
+        if (pair) { for (size_t r = 0; r < (size_t)ts::TILE_M * T; ++r) pair[r] = -1; tvp[0] = 0; }
     }
     lap("csr fill", t_lap);
-    if (e->stream) {
-        int* pair = (int*)(base + e->off_pair);
-        int* vptr = (int*)(base + e->off_vptr);
-        int* vsrc = (int*)(base + e->off_vsrc);
-        int* tvp = (int*)(base + e->off_tvp);
-        int* vinfo = (int*)(base + e->off_vinfo);
-        number_virtual_rows(ntiles, T, tile_start.data(), row_ptr, csr_src, pair, vptr, vsrc, tvp, vinfo);
-    }
     if (e->has_transpose) {   // messages keyed by (source, type): the scatter of the backward pass becomes a gather
         int* trow = (int*)(base + e->off_trow);
         int* ttgt = (int*)(base + e->off_ttgt);
@@ -997,14 +1159,6 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
                 if (tslot) tslot[j] = slot_of_msg[m];
             }
     }
-    if (V > 0) memcpy(h_indeg, indeg, sizeof(float) * (size_t)V * T);
-    for (int v = 0; v < V; ++v) {
-        const float* row = indeg + (size_t)v * T;
-        float s = 0.0f;  // tf.reduce_sum over the type axis in fp32 (sparse:207), then + SMALL_NUMBER (:209)
-        for (int t = 0; t < T; ++t) s += row[t];
-        h_denom[v] = s + 1e-7f;
-    }
-    for (int i = 0; i <= ntiles; ++i) h_tiles[i] = tile_start[i];
     lap("denom+masks+extra", t_lap);
     g->valid = true;
     return GGNN_OK;
@@ -1088,6 +1242,13 @@ int ggnn_prepared_graph_arrays(const ggnn_prepared_graph* g, int32_t* row_ptr, i
     if (tile_start) memcpy(tile_start, base + q.off_tiles, sizeof(int) * (size_t)(q.ntiles + 1));
     if (denom && V) memcpy(denom, base + q.off_denom, sizeof(float) * V);
     if (pair_src && q.stream) memcpy(pair_src, base + q.off_pair, sizeof(int) * (size_t)std::max(q.ntiles, 1) * ts::TILE_M * T);
+    return GGNN_OK;
+}
+
+int ggnn_prepared_graph_image(const ggnn_prepared_graph* g, void* dst, int64_t capacity) {
+    if (!g || !g->valid || !dst) return GGNN_ESTATE;
+    if (capacity < (int64_t)g->bytes) return GGNN_EINVAL;
+    memcpy(dst, g->image, g->bytes);
     return GGNN_OK;
 }
 

@@ -127,6 +127,13 @@ class PreparedGraph:
             out["pair_src"] = pair
         return out
 
+    def image(self) -> np.ndarray:
+        """The packed image, byte for byte what ``set_graph_prepared`` uploads."""
+        out = np.empty(self.info()["image_bytes"], np.uint8)
+        if self.lib.ggnn_prepared_graph_image(self._h, out.ctypes.data, out.nbytes) != 0:
+            raise GgnnError("the prepared graph is empty")
+        return out
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self.lib.ggnn_free_prepared_graph(self._h)

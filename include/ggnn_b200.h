@@ -140,6 +140,10 @@ int ggnn_prepared_graph_info(const ggnn_prepared_graph* g, int32_t* num_nodes, i
                              int32_t* is_streaming, char* plan_text, int32_t plan_text_capacity);
 int ggnn_prepared_graph_arrays(const ggnn_prepared_graph* g, int32_t* row_ptr, int32_t* src, int32_t* msg, int32_t* tile_start, float* denom,
                                int32_t* pair_src);
+/* The whole packed image (image_bytes of ggnn_prepared_graph_info) -- exactly the bytes ggnn_set_graph_prepared uploads.  The builder
+ * splits its passes over host threads by target ranges (GGNN_HOST_THREADS overrides the count); the tests require identical bytes for
+ * every thread count. */
+int ggnn_prepared_graph_image(const ggnn_prepared_graph* g, void* dst, int64_t capacity);
 
 /* Dense wire format (dense:214-224): adjacency_matrix [b, T, v, v] float32 HOST pointer with
  * A[g, t, dest, src] (dense:30-36).  Rows are the b*v padded nodes. */

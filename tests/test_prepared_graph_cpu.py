@@ -147,3 +147,27 @@ def test_errors_are_reported_like_the_direct_call():
         PreparedGraph.host_only(dict(p, graph_rnn_cell="lstm"), 4, adj, indeg)
     empty = PreparedGraph.host_only(p, 4, [np.zeros((0, 2), np.int32)] * 4, np.zeros((0, 4), np.float32))
     assert empty.info()["num_nodes"] == 0 and empty.info()["num_tiles"] == 0
+
+
+@pytest.mark.parametrize("name,D,precision,make", [
+    ("random_graph_streaming", 100, "bf16x3", lambda: _one_big_graph(6000, 4, 9000, 31)),        # many virtual rows (pairs with several messages)
+    ("molecules_tile_local", 100, "bf16x3", lambda: _molecules(700, 4, 32)),
+    ("molecules_streaming_8_types", 256, "bf16x3", lambda: _molecules(400, 8, 33)),
+    ("molecules_fp32", 64, "fp32", lambda: _molecules(500, 4, 34)),
+], ids=lambda x: x if isinstance(x, str) else None)
+def test_image_is_identical_for_every_host_thread_count(monkeypatch, name, D, precision, make):
+    """The builder splits every pass over host threads by target ranges (each thread walks the whole edge list in the reference's order and
+    writes only its own rows): the packed image -- CSR, tile plan, masks, streaming tables, source-keyed CSR of the backward pass -- must
+    not depend on the thread count, down to the last byte."""
+    adj, indeg = make()
+    p = dict(GRU, hidden_size=D)
+    ref = None
+    for nth in (1, 2, 3, 5, 8):
+        monkeypatch.setenv("GGNN_HOST_THREADS", str(nth))
+        g = PreparedGraph.host_only(p, len(adj), adj, indeg, precision=precision, save_for_backward=True)
+        img, info = g.image(), g.info()
+        if ref is None:
+            ref, ref_info = img, info
+        else:
+            assert info == ref_info
+            assert np.array_equal(img, ref), "image differs at %d host threads (first byte %d)" % (nth, int(np.argmax(img != ref)))
