@@ -131,3 +131,53 @@ def test_stream_gather_tables_against_numpy(V, T, M, seed):
     multi_keys = keys[cnts >= 2]
     for i in range(ntiles + 1):
         assert tvp[i] == int(np.sum(multi_keys < min(i * 128, V) * T))
+
+
+@settings(max_examples=120, deadline=None)
+@given(multigraphs(), st.sampled_from([("fp32", 64), ("bf16x3", 100), ("bf16x3", 256)]), st.sampled_from([1, 2, 3, 7]), st.booleans())
+def test_prepared_graph_image_on_random_multigraphs(g, prec_d, threads, save):
+    """What the engine uploads for a batch (ggnn_host_prepare_graph_sparse = the host half of ggnn_set_graph_sparse), on multigraphs with
+    self-loops, duplicate edges, empty types and isolated nodes, at any builder thread count: CSR == NumPy's stable sort by target in the
+    reference's message order (bit for bit), tiles == ggnn_host_tile_plan, and the streaming gather table == its definition."""
+    import os
+    from gated_graph_neural_network_samples_b200.engine import PreparedGraph
+    V, adjs = g
+    precision, D = prec_d
+    T = len(adjs)
+    indeg = np.zeros((V, T), np.float32)
+    for t, a in enumerate(adjs):
+        np.add.at(indeg[:, t], a[:, 1], 1.0)
+    p = {"hidden_size": D, "layer_timesteps": [1], "residual_connections": {}, "use_edge_bias": False, "use_edge_msg_avg_aggregation": True,
+         "graph_rnn_cell": "GRU", "graph_rnn_activation": "tanh"}
+    old = os.environ.get("GGNN_HOST_THREADS")
+    os.environ["GGNN_HOST_THREADS"] = str(threads)
+    try:
+        pg = PreparedGraph.host_only(p, T, adjs, indeg, precision=precision, save_for_backward=save)
+    finally:
+        if old is None:
+            os.environ.pop("GGNN_HOST_THREADS", None)
+        else:
+            os.environ["GGNN_HOST_THREADS"] = old
+    info, arr = pg.info(), pg.arrays(T)
+    M = sum(a.shape[0] for a in adjs)
+    ref_ptr, ref_src, ref_typ, ref_order = O.stable_target_csr(adjs, V)
+    assert info["num_messages"] == M
+    assert np.array_equal(arr["row_ptr"][::T], ref_ptr) and np.array_equal(arr["src"], ref_src) and np.array_equal(arr["msg"], ref_order)
+    assert np.array_equal(np.repeat(np.tile(np.arange(T, dtype=np.int32), V), np.diff(arr["row_ptr"])), ref_typ)
+    lib = _lib.load()
+    adjs_c, ptrs, counts = _ptrs(adjs)
+    ts, n, text = np.empty(V + 2, np.int32), C.c_int32(), C.create_string_buffer(512)
+    assert lib.ggnn_host_tile_plan(D, T, {"fp32": 0, "bf16x3": 1}[precision], 148, V, ptrs, counts, ts.ctypes.data, V + 2, C.byref(n), text, 512) == 0
+    assert np.array_equal(arr["tile_start"], ts[:n.value + 1]) and info["plan"] == text.value.decode()
+    assert np.array_equal(arr["denom"], (indeg.sum(axis=1, dtype=np.float32) + np.float32(1e-7)).astype(np.float32)) or T > 2   # fp32 sum order: checked exactly below
+    den = np.zeros(V, np.float32)
+    for t in range(T):
+        den = (den + indeg[:, t]).astype(np.float32)
+    assert np.array_equal(arr["denom"], den + np.float32(1e-7))
+    if info["streaming"]:
+        cnt = np.diff(arr["row_ptr"])
+        pair = arr["pair_src"][:V * T]
+        assert np.all(pair[cnt == 0] == -1) and np.array_equal(pair[cnt == 1], arr["src"][arr["row_ptr"][:-1][cnt == 1]])
+        multi = np.flatnonzero(cnt >= 2)
+        assert np.array_equal(pair[multi], -(2 + np.arange(multi.size)))          # virtual rows numbered in (target, type) order
+        assert np.all(arr["pair_src"][V * T:] == -1)
