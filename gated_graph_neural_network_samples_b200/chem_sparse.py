@@ -116,7 +116,13 @@ class SparseGGNNChemModel(ChemModel):
             else:                    # BasicRNNCell
                 cell = {'cand_kernel': var(glorot_init([din + h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
             self.gnn_weights.rnn_cells.append(cell)
-        self.engine = PropagationEngine(self.params, T, device=self.device.index or 0, precision=self.precision)
+        # The kernels move node-state rows as 16-byte vectors, so the engine wants hidden sizes that are multiples of 4; the reference accepts
+        # any.  Other sizes run zero-padded: padded state columns, weight rows/columns and biases are zero, which keeps the padded units at
+        # exactly 0 through every cell (c = act(0) = 0, h' = u*0 + (1-u)*0) and out of every real unit's sums -- hook 2 pads, the engine
+        # works at the padded width, the result is sliced back.  Variables keep the reference's shapes.
+        self._padded_hidden = (h_dim + 3) // 4 * 4
+        self.engine = PropagationEngine(dict(self.params, hidden_size=self._padded_hidden), T, device=self.device.index or 0,
+                                        precision=self.precision)
         self._propagation = _propagation_function()
         self._readout = gated_readout_function()
 
@@ -185,7 +191,35 @@ class SparseGGNNChemModel(ChemModel):
                 lay[k] = len(flat); flat.append(v)
             layout.append(lay)
         h0 = self.initial_node_representation_tensor()
+        DP = getattr(self, '_padded_hidden', D)
+        if DP != D:
+            flat = [self._pad_hidden(k, flat[i], D, DP) for lay in layout for k, i in lay.items()]   # layout indices are consecutive in this order
+            h0 = torch.nn.functional.pad(h0, (0, DP - D))
+            return self._propagation.apply(self.engine, layout, h0.contiguous(), *flat)[:, :D]
         return self._propagation.apply(self.engine, layout, h0, *flat)                           # [V, D]
+
+    @staticmethod
+    def _pad_hidden(key, w, D, DP):
+        """Zero-pad one trainable from hidden size D to DP (a multiple of 4): every D-wide block of rows / columns becomes DP wide."""
+        import torch
+        pad = torch.nn.functional.pad
+        if key == 'edge_weights':                    # [T, D, D]
+            return pad(w, (0, DP - D, 0, DP - D)).contiguous()
+        if key in ('edge_biases',):                  # [T, D]
+            return pad(w, (0, DP - D)).contiguous()
+        if key == 'edge_type_attention_weights':     # [T]
+            return w
+        if key in ('cand_bias', 'cand_hidden_bias'):  # [D]
+            return pad(w, (0, DP - D)).contiguous()
+        if key == 'gate_bias':                       # [2D] = [r | u]
+            return pad(w.view(2, D), (0, DP - D)).reshape(2 * DP).contiguous()
+        if key == 'cand_kernel':                     # [nseg*D, D]: row blocks [res.. | agg | h]
+            nseg = w.shape[0] // D
+            return pad(w.view(nseg, D, D), (0, DP - D, 0, DP - D)).reshape(nseg * DP, DP).contiguous()
+        if key == 'gate_kernel':                     # [nseg*D, 2D]: row blocks as above, column blocks [r | u]
+            nseg = w.shape[0] // D
+            return pad(w.view(nseg, D, 2, D), (0, DP - D, 0, 0, 0, DP - D)).reshape(nseg * DP, 2 * DP).contiguous()
+        raise KeyError(key)
 
     # ------------------------------------------------------------------ readout (sparse:220-231), SURVEY 8f-1
     def gated_regression(self, last_h, regression_gate, regression_transform):
@@ -193,7 +227,7 @@ class SparseGGNNChemModel(ChemModel):
         h0 = self.initial_node_representation_tensor()
         ag = regression_gate.affine() if hasattr(regression_gate, 'affine') else None
         at = regression_transform.affine() if hasattr(regression_transform, 'affine') else None
-        if ag is not None and at is not None and last_h.is_cuda:
+        if ag is not None and at is not None and last_h.is_cuda and getattr(self, '_padded_hidden', last_h.shape[-1]) == last_h.shape[-1]:
             # the fused kernel: both dot products, sigmoid, product and the per-graph segment sum in one launch
             self.engine.readout_set_graphs(int(self.feed[self.placeholders['num_graphs']]),
                                            graph_nodes_list=self.feed[self.placeholders['graph_nodes_list']])

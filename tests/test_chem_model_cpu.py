@@ -220,3 +220,42 @@ def test_a_graph_larger_than_the_node_budget_raises_instead_of_hanging(tmp_path,
     m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, batch_size=5))   # every molecule has more than 5 nodes (sparse:297 loops forever)
     with pytest.raises(Exception, match="does not fit"):
         m.run_epoch("valid", m.valid_data, False)
+
+
+@pytest.mark.parametrize("cfg", [{"hidden_size": 10}, {"hidden_size": 7, "graph_rnn_cell": "RNN", "graph_rnn_activation": "ReLU", "use_edge_bias": True},
+                                 {"hidden_size": 9, "graph_rnn_cell": "CudnnCompatibleGRUCell"}, {"hidden_size": 6, "use_propagation_attention": True}])
+def test_hidden_sizes_that_are_not_multiples_of_4_run_zero_padded(tmp_path, stand_in, cfg):
+    """The reference accepts any hidden size; the engine wants multiples of 4 (16-byte row vectors).  The plug-in zero-pads states and
+    weights at the engine boundary and slices the result: padded units stay exactly 0 through every cell, so the real units see the same
+    sums.  Checked here through the stand-in engine (which receives the PADDED problem) against the oracle on the UNPADDED one."""
+    import torch
+    mols = synthetic.make_molecules(64, seed=3)
+    m = chem_sparse.SparseGGNNChemModel(_args(tmp_path, mols, edge_weight_dropout_keep_prob=1.0, graph_state_dropout_keep_prob=1.0, **cfg))
+    D = cfg["hidden_size"]
+    assert m._padded_hidden == (D + 3) // 4 * 4 != D and m.engine.D == m._padded_hidden
+    feed = next(iter(m.make_minibatch_iterator(m.valid_data, False)))
+    m.feed = feed
+    with torch.no_grad():
+        got = m.compute_final_node_representations().numpy()
+    assert got.shape[1] == D
+    ren = {"cand_kernel": "rnn_kernel", "cand_bias": "rnn_bias"} if cfg.get("graph_rnn_cell") == "RNN" else {}
+    weights = []
+    for l in range(len(m.params["layer_timesteps"])):
+        w = {"edge_weights": m.gnn_weights.edge_weights[l].detach().numpy().reshape(m.num_edge_types, D, D)}
+        if m.params["use_edge_bias"]:
+            w["edge_biases"] = m.gnn_weights.edge_biases[l].detach().numpy()
+        if m.params["use_propagation_attention"]:
+            w["edge_type_attention_weights"] = m.gnn_weights.edge_type_attention_weights[l].detach().numpy()
+        cell = {k: v.detach().numpy() for k, v in m.gnn_weights.rnn_cells[l].items()}
+        if "cand_input_kernel" in cell:
+            cell["cand_kernel"] = np.concatenate([cell.pop("cand_input_kernel"), cell.pop("cand_hidden_kernel")], axis=0)
+        w.update({ren.get(k, k): v for k, v in cell.items()})
+        weights.append(w)
+    ref = O.sparse_propagation_np(feed["initial_node_representation"], [feed[k] for k in m.placeholders["adjacency_lists"]],
+                                  feed["num_incoming_edges_per_type"], weights, m.params, dtype=np.float64)
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
+    l0 = m.run_epoch("valid0", m.valid_data, False)[0]           # and it trains: gradients flow back through pad / slice to the D-wide variables
+    for ep in range(4):
+        m.run_epoch("train%d" % ep, m.train_data, True)
+    assert m.run_epoch("valid1", m.valid_data, False)[0] < l0
+    assert tuple(m.gnn_weights.edge_weights[0].shape) == (m.num_edge_types * D, D)
