@@ -41,7 +41,10 @@ class DenseGGNNChemModel(ChemModel):
             self.weights['edge_biases'] = var(np.zeros([T, 1, h_dim]))                           # dense:86
         self.weights['node_gru'] = {'gate_kernel': var(glorot_init([2 * h_dim, 2 * h_dim])), 'gate_bias': var(np.ones(2 * h_dim)),
                                     'cand_kernel': var(glorot_init([2 * h_dim, h_dim])), 'cand_bias': var(np.zeros(h_dim))}
-        self.engine = PropagationEngine(dense_engine_params(self.params), T, device=self.device.index or 0, precision=self.precision)
+        # hidden sizes that are not multiples of 4 run zero-padded at the engine boundary (see SparseGGNNChemModel.prepare_specific_graph_model)
+        self._padded_hidden = (h_dim + 3) // 4 * 4
+        self.engine = PropagationEngine(dense_engine_params(dict(self.params, hidden_size=self._padded_hidden)), T,
+                                        device=self.device.index or 0, precision=self.precision)
         self._propagation = _propagation_function()
         self._readout = gated_readout_function()
 
@@ -80,6 +83,12 @@ class DenseGGNNChemModel(ChemModel):
         for k, t in self.weights['node_gru'].items():
             lay[k] = len(flat); flat.append(t)
         h0 = self.initial_node_representation_tensor().reshape(b * v, D)                         # dense:97
+        DP = getattr(self, '_padded_hidden', D)
+        if DP != D:
+            from .chem_sparse import SparseGGNNChemModel
+            flat = [SparseGGNNChemModel._pad_hidden(k, flat[i], D, DP) for k, i in lay.items()]
+            h0 = torch.nn.functional.pad(h0, (0, DP - D)).contiguous()
+            return self._propagation.apply(self.engine, [lay], h0, *flat)[:, :D].reshape(b, v, D)
         out = self._propagation.apply(self.engine, [lay], h0, *flat)
         return out.reshape(b, v, D)                                                              # dense:116
 
@@ -89,7 +98,7 @@ class DenseGGNNChemModel(ChemModel):
         h0 = self.initial_node_representation_tensor()
         ag = regression_gate.affine() if hasattr(regression_gate, 'affine') else None
         at = regression_transform.affine() if hasattr(regression_transform, 'affine') else None
-        if ag is not None and at is not None and last_h.is_cuda:   # fused kernel: masked per-graph sum included
+        if ag is not None and at is not None and last_h.is_cuda and getattr(self, '_padded_hidden', D) == D:   # fused kernel: masked per-graph sum included
             b, v = last_h.shape[0], last_h.shape[1]
             self.engine.readout_set_graphs(b, nodes_per_graph=v, node_mask=self.feed[self.placeholders['node_mask']])
             self.output = self._readout.apply(self.engine, last_h.reshape(b * v, D), h0.reshape(b * v, D), ag[0], ag[1], at[0], at[1])

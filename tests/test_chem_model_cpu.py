@@ -259,3 +259,25 @@ def test_hidden_sizes_that_are_not_multiples_of_4_run_zero_padded(tmp_path, stan
         m.run_epoch("train%d" % ep, m.train_data, True)
     assert m.run_epoch("valid1", m.valid_data, False)[0] < l0
     assert tuple(m.gnn_weights.edge_weights[0].shape) == (m.num_edge_types * D, D)
+
+
+def test_dense_hidden_size_that_is_not_a_multiple_of_4_runs_zero_padded(tmp_path, stand_in):
+    import torch
+    mols = synthetic.make_molecules(48, seed=4)
+    args = {"--log_dir": str(tmp_path), "--device": "cpu", "--train_data": mols[:32], "--valid_data": mols[32:],
+            "--config": {"hidden_size": 10, "batch_size": 4, "num_timesteps": 2, "learning_rate": 0.01, "num_epochs": 1}}
+    m = chem_dense.DenseGGNNChemModel(args)
+    assert m._padded_hidden == 12 and m.engine.D == 12
+    feed = next(iter(m.make_minibatch_iterator(m.valid_data, False)))
+    m.feed = feed
+    with torch.no_grad():
+        got = m.compute_final_node_representations().numpy()
+    w = {"edge_weights": m.weights["edge_weights"].detach().numpy(), "edge_biases": m.weights["edge_biases"].detach().numpy()}
+    w.update({k: v.detach().numpy() for k, v in m.weights["node_gru"].items()})
+    ref = O.dense_propagation_loops(feed["initial_node_representation"], feed["adjacency_matrix"], w, {"num_timesteps": 2, "use_edge_bias": True})
+    assert got.shape == ref.shape and got.shape[-1] == 10
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
+    l0 = m.run_epoch("valid0", m.valid_data, False)[0]
+    for ep in range(4):
+        m.run_epoch("train%d" % ep, m.train_data, True)
+    assert m.run_epoch("valid1", m.valid_data, False)[0] < l0
