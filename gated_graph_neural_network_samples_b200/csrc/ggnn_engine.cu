@@ -1321,16 +1321,19 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
             // graphs are split into contiguous ranges over a few OpenMP threads; every thread appends to its own per-type lists (order inside
             // a range: graph, target row, source column) and the ranges are concatenated in order -- the result is the single-thread list.
             indeg.assign((size_t)std::max(V, 1) * T, 0.0f);
-            int nthreads = 1;
+            int nthreads = 1;   // graph ranges scanned concurrently
+            int team = 1;       // OpenMP team size: ONE size per process (the sparse builder's), used only if its region entry is cheap here
 #ifdef _OPENMP
-            nthreads = std::max(1, std::min(std::min(8, omp_get_max_threads()), b / 8));
-            if (const char* nt = getenv("GGNN_HOST_THREADS")) nthreads = std::max(1, std::min(atoi(nt), std::max(b, 1)));
+            team = b >= 16 ? std::min(8, omp_get_max_threads()) : 1;
+            if (team > 1 && !host_team_is_fast(team)) team = 1;
+            nthreads = std::max(1, std::min(team, b / 8));
+            if (const char* nt = getenv("GGNN_HOST_THREADS")) { nthreads = std::max(1, std::min(atoi(nt), std::max(b, 1))); team = nthreads; }
 #endif
             std::vector<std::vector<std::vector<int32_t>>> part(nthreads, std::vector<std::vector<int32_t>>(T));
             std::vector<int> bad(nthreads, 0);
             const int chunk = (b + nthreads - 1) / std::max(nthreads, 1);
 #ifdef _OPENMP
-#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+#pragma omp parallel for schedule(static, 1) num_threads(team) if (team > 1)
 #endif
             for (int k = 0; k < nthreads; ++k) {
                 std::vector<std::vector<int32_t>>& mine = part[k];

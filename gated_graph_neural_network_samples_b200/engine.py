@@ -227,13 +227,18 @@ class PropagationEngine:
         self.V = V
         self._graph_keepalive = (adjs, indeg)
 
-    def prepare_graph_sparse(self, adjacency_lists, num_incoming_edges_per_type, save_for_backward: Optional[bool] = None,
-                             reuse: Optional["PreparedGraph"] = None) -> "PreparedGraph":
+    def marshal_sparse(self, adjacency_lists, num_incoming_edges_per_type):
+        """The ctypes view of one batch's graph feeds (contiguous int32 / float32 arrays, pointer and count tables), reusable across calls:
+        pass it as ``marshalled=`` to keep a producer thread's time under the GIL to a few microseconds per batch."""
+        return self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+
+    def prepare_graph_sparse(self, adjacency_lists=None, num_incoming_edges_per_type=None, save_for_backward: Optional[bool] = None,
+                             reuse: Optional["PreparedGraph"] = None, marshalled=None) -> "PreparedGraph":
         """The HOST half of ``set_graph_sparse`` (validation, CSR, tile plan, one pinned image) -- may run in a producer thread while the
         engine's stream works on the previous batch (ThreadedIterator, chem_tensorflow.py:225).  ``save_for_backward``: whether the batch
         will be trained on (None = the engine's current flag).  ``reuse``: rebuild a prepared graph in place (its pinned image is kept; the
         call waits for its previous upload first)."""
-        adjs, indeg, ptrs, counts = self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
+        adjs, indeg, ptrs, counts = marshalled if marshalled is not None else self._sparse_args(adjacency_lists, num_incoming_edges_per_type)
         g = reuse if reuse is not None else PreparedGraph(self.lib)
         h = C.c_void_p(g._h.value)
         rc = self.lib.ggnn_prepare_graph_sparse(self._h, -1 if save_for_backward is None else int(bool(save_for_backward)), indeg.shape[0], ptrs,
