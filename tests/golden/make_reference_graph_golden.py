@@ -216,6 +216,42 @@ def dense_case(ref_dense, ref_utils, mols):
     print("dense b,v =", h0.shape[:2], "final max %.3f readout[:3] %s" % (np.abs(out_final).max(), np.round(out_ro[:3], 4)))
 
 
+def dense_case_wide(ref_dense, mols):
+    """BASELINE configs[2] width (hidden 100, 4 timesteps, edge bias) through the reference's dense graph code; the float32-rounded
+    weights the reference code created are committed, h0 is exactly representable in fp32."""
+    cfg = {"hidden_size": 100, "num_timesteps": 4, "use_edge_bias": True}
+    m = object.__new__(ref_dense.DenseGGNNChemModel)
+    m.params = {"task_ids": [0], "tie_fwd_bkwd": True, "task_sample_ratios": {}, "batch_size": 8, "out_layer_dropout_keep_prob": 1.0,
+                "graph_state_dropout_keep_prob": 1.0, "edge_weight_dropout_keep_prob": 1.0, "use_graph": True}
+    m.params.update(cfg)
+    m.num_edge_types, m.annotation_size = 4, len(mols[0]["node_features"][0])
+    np.random.seed(13)
+    tf_shim.CELL_RNG.seed(778)
+    ro_w = build_model(m)                                         # make_model -> dense:68-91, 93-117, 119-129, unmodified
+    f32 = lambda a: np.asarray(a, np.float64).astype(np.float32).astype(np.float64)
+    m.weights["edge_weights"].value = f32(m.weights["edge_weights"].value)
+    m.weights["edge_biases"].value = f32(np.random.RandomState(7).uniform(-0.1, 0.1, m.weights["edge_biases"].value.shape))
+    data = m.process_raw_graphs(mols, is_training_data=False)
+    feed = next(iter(m.make_minibatch_iterator(data, is_training=False)))
+    h0 = np.asarray(feed[m.placeholders["initial_node_representation"]], dtype=np.float64)
+    h0 = f32(h0 + np.random.RandomState(5).normal(0, 0.1, h0.shape))
+    feed[m.placeholders["initial_node_representation"]] = h0
+    evaluate_model(m, feed)                                       # first evaluation creates the cell's kernels
+    for k in list(m.weights["node_gru"].vars):
+        m.weights["node_gru"].vars[k] = f32(m.weights["node_gru"].vars[k])
+    out_final, out_ro, loss, acc = evaluate_model(m, feed)
+    out = {"params_json": np.asarray(json.dumps(cfg)), "h0": h0.astype(np.float32), "final": out_final, "readout": out_ro, "loss": np.float64(loss),
+           "accuracy": np.float64(acc), "adj": np.asarray(feed[m.placeholders["adjacency_matrix"]], np.float32),
+           "node_mask": np.asarray(feed[m.placeholders["node_mask"]], np.float32),
+           "w_edge_weights": m.weights["edge_weights"].value.astype(np.float32), "w_edge_biases": m.weights["edge_biases"].value.astype(np.float32)}
+    for k, v in m.weights["node_gru"].vars.items():
+        out["w_" + k] = np.asarray(v, np.float32)
+    for k, v in ro_w.items():
+        out["ro_" + k] = v.value
+    np.savez_compressed(os.path.join(HERE, "refgraph_dense_cfg3_shape.npz"), **out)
+    print("dense cfg3 shape b,v =", h0.shape[:2], "final max %.3f readout[:3] %s" % (np.abs(out_final).max(), np.round(out_ro[:3], 4)))
+
+
 def main():
     ref_sparse, ref_dense, ref_utils = import_reference()
     mols = synthetic.make_molecules(12, seed=321)
@@ -246,6 +282,7 @@ def main():
                                                 "use_edge_bias": False, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "GRU",
                                                 "graph_rnn_activation": "tanh"},
                      synthetic.make_molecules(12, seed=78, num_bond_types=8), T=8, store_weights=False)
+    dense_case_wide(ref_dense, synthetic.make_molecules(32, seed=125))
     print("reference-graph fixtures written to", HERE)
 
 

@@ -38,9 +38,10 @@ def test_sparse_propagation_and_readout_match_the_reference_graph_code(golden_di
     assert err < 1e-4
 
 
+@pytest.mark.parametrize("fixture", ["refgraph_dense.npz", "refgraph_dense_cfg3_shape.npz"])   # hidden 12; BASELINE configs[2] width (hidden 100)
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
-def test_dense_propagation_matches_the_reference_graph_code(golden_dir, precision):
-    z = np.load(os.path.join(golden_dir, "refgraph_dense.npz"))
+def test_dense_propagation_matches_the_reference_graph_code(golden_dir, precision, fixture):
+    z = np.load(os.path.join(golden_dir, fixture))
     p = json.loads(str(z["params_json"]))
     w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
     got = U.engine_dense(p, 4, w, z["adj"].astype(np.float32), z["h0"].astype(np.float32), precision=precision)

@@ -247,14 +247,15 @@ def test_oracle_reproduces_the_reference_graph_code_at_baseline_widths(golden_di
     np.testing.assert_allclose(ro, z["readout"], rtol=1e-10, atol=1e-12)
 
 
-def test_oracle_reproduces_the_reference_graph_code_dense(golden_dir):
+@pytest.mark.parametrize("fixture", ["refgraph_dense.npz", "refgraph_dense_cfg3_shape.npz"])   # hidden 12; BASELINE configs[2] width (hidden 100)
+def test_oracle_reproduces_the_reference_graph_code_dense(golden_dir, fixture):
     import torch
-    z = np.load(os.path.join(golden_dir, "refgraph_dense.npz"))
+    z = np.load(os.path.join(golden_dir, fixture))
     p = json.loads(str(z["params_json"]))
     w = {k[2:]: z[k] for k in z.files if k.startswith("w_")}
     for got in (O.dense_propagation_loops(z["h0"], z["adj"], w, p), O.dense_propagation_torch(z["h0"], z["adj"], w, p, dtype=torch.float64).numpy(),
                 CO.dense_propagation_c(z["h0"], z["adj"], w, p)):
-        np.testing.assert_allclose(got, z["final"], rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(got, z["final"], rtol=1e-10, atol=1e-12)
     ro = O.gated_regression_torch(z["final"], z["h0"], z["ro_w_gate"], z["ro_b_gate"], z["ro_w_trans"], z["ro_b_trans"],
                                   node_mask=z["node_mask"], dtype=torch.float64).numpy()
-    np.testing.assert_allclose(ro, z["readout"], rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(ro, z["readout"], rtol=1e-10, atol=1e-12)
