@@ -48,6 +48,8 @@ SYMBOLS = {
     "ggnn_prepared_graph_error": (C.c_char_p, [C.c_void_p]),
     "ggnn_host_prepare_graph_sparse": (C.c_int, [C.POINTER(GgnnConfig), C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), c_i32p, C.c_void_p,
                                                  C.POINTER(C.c_void_p)]),
+    "ggnn_prepare_graph_dense": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ggnn_host_prepare_graph_dense": (C.c_int, [C.POINTER(GgnnConfig), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ggnn_prepared_graph_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64),
                                            C.POINTER(C.c_int32), C.c_char_p, C.c_int32]),
     "ggnn_prepared_graph_arrays": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6),

@@ -1317,6 +1317,135 @@ int ggnn_set_graph_sparse(ggnn_engine* e, int32_t V, const int32_t* const* adj, 
 }
 
 
+// The reference only ever feeds 0/1 adjacency (dense:30-36).  A binary adjacency IS an edge list: A_t.(h W_t + b_t) =
+// (sum of h over the row's sources) W_t + rowsum(A_t) b_t, which is exactly the sparse path with in-degree = row sums.  One scan of
+// [b, T, v, v] -> per-type (source, target) lists in the order (graph, target row, source column) and the row sums; false when an entry is
+// neither 0 nor 1 (a weighted matrix keeps the matrix walk).
+// The scan is a stream over b*T*v*v floats (4 MB at cfg3) of which ~99 % are zero: memory-bound on one core (~0.5 ms), so the
+// graphs are split into contiguous ranges over a few OpenMP threads; every thread appends to its own per-type lists (order inside
+// a range: graph, target row, source column) and the ranges are concatenated in order -- the result is the single-thread list.
+static bool scan_binary_dense(int T, int b, int v, const float* adjm, std::vector<std::vector<int32_t>>& lists, std::vector<float>& indeg) {
+    const int V = b * v;
+    bool binary = true;
+    lists.assign(T, std::vector<int32_t>());
+    {
+    indeg.assign((size_t)std::max(V, 1) * T, 0.0f);
+    int nthreads = 1;   // graph ranges scanned concurrently
+    int team = 1;       // OpenMP team size: ONE size per process (the sparse builder's), used only if its region entry is cheap here
+#ifdef _OPENMP
+    team = b >= 16 ? host_team_size() : 1;
+    if (team > 1 && !host_team_is_fast(team)) team = 1;
+    nthreads = std::max(1, std::min(team, b / 8));
+    if (const char* nt = getenv("GGNN_HOST_THREADS")) { nthreads = std::max(1, std::min(atoi(nt), std::max(b, 1))); team = nthreads; }
+#endif
+    std::vector<std::vector<std::vector<int32_t>>> part(nthreads, std::vector<std::vector<int32_t>>(T));
+    std::vector<int> bad(nthreads, 0);
+    const int chunk = (b + nthreads - 1) / std::max(nthreads, 1);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(team) if (team > 1)
+#endif
+    for (int k = 0; k < nthreads; ++k) {
+        std::vector<std::vector<int32_t>>& mine = part[k];
+        const int g0 = k * chunk, g1 = std::min(b, g0 + chunk);
+        for (int t = 0; t < T; ++t) mine[t].reserve((size_t)std::max(g1 - g0, 0) * v * 3);
+        bool ok = true;
+        for (int g = g0; g < g1 && ok; ++g)
+            for (int t = 0; t < T && ok; ++t) {
+                const float* m = adjm + ((size_t)g * T + t) * v * v;
+                std::vector<int32_t>& lst = mine[t];
+                for (int i = 0; i < v && ok; ++i) {
+                    const float* row = m + (size_t)i * v;
+                    int cnt = 0;
+                    auto visit = [&](int j) {
+                        const float a = row[j];
+                        if (a != 0.0f) {
+                            if (a != 1.0f) { ok = false; return; }
+                            lst.push_back(g * v + j);   // source
+                            lst.push_back(g * v + i);   // target
+                            ++cnt;
+                        }
+                    };
+                    int j = 0;
+                    for (; j + 4 <= v && ok; j += 4) {   // test 16 bytes at a time
+                        uint64_t w0, w1;
+                        memcpy(&w0, row + j, 8); memcpy(&w1, row + j + 2, 8);
+                        if ((w0 | w1) == 0) continue;
+                        visit(j); visit(j + 1); visit(j + 2); visit(j + 3);
+                    }
+                    for (; j < v && ok; ++j) visit(j);
+                    indeg[((size_t)g * v + i) * T + t] = (float)cnt;
+                }
+            }
+        bad[k] = ok ? 0 : 1;
+    }
+    for (int k = 0; k < nthreads; ++k) binary = binary && !bad[k];
+    if (binary)
+        for (int t = 0; t < T; ++t) {
+            size_t total = 0;
+            for (int k = 0; k < nthreads; ++k) total += part[k][t].size();
+            lists[t].resize(total);
+            size_t off = 0;
+            for (int k = 0; k < nthreads; ++k) {
+                if (!part[k][t].empty()) memcpy(lists[t].data() + off, part[k][t].data(), part[k][t].size() * sizeof(int32_t));
+                off += part[k][t].size();
+            }
+        }
+    }
+    return binary;
+}
+
+// Host half of ggnn_set_graph_dense for a 0/1 adjacency: scan -> edge lists -> the sparse builder.  *not_binary tells a weighted matrix
+// (GGNN_EUNSUPPORTED) from a real failure.
+static int prepare_dense_into(ggnn_prepared_graph* g, int32_t b, int32_t v, const float* adjm, bool* not_binary) {
+    ggnn_engine* q = &g->plan;
+    g->valid = false;
+    *not_binary = false;
+    if (b < 0 || v <= 0 || (!adjm && b > 0)) return q->fail(GGNN_EINVAL, "null/negative argument");
+    if (q->use_att) return q->fail(GGNN_EUNSUPPORTED, "propagation attention exists only in the sparse model (sparse:170-196)");
+    const int T = q->T;
+    if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return q->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
+    std::vector<std::vector<int32_t>> lists;
+    std::vector<float> indeg;
+    if (getenv("GGNN_DENSE_KEEP_MATRIX") || !scan_binary_dense(T, b, v, adjm, lists, indeg)) {
+        *not_binary = true;
+        return q->fail(GGNN_EUNSUPPORTED, "the adjacency matrix is not 0/1: a weighted matrix is fed through ggnn_set_graph_dense (matrix walk)");
+    }
+    std::vector<const int32_t*> ptrs(T);
+    std::vector<int32_t> counts(T);
+    for (int t = 0; t < T; ++t) { ptrs[t] = lists[t].data(); counts[t] = (int32_t)(lists[t].size() / 2); }
+    int rc = build_sparse_image(g, b * v, ptrs.data(), counts.data(), indeg.data());
+    if (rc) return rc;
+    q->dense_v = v;
+    q->plan_text += " [binary dense adjacency -> CSR]";
+    return GGNN_OK;
+}
+
+int ggnn_prepare_graph_dense(const ggnn_engine* e, int32_t save_for_backward, int32_t b, int32_t v, const float* adjm, ggnn_prepared_graph** inout) {
+    if (!e || !inout) return GGNN_EINVAL;
+    ggnn_prepared_graph* g = *inout;
+    if (!g) { g = new ggnn_prepared_graph(); *inout = g; }
+    g->use_cuda = true;
+    copy_model_shape(&g->plan, e);
+    if (save_for_backward >= 0) g->plan.save = save_for_backward != 0;
+    if (cudaSetDevice(e->device) != cudaSuccess) return g->plan.fail(GGNN_ECUDA, "cudaSetDevice(%d) failed", e->device);
+    bool not_binary = false;
+    return prepare_dense_into(g, b, v, adjm, &not_binary);
+}
+
+int ggnn_host_prepare_graph_dense(const ggnn_config* cfg, int32_t num_sms, int32_t save_for_backward, int32_t b, int32_t v, const float* adjm,
+                                  ggnn_prepared_graph** inout) {
+    if (!cfg || !inout || num_sms <= 0) return GGNN_EINVAL;
+    ggnn_prepared_graph* g = *inout;
+    if (!g) { g = new ggnn_prepared_graph(); *inout = g; }
+    g->use_cuda = false;
+    g->valid = false;
+    if (int rc = init_model_shape(&g->plan, cfg, g->plan.err)) return rc;
+    g->plan.num_sms = num_sms; g->plan.max_smem = 227 * 1024;
+    g->plan.save = save_for_backward != 0;
+    bool not_binary = false;
+    return prepare_dense_into(g, b, v, adjm, &not_binary);
+}
+
 int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm, ggnn_stream_t stream) {
     if (!e) return GGNN_EINVAL;
     e->graph_set = false; e->saved_valid = false;
@@ -1326,86 +1455,15 @@ int ggnn_set_graph_dense(ggnn_engine* e, int32_t b, int32_t v, const float* adjm
     const int T = e->T;
     if ((int64_t)b * v > 0x7fffffff / std::max(T, 1)) return e->fail(GGNN_EUNSUPPORTED, "batch too large for int32 indexing");
     const int V = b * v;
-    {   // The reference only ever feeds 0/1 adjacency (dense:30-36).  A binary adjacency IS an edge list: A_t.(h W_t + b_t) =
-        // (sum of h over the row's sources) W_t + rowsum(A_t) b_t, which is exactly the sparse path with in-degree = row sums.
-        // Convert once on the host and use the CSR gather (deterministic source order j ascending) instead of the matrix walk.
-        bool binary = !getenv("GGNN_DENSE_KEEP_MATRIX");
-        std::vector<std::vector<int32_t>> lists(T);
-        std::vector<float> indeg;
-        if (binary) {
-            // The scan is a stream over b*T*v*v floats (4 MB at cfg3) of which ~99 % are zero: memory-bound on one core (~0.5 ms), so the
-            // graphs are split into contiguous ranges over a few OpenMP threads; every thread appends to its own per-type lists (order inside
-            // a range: graph, target row, source column) and the ranges are concatenated in order -- the result is the single-thread list.
-            indeg.assign((size_t)std::max(V, 1) * T, 0.0f);
-            int nthreads = 1;   // graph ranges scanned concurrently
-            int team = 1;       // OpenMP team size: ONE size per process (the sparse builder's), used only if its region entry is cheap here
-#ifdef _OPENMP
-            team = b >= 16 ? host_team_size() : 1;
-            if (team > 1 && !host_team_is_fast(team)) team = 1;
-            nthreads = std::max(1, std::min(team, b / 8));
-            if (const char* nt = getenv("GGNN_HOST_THREADS")) { nthreads = std::max(1, std::min(atoi(nt), std::max(b, 1))); team = nthreads; }
-#endif
-            std::vector<std::vector<std::vector<int32_t>>> part(nthreads, std::vector<std::vector<int32_t>>(T));
-            std::vector<int> bad(nthreads, 0);
-            const int chunk = (b + nthreads - 1) / std::max(nthreads, 1);
-#ifdef _OPENMP
-#pragma omp parallel for schedule(static, 1) num_threads(team) if (team > 1)
-#endif
-            for (int k = 0; k < nthreads; ++k) {
-                std::vector<std::vector<int32_t>>& mine = part[k];
-                const int g0 = k * chunk, g1 = std::min(b, g0 + chunk);
-                for (int t = 0; t < T; ++t) mine[t].reserve((size_t)std::max(g1 - g0, 0) * v * 3);
-                bool ok = true;
-                for (int g = g0; g < g1 && ok; ++g)
-                    for (int t = 0; t < T && ok; ++t) {
-                        const float* m = adjm + ((size_t)g * T + t) * v * v;
-                        std::vector<int32_t>& lst = mine[t];
-                        for (int i = 0; i < v && ok; ++i) {
-                            const float* row = m + (size_t)i * v;
-                            int cnt = 0;
-                            auto visit = [&](int j) {
-                                const float a = row[j];
-                                if (a != 0.0f) {
-                                    if (a != 1.0f) { ok = false; return; }
-                                    lst.push_back(g * v + j);   // source
-                                    lst.push_back(g * v + i);   // target
-                                    ++cnt;
-                                }
-                            };
-                            int j = 0;
-                            for (; j + 4 <= v && ok; j += 4) {   // test 16 bytes at a time
-                                uint64_t w0, w1;
-                                memcpy(&w0, row + j, 8); memcpy(&w1, row + j + 2, 8);
-                                if ((w0 | w1) == 0) continue;
-                                visit(j); visit(j + 1); visit(j + 2); visit(j + 3);
-                            }
-                            for (; j < v && ok; ++j) visit(j);
-                            indeg[((size_t)g * v + i) * T + t] = (float)cnt;
-                        }
-                    }
-                bad[k] = ok ? 0 : 1;
-            }
-            for (int k = 0; k < nthreads; ++k) binary = binary && !bad[k];
-            if (binary)
-                for (int t = 0; t < T; ++t) {
-                    size_t total = 0;
-                    for (int k = 0; k < nthreads; ++k) total += part[k][t].size();
-                    lists[t].resize(total);
-                    size_t off = 0;
-                    for (int k = 0; k < nthreads; ++k) {
-                        if (!part[k][t].empty()) memcpy(lists[t].data() + off, part[k][t].data(), part[k][t].size() * sizeof(int32_t));
-                        off += part[k][t].size();
-                    }
-                }
-        }
-        if (binary) {
-            std::vector<const int32_t*> ptrs(T);
-            std::vector<int32_t> counts(T);
-            for (int t = 0; t < T; ++t) { ptrs[t] = lists[t].data(); counts[t] = (int32_t)(lists[t].size() / 2); }
-            int rc = ggnn_set_graph_sparse(e, V, ptrs.data(), counts.data(), indeg.data(), stream);
-            if (rc == GGNN_OK) { e->dense_v = v; e->plan_text += " [binary dense adjacency -> CSR]"; }
-            return rc;
-        }
+    {   // a 0/1 adjacency (all the reference feeds) takes the CSR path: the same two halves as ggnn_set_graph_sparse, on the engine's own prepared graph
+        if (!e->own_prep) e->own_prep = new ggnn_prepared_graph();
+        ggnn_prepared_graph* g = e->own_prep;
+        g->use_cuda = true;
+        copy_model_shape(&g->plan, e);
+        bool not_binary = false;
+        const int rc = prepare_dense_into(g, b, v, adjm, &not_binary);
+        if (rc == GGNN_OK) return ggnn_set_graph_prepared(e, g, stream);
+        if (!not_binary) { e->err = g->plan.err; return rc; }
     }
     e->V = V; e->M = 0; e->gather_mode = GATHER_DENSE; e->dense_v = v;
     e->has_transpose = true;   // the dense adjacency is its own transpose source

@@ -105,6 +105,23 @@ class PreparedGraph:
         g.T = T
         return g
 
+    @classmethod
+    def host_only_dense(cls, params: dict, num_edge_types: int, adjacency_matrix, precision: str = "fp32", num_sms: int = 148,
+                        save_for_backward: bool = False, reuse: Optional["PreparedGraph"] = None) -> "PreparedGraph":
+        """``ggnn_host_prepare_graph_dense``: a 0/1 ``[b, T, v, v]`` adjacency through the CSR builder, no engine, no GPU."""
+        g = reuse if reuse is not None else cls()
+        cfg, keep = make_config(params, num_edge_types, 0, precision)
+        a = np.ascontiguousarray(np.asarray(adjacency_matrix, dtype=np.float32))
+        h = C.c_void_p(g._h.value)
+        rc = g.lib.ggnn_host_prepare_graph_dense(C.byref(cfg), int(num_sms), int(bool(save_for_backward)), a.shape[0], a.shape[2], a.ctypes.data,
+                                                 C.byref(h))
+        g._h = h
+        if rc != 0:
+            raise GgnnError(g.lib.ggnn_prepared_graph_error(g._h).decode())
+        g.V = a.shape[0] * a.shape[2]
+        g.T = int(num_edge_types)
+        return g
+
     def info(self) -> dict:
         V, M, nt, nb, st = C.c_int32(), C.c_int64(), C.c_int32(), C.c_int64(), C.c_int32()
         buf = C.create_string_buffer(512)
@@ -247,6 +264,23 @@ class PropagationEngine:
         if rc != 0:
             raise GgnnError(self.lib.ggnn_prepared_graph_error(g._h).decode())
         g.V = indeg.shape[0]
+        return g
+
+    def prepare_graph_dense(self, adjacency_matrix, save_for_backward: Optional[bool] = None,
+                            reuse: Optional["PreparedGraph"] = None) -> "PreparedGraph":
+        """The HOST half of ``set_graph_dense`` for a 0/1 adjacency ``[b, T, v, v]`` (scan to edge lists + the CSR builder); raises
+        ``GgnnError`` for a weighted matrix, which only ``set_graph_dense`` takes."""
+        a = np.ascontiguousarray(np.asarray(adjacency_matrix, dtype=np.float32))
+        if a.ndim != 4 or a.shape[1] != self.T or a.shape[2] != a.shape[3]:
+            raise GgnnError("adjacency_matrix must be [b, %d, v, v]" % self.T)
+        g = reuse if reuse is not None else PreparedGraph(self.lib)
+        h = C.c_void_p(g._h.value)
+        rc = self.lib.ggnn_prepare_graph_dense(self._h, -1 if save_for_backward is None else int(bool(save_for_backward)), a.shape[0], a.shape[2],
+                                               a.ctypes.data, C.byref(h))
+        g._h = h
+        if rc != 0:
+            raise GgnnError(self.lib.ggnn_prepared_graph_error(g._h).decode())
+        g.V = a.shape[0] * a.shape[2]
         return g
 
     def set_graph_prepared(self, g: "PreparedGraph"):
