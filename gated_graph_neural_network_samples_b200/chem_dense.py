@@ -66,7 +66,12 @@ class DenseGGNNChemModel(ChemModel):
         adj = np.asarray(feed[self.placeholders['adjacency_matrix']], dtype=np.float32)          # [b, e, v, v]
         b, v = adj.shape[0], adj.shape[2]
         self.engine.set_save_for_backward(torch.is_grad_enabled())
-        self.engine.set_graph_dense(adj)
+        prepared = feed.get('_prepared_graph')
+        if prepared is not None and prepared.for_training == torch.is_grad_enabled():
+            self.engine.set_graph_prepared(prepared)     # built by the batch producer thread: only the upload is left
+            self._prepared_pool.append(prepared)
+        else:
+            self.engine.set_graph_dense(adj)
         keep = float(feed.get(self.placeholders['edge_weight_dropout_keep_prob'], 1.0))
         edge_weights = self.weights['edge_weights']
         if keep < 1.0:
@@ -149,4 +154,12 @@ class DenseGGNNChemModel(ChemModel):
             feed['graph_state_keep_prob'] = keep
             feed['edge_weight_dropout_keep_prob'] = keep
             counters[bucket] += 1
+            # as in the sparse plug-in: this generator runs in run_epoch's ThreadedIterator (chem_tensorflow.py:225), so the engine's host
+            # half of the batch (0/1 adjacency -> edge lists -> CSR, tile plan, one pinned image) is built here, next to the packing
+            eng = getattr(self, 'engine', None)
+            if getattr(self, 'prepare_graphs_in_producer', True) and hasattr(eng, 'prepare_graph_dense'):
+                pool = self.__dict__.setdefault('_prepared_pool', [])
+                g = eng.prepare_graph_dense(feed['adjacency_matrix'], save_for_backward=is_training, reuse=pool.pop() if pool else None)
+                g.for_training = bool(is_training)
+                feed['_prepared_graph'] = g
             yield feed

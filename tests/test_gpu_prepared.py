@@ -164,3 +164,70 @@ def test_plugin_epochs_use_prepared_graphs_and_match_the_one_call_path(tmp_path)
     np.random.seed(5); tb = b.run_epoch("train", b.train_data, True)
     assert ta[4] == tb[4] >= 3 and abs(ta[0] - tb[0]) < 1e-3 * max(1.0, abs(ta[0]))
     assert len(a._prepared_pool) >= 1                          # prepared graphs went through hook 2 and back to the pool
+
+
+def test_dense_prepared_equals_direct_and_weighted_matrices_keep_the_matrix_walk():
+    import torch
+    from gated_graph_neural_network_samples_b200 import packing, synthetic
+    from gated_graph_neural_network_samples_b200.engine import GgnnError, PropagationEngine
+    D, T, v = 100, 4, 29
+    db = packing.pack_dense_batch(synthetic.make_molecules(48, seed=6), v, D, T)
+    A = np.asarray(db["adjacency_matrix"], np.float32)
+    b = A.shape[0]
+    h0 = (db["initial_node_representation"] + np.random.default_rng(1).normal(0, 0.1, db["initial_node_representation"].shape)).astype(np.float32)
+    dp = {"num_timesteps": 3, "use_edge_bias": True}
+    dw = O.init_dense_weights({"hidden_size": D}, T, np.random.default_rng(5))
+    params = U.dense_params_as_engine_params(dp, D)
+    w = dict(dw, edge_biases=np.asarray(dw["edge_biases"]).reshape(T, D))
+    ref = O.dense_propagation_loops(h0, A, dw, dp).reshape(b * v, D)
+
+    def run(precision, prepared):
+        eng = PropagationEngine(params, T, precision=precision)
+        eng.set_weights(U.to_cuda_weights([w]))
+        if prepared:
+            g = eng.prepare_graph_dense(A)
+            assert "binary dense adjacency -> CSR" in g.info()["plan"]
+            eng.set_graph_prepared(g)
+        else:
+            eng.set_graph_dense(A)
+        return _forward(eng, h0.reshape(b * v, D)), eng.plan
+
+    for precision in ("fp32", "bf16x3"):
+        (o1, p1), (o2, p2) = run(precision, False), run(precision, True)
+        assert p1 == p2
+        if precision == "fp32":
+            np.testing.assert_array_equal(o1, o2)
+        else:
+            np.testing.assert_allclose(o1, o2, rtol=1e-4, atol=1e-5)
+        assert U.max_rel_err(o2, ref) < 1e-4
+    W = A.copy()
+    W[A > 0] = 0.5                                                  # a weighted adjacency: the CSR shortcut does not apply ...
+    eng = PropagationEngine(params, T, precision="fp32")
+    eng.set_weights(U.to_cuda_weights([w]))
+    with pytest.raises(GgnnError, match="not 0/1"):
+        eng.prepare_graph_dense(W)
+    eng.set_graph_dense(W)                                          # ... the one-call path walks the matrix
+    got = _forward(eng, h0.reshape(b * v, D))
+    assert U.max_rel_err(got, O.dense_propagation_loops(h0, W, dw, dp).reshape(b * v, D)) < 1e-4
+
+
+def test_dense_plugin_epochs_use_prepared_graphs(tmp_path):
+    from gated_graph_neural_network_samples_b200 import synthetic
+    from gated_graph_neural_network_samples_b200.chem_dense import DenseGGNNChemModel
+    mols = synthetic.make_molecules(64, seed=2)
+
+    def model():
+        np.random.seed(0)
+        return DenseGGNNChemModel({"--log_dir": str(tmp_path), "--train_data": mols[:48], "--valid_data": mols[48:],
+                                   "--config": {"hidden_size": 32, "batch_size": 8, "num_timesteps": 2, "learning_rate": 0.01, "num_epochs": 1,
+                                                "random_seed": 3}})
+    a, b = model(), model()
+    b.prepare_graphs_in_producer = False
+    assert all(f.get("_prepared_graph") is not None for f in a.make_minibatch_iterator(a.valid_data, False))
+    assert all("_prepared_graph" not in f for f in b.make_minibatch_iterator(b.valid_data, False))
+    la, lb = a.run_epoch("valid", a.valid_data, False)[0], b.run_epoch("valid", b.valid_data, False)[0]
+    assert abs(la - lb) < 1e-5 * max(1.0, abs(la))
+    np.random.seed(5); ta = a.run_epoch("train", a.train_data, True)
+    np.random.seed(5); tb = b.run_epoch("train", b.train_data, True)
+    assert ta[4] == tb[4] >= 3 and abs(ta[0] - tb[0]) < 1e-3 * max(1.0, abs(ta[0]))
+    assert len(a._prepared_pool) >= 1

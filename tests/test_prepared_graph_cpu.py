@@ -171,3 +171,32 @@ def test_image_is_identical_for_every_host_thread_count(monkeypatch, name, D, pr
         else:
             assert info == ref_info
             assert np.array_equal(img, ref), "image differs at %d host threads (first byte %d)" % (nth, int(np.argmax(img != ref)))
+
+
+def test_dense_adjacency_prepares_like_its_edge_lists(monkeypatch):
+    """ggnn_host_prepare_graph_dense (the host half of ggnn_set_graph_dense for the 0/1 adjacency the reference feeds, dense:30-36): the
+    scan emits, per type, (source, target) pairs in the order (graph, target row, source column) with in-degree = row sums -- exactly
+    NumPy's nonzero order -- and the image is the sparse builder's image of those lists, for every scan thread count."""
+    from gated_graph_neural_network_samples_b200 import packing as P
+    T, v, D = 4, 29, 100
+    mols = synthetic.make_molecules(40, seed=17)
+    db = P.pack_dense_batch(mols, v, D, T)
+    A = np.asarray(db["adjacency_matrix"], np.float32)                      # [b, T, v, v], A[g, t, target, source]
+    b = A.shape[0]
+    lists, indeg = [], np.zeros((b * v, T), np.float32)
+    for t in range(T):
+        g, i, j = np.nonzero(A[:, t])                                       # row-major: graph, target row, source column
+        lists.append(np.stack([g * v + j, g * v + i], 1).astype(np.int32))
+        indeg[:, t] = A[:, t].sum(axis=2).reshape(-1)
+    p = dict(GRU, hidden_size=D, layer_timesteps=[4], residual_connections={})
+    ref = PreparedGraph.host_only(p, T, lists, indeg, precision="bf16x3", save_for_backward=True)
+    for nth in (1, 2, 5):
+        monkeypatch.setenv("GGNN_HOST_THREADS", str(nth))
+        g = PreparedGraph.host_only_dense(p, T, A, precision="bf16x3", save_for_backward=True)
+        assert g.info()["plan"] == ref.info()["plan"] + " [binary dense adjacency -> CSR]"
+        assert g.info()["num_messages"] == int(A.sum()) and g.info()["num_nodes"] == b * v
+        assert np.array_equal(g.image(), ref.image())
+    monkeypatch.delenv("GGNN_HOST_THREADS")
+    W = A.copy(); W[0, 1, 2, 3] = 0.5                                       # a weighted entry: not this path
+    with pytest.raises(GgnnError, match="not 0/1"):
+        PreparedGraph.host_only_dense(p, T, W)
