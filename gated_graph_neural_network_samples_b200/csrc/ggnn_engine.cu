@@ -1053,8 +1053,8 @@ static int build_sparse_image(ggnn_prepared_graph* g, int32_t V, const int32_t* 
     int* vinfo = e->stream ? (int*)(base + e->off_vinfo) : nullptr;
     lap("stage reserve", t_lap);
 
-    // ---- pass 2, per thread over its tile range: exclusive scan of the (target, type) rows -> row_ptr, fill cursors (stored over the
-    // consumed counts), the tiles' edge-type masks and the largest per-tile message count; then the stable fill -- every thread walks the
+    // ---- pass 2, per thread over its tile range: exclusive scan of the (target, type) rows -> row_ptr, fill cursors, the tiles'
+    // edge-type masks and the largest per-tile message count; then the stable fill -- every thread walks the
     // lists in the reference's order (type-major, then list order, sparse:124-129) and places the messages of ITS rows, so within a row
     // they stay in message order: this IS NumPy's stable argsort by target, tests pin it bit for bit; then (streaming plan) the gather
     // table and the virtual rows of its range, numbered from the range's offset; then in-degrees / denominators of its nodes.
