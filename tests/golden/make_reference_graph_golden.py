@@ -270,6 +270,15 @@ def main():
         "cudnn_gru": {"hidden_size": 12, "layer_timesteps": [2, 1], "residual_connections": {"1": [0]},
                       "use_edge_bias": True, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "CudnnCompatibleGRUCell",
                       "graph_rnn_activation": "tanh"},
+        # more branch combinations of sparse:75-81,102-112,170-209 (oracle-level pins only; the engine is held to the cases above)
+        "gru_relu_sum_nobias": {"hidden_size": 8, "layer_timesteps": [3], "residual_connections": {}, "use_edge_bias": False,
+                                "use_edge_msg_avg_aggregation": False, "graph_rnn_cell": "gru", "graph_rnn_activation": "relu"},
+        "rnn_tanh_avg_two_residuals": {"hidden_size": 8, "layer_timesteps": [1, 1, 2], "residual_connections": {"2": [0, 1]},
+                                       "use_edge_bias": False, "use_edge_msg_avg_aggregation": True, "graph_rnn_cell": "RNN",
+                                       "graph_rnn_activation": "tanh"},
+        "attention_rnn_sum": {"hidden_size": 8, "layer_timesteps": [2], "residual_connections": {}, "use_edge_bias": False,
+                              "use_edge_msg_avg_aggregation": False, "graph_rnn_cell": "RNN", "graph_rnn_activation": "tanh",
+                              "use_propagation_attention": True},
     }
     for name, cfg in cases.items():
         sparse_case(ref_sparse, ref_utils, name, cfg, mols)

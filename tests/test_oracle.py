@@ -202,7 +202,8 @@ def test_propagation_attention_three_statements_agree():
     np.testing.assert_allclose(att, mean, rtol=1e-6, atol=1e-7)
 
 
-REFGRAPH_SPARSE = ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg", "cudnn_gru"]
+REFGRAPH_SPARSE = ["true_default_shape", "rnn_relu_bias_sum", "attention_bias_avg", "cudnn_gru", "gru_relu_sum_nobias", "rnn_tanh_avg_two_residuals",
+                   "attention_rnn_sum"]
 
 
 def _load_refgraph_sparse(golden_dir, name):
